@@ -1,0 +1,90 @@
+"""CPU: the oracle restatement reproduces the REAL reference's outputs stored in tests/golden/
+(written by oracle/gen_golden.py from /root/reference).  Tokens exact; floats <= 2e-5 abs
+(reference fp32-vs-fp64 drift is ~1.2e-6; 2e-5 leaves room for BLAS thread counts)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rfnet_oracle as O
+from tests import _golden as G
+
+TOL = 2e-5
+
+
+def _close(a, b, tol=TOL):
+    a = torch.as_tensor(np.asarray(a)).double()
+    b = torch.as_tensor(np.asarray(b)).double()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert float((a - b).abs().max()) <= tol, float((a - b).abs().max())
+
+
+@pytest.mark.parametrize("name", G.TINY + G.FULL)
+def test_oracle_matches_reference_fixture(name):
+    torch.set_num_threads(8)
+    cfg, sd, fc, att, labels, masks, top_words, d = G.load_case(name)
+    stride = int(d["stride"])
+    tol = TOL * (10 if "sharp" in name else 1)
+    with torch.no_grad():
+        lp, rp = O.forward_xe(sd, cfg, fc, att, labels)
+        assert lp.shape[1] == int(d["xe_T"])
+        _close(lp[:, :, ::stride], d["xe_lp_strided"], tol)
+        _close(torch.stack([r[:, ::max(1, stride // 8)] for r in rp]), d["reason_pred_strided"], tol)
+        s, sl, la, _ = O.sample(sd, cfg, fc, att, sample_max=1)
+        assert np.array_equal(s.numpy(), d["greedy_seq"])
+        _close(sl, d["greedy_slp"], tol)
+        _close(la[:, :, ::stride], d["greedy_lp_all_strided"], tol)
+        bs, bl, ts, tp, _ = O.sample_beam(sd, cfg, fc, att, beam_size=int(d["beam"]))
+        assert np.array_equal(bs.numpy(), d["beam_seq"])
+        _close(bl, d["beam_lp"], tol)
+        gs, gp = G.top_lists(d)
+        assert [t.shape for t in ts] == [t.shape for t in gs]
+        for a, b, pa, pb in zip(ts, gs, tp, gp):
+            assert torch.equal(a, b)
+            _close(pa, pb, tol)
+        # criteria
+        l1 = O.xe_loss(lp, labels[:, 1:], masks[:, 1:], rp, top_words, 10.0, 0.1)
+        l0 = O.xe_loss(lp, labels[:, 1:], masks[:, 1:], rp, top_words, 10.0, 0.0)
+        assert abs(float(l1) - float(d["xe_loss_ls"])) <= 1e-4 * max(1.0, abs(float(l1)))
+        assert abs(float(l0) - float(d["xe_loss_nols"])) <= 1e-4 * max(1.0, abs(float(l0)))
+        g = torch.Generator().manual_seed(int(d["rl_reward_seed"]))
+        reward = torch.randn(s.shape[0], 1, generator=g).expand(s.shape[0], s.shape[1]).contiguous()
+        r = O.rl_loss(sl, s, reward, la, 0.01, rp, top_words, 10.0)
+        assert abs(float(r) - float(d["rl_loss"])) <= 1e-4 * max(1.0, abs(float(r)))
+
+
+def test_state_dict_has_773_tensors_for_full_model():
+    shapes = O.state_dict_shapes(O.RFNConfig())
+    assert len(shapes) == 773
+    n = sum(int(np.prod(s)) for s in shapes.values())
+    assert n == 489_465_041
+
+
+def test_inverse_cdf_sampler_distribution():
+    g = torch.Generator().manual_seed(3)
+    p = torch.tensor([[0.1, 0.0, 0.6, 0.3]]).expand(20000, 4).contiguous()
+    u = torch.rand(20000, generator=g)
+    tok = O.inverse_cdf_sample(p, u)
+    freq = torch.bincount(tok, minlength=4).double() / 20000
+    assert freq[1] == 0
+    assert float((freq - p[0].double()).abs().max()) < 0.02
+
+
+def test_beam_merge_edge_cases():
+    # t == 1: only beam 0 is live; ties keep (c, q) insertion order
+    L, b = 4, 3
+    seq = torch.zeros(L, b, dtype=torch.int64)
+    lp = torch.zeros(L, b)
+    sm = torch.zeros(b)
+    done = []
+    ys = torch.tensor([[-1.0, -1.0, -2.0]] * 3)
+    ix = torch.tensor([[5, 0, 7]] * 3)
+    src = O.beam_merge(b, 1, L, ys, ix, seq, lp, sm, done)
+    assert src == [0, 0, 0]
+    assert seq[0].tolist() == [5, 0, 7]
+    assert len(done) == 1 and done[0]["seq"].tolist() == [0, 0, 0, 0]
+    # t == 2: beam 1 ended (token 0) and is skipped, its slot is refilled from live beams
+    src = O.beam_merge(b, 2, L, ys, ix, seq, lp, sm, done)
+    assert 1 not in src
+    # all beams ended -> None
+    seq[1] = 0
+    assert O.beam_merge(b, 3, L, ys, ix, seq, lp, sm, done) is None
