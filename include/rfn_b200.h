@@ -1,0 +1,203 @@
+/*
+ * rfn_b200.h -- C ABI of the B200-native RFNet recurrent fusion + decode path.
+ *
+ * The reference (cswhjiang/Recurrent_Fusion_Network) has no FFI: its boundary is the Python
+ * nn.Module surface of misc/RecurrentFusionModel.py reached through models.py:14-38.  This
+ * library sits directly under that surface; recurrent_fusion_network_b200/model.py binds it with
+ * ctypes (INTEGRATION.md shows the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - every pointer named d_* / every `const float*` tensor argument is a DEVICE pointer owned
+ *     by the caller; the library never allocates or frees device memory and keeps no global
+ *     mutable state besides the thread-local error string;
+ *   - `params` is a HOST array of device pointers to the model's fp32 tensors in the reference's
+ *     state_dict registration order (misc/RecurrentFusionModel.py:153-184; 773 entries for the
+ *     five-encoder model), Linear weights (out,in) row-major exactly as torch stores them;
+ *   - every call is asynchronous on `stream` (a cudaStream_t) and returns 0 on success or a
+ *     negative rfn_status; rfn_last_error() gives the message.  No exceptions cross the ABI;
+ *   - row-major contiguous tensors unless a leading dimension is passed.
+ */
+#ifndef RFN_B200_H
+#define RFN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* rfn_stream_t; /* cudaStream_t */
+
+enum rfn_status {
+  RFN_OK = 0,
+  RFN_ERR_INVALID = -1,     /* bad argument (shape, alignment, null pointer) */
+  RFN_ERR_CUDA = -2,        /* a CUDA call / launch failed */
+  RFN_ERR_WORKSPACE = -3,   /* workspace too small */
+  RFN_ERR_UNSUPPORTED = -4  /* configuration outside what the kernels support */
+};
+
+#define RFN_MAX_ENCODERS 8
+#define RFN_MAX_BEAM 8
+
+/* The `opt` fields RecurrentFusionModel reads (misc/RecurrentFusionModel.py:120-151). */
+typedef struct rfn_dims {
+  int32_t J;                              /* number of CNN encoders (feat_array_info entries) */
+  int32_t att_num[RFN_MAX_ENCODERS];      /* N_j */
+  int32_t att_feat_size[RFN_MAX_ENCODERS];/* D_j */
+  int32_t fc_feat_size[RFN_MAX_ENCODERS]; /* F_j */
+  int32_t rnn_size;                       /* R */
+  int32_t att_hid_size;                   /* A */
+  int32_t input_encoding_size;            /* E */
+  int32_t vocab_plus1;                    /* V1 = vocab_size + 1 */
+  int32_t top_words_count;                /* K */
+  int32_t num_review_steps_0;             /* S0: stage-1 fusion steps */
+  int32_t num_review_steps;               /* S1: stage-2 review steps */
+  int32_t seq_length;                     /* L */
+} rfn_dims;
+
+/* ---- library -------------------------------------------------------------------------- */
+const char* rfn_last_error(void);
+int rfn_version(void);
+/* 0 if the current device is sm_100 (B200); RFN_ERR_UNSUPPORTED otherwise. */
+int rfn_check_device(void);
+/* number of entries `params` must hold for these dims (773 for the full model) */
+int rfn_num_params(const rfn_dims* dims);
+/* number of kernels this library has launched in the calling process (bench accounting) */
+uint64_t rfn_launch_count(void);
+/* selects the contraction engine for the large GEMMs: 0 = fp32 SIMT FMA,
+ * 1 = tcgen05 3xTF32 (fp32-equivalent), 2 = tcgen05 bf16.  Small-row problems always use SIMT. */
+int rfn_set_gemm_mode(int mode);
+int rfn_get_gemm_mode(void);
+
+/* ---- operator level (the per-timestep cores' building blocks) --------------------------- */
+
+/* y[M,N] = (accumulate ? y : 0) + sum_i x_i[M,K_i] . W_i[N,K_i]^T + sum_i bias_i[N]
+ * replaces nn.Linear at every call site of the path, e.g. H2h(H) + z2h(z)
+ * (misc/RecurrentFusionModel.py:53), i2h + h2h + z2h (misc/LSTMSoftAttentionCore.py:81).
+ * n_src in 1..3; bias_i may be NULL; K_i % 4 == 0 and 16-byte aligned rows required. */
+int rfn_linear_f32(int n_src, const float* const* x, const int* ldx, const float* const* W,
+                   const int* K, const float* const* bias, float* y, int ldy, int M, int N,
+                   int accumulate, rfn_stream_t stream);
+
+/* Additive soft attention given P = att_2_att_h(A) (misc/AttentionModelCore.py:36-47):
+ *   e[r,n] = w . tanh(P[r/div, n, :] + g[r, :]) + wb ; a = softmax_n(e) ; z[r,:] = sum_n a[r,n] A[r/div,n,:]
+ * A (rowsA,N,D), P (rowsA,N,Ah), g (rows,Ah) = h_2_att_h(h), w (Ah), d_wb device scalar,
+ * z (rows, ldz), alpha (rows,N) optional.  `div` lets `div` consecutive query rows share one
+ * feature row (beam rows of one image); rowsA = ceil(rows/div). */
+int rfn_attention_step_f32(const float* A, const float* P, const float* g, const float* w,
+                           const float* d_wb, float* z, int ldz, float* alpha, int rows, int N,
+                           int D, int Ah, int div, rfn_stream_t stream);
+
+/* Full AttentionModelCore.forward(pre_h, att_seq) (misc/AttentionModelCore.py:31-48) from the six
+ * module tensors.  workspace: rows*N*Ah + rows*Ah floats. */
+int rfn_attention_core_f32(const float* h, const float* A, const float* U_w, const float* U_b,
+                           const float* Wh_w, const float* Wh_b, const float* v_w,
+                           const float* d_v_b, float* z, float* alpha, int rows, int N, int D,
+                           int R, int Ah, void* workspace, size_t workspace_bytes,
+                           rfn_stream_t stream);
+
+/* LSTM update, gate layout [i|f|o|g] along 4R (misc/RecurrentFusionModel.py:55-73):
+ * c' = sig(f) c + sig(i) tanh(g); h' = sig(o) tanh(c').  h_out2 (optional) receives a second
+ * copy of h' with leading dimension ldh2 (the thought-vector slot). */
+int rfn_lstm_cell_f32(const float* G, const float* c_prev, float* h_out, float* c_out,
+                      float* h_out2, int ldh2, int rows, int R, rfn_stream_t stream);
+
+/* lp[r,:] = log_softmax(logits[r,:]) (F.log_softmax, misc/RecurrentFusionModel.py:278). */
+int rfn_log_softmax_f32(const float* logits, int ld_in, float* lp, int ld_out, int rows, int V,
+                        rfn_stream_t stream);
+
+/* ---- path level --------------------------------------------------------------------------- */
+
+/* Bytes of scratch the path-level calls need for `rows` feature rows and `dec_rows` decoder rows
+ * (dec_rows = rows for greedy/sample/teacher forcing, rows*beam for beam search). */
+size_t rfn_workspace_bytes(const rfn_dims* dims, int rows, int dec_rows);
+
+/* scratch for rfn_ensemble_decode_beam */
+size_t rfn_ensemble_workspace_bytes(const rfn_dims* dims, int n_models, int images, int beam);
+
+/* get_init_state + get_thought_vectors (misc/RecurrentFusionModel.py:333-343, :283-331):
+ * fc[j] (rows,F_j), att[j] (rows,N_j,D_j) ->
+ *   TVc (rows,S1,R), state h/c (rows,R) = final stage-2 state,
+ *   TV (J,rows,S0,R) optional, reason_pred (J+1,rows,K) optional.
+ * If fc is NULL the initial states are taken from init_h[j] / init_c[j] (rows,R) instead of
+ * fc2h_j(fc_j) -- the state_list a caller got from get_init_state. */
+int rfn_thought_vectors(const rfn_dims* dims, const float* const* params, const float* const* fc,
+                        const float* const* init_h, const float* const* init_c,
+                        const float* const* att, int rows, float* TVc, float* h_out, float* c_out,
+                        float* TV, float* reason_pred, void* workspace, size_t workspace_bytes,
+                        rfn_stream_t stream);
+
+/* one_time_step (misc/RecurrentFusionModel.py:345-350; misc/LSTMSoftAttentionCore.py:60-102):
+ * xt (rows,E), TVc (rows/div,S1,R), state in/out (rows,R) -> logits (rows,V1) (not log-probs). */
+int rfn_one_time_step(const rfn_dims* dims, const float* const* params, const float* xt,
+                      const float* TVc, int div, const float* h_in, const float* c_in,
+                      float* h_out, float* c_out, float* logits, int rows, void* workspace,
+                      size_t workspace_bytes, rfn_stream_t stream);
+
+/* Teacher-forced decoder (forward's loop, misc/RecurrentFusionModel.py:259-279) for T steps:
+ * seq (rows, ld_seq) int64, feeds columns 0..T-1 -> logprobs (rows,T,V1).  The caller derives T
+ * from the first all-zero column (:274-275). */
+int rfn_decode_teacher_forced(const rfn_dims* dims, const float* const* params, const float* TVc,
+                              const float* h0, const float* c0, const int64_t* seq, int ld_seq,
+                              int T, int rows, float* logprobs, void* workspace,
+                              size_t workspace_bytes, rfn_stream_t stream);
+
+/* Greedy (uniforms == NULL) or multinomial sample() loop (misc/RecurrentFusionModel.py:616-658).
+ * Runs all L+1 steps on the device; outputs are (rows,L) / (rows,L+1,V1) buffers and
+ * d_T (device int32) receives the number of token columns the reference would have produced
+ * (its early `break`, :645); the caller slices [:T] / [:T+1].  lp_all may be NULL.
+ * uniforms (rows,L) in [0,1) drive inverse-CDF sampling of exp(lp/temperature) in index order
+ * (the reference draws on the CPU RNG, :624-631, which cannot be replayed -- SURVEY D8). */
+int rfn_decode_sample(const rfn_dims* dims, const float* const* params, const float* TVc,
+                      const float* h0, const float* c0, int rows, const float* uniforms,
+                      float temperature, int64_t* seq, float* seq_logprobs, float* lp_all,
+                      int32_t* d_T, void* workspace, size_t workspace_bytes, rfn_stream_t stream);
+
+/* Batched sample_beam (misc/RecurrentFusionModel.py:352-543) over `images` images at once,
+ * beam rows expanded on the device (stage 1-2 outputs are shared by an image's beams).
+ *   seq (images,L) int64, seq_logprobs (images,L): best finished beam per image (:529-531);
+ *   done_seq (images,cap,L) int32, done_logps (images,cap,L), done_p (images,cap) and
+ *   n_done (images) list every finished beam sorted by -p (top_seq / top_prob), cap = beam*L. */
+int rfn_decode_beam(const rfn_dims* dims, const float* const* params, const float* TVc,
+                    const float* h0, const float* c0, int images, int beam, int64_t* seq,
+                    float* seq_logprobs, int32_t* done_seq, float* done_logps, float* done_p,
+                    int32_t* n_done, void* workspace, size_t workspace_bytes,
+                    rfn_stream_t stream);
+
+/* Ensemble beam search (eval_utils.py:268-290 logit mean -> log_softmax; :482-658 beam loop) over
+ * n_models weight sets sharing one beam; params_m[m], TVc_m[m], h0_m[m], c0_m[m] per model. */
+int rfn_ensemble_decode_beam(const rfn_dims* dims, int n_models, const float* const* const* params_m,
+                             const float* const* TVc_m, const float* const* h0_m,
+                             const float* const* c0_m, int images, int beam, int64_t* seq,
+                             float* seq_logprobs, int32_t* done_seq, float* done_logps,
+                             float* done_p, int32_t* n_done, void* workspace,
+                             size_t workspace_bytes, rfn_stream_t stream);
+
+/* ReviewNetEnsembleCriterion's sequence term (misc/utils.py:161-184), fused over the vocab:
+ * out[0] = -(1/rows) sum_{b,t} mask[b,t] ((1-eps) lp[b,t,y] + eps/V1 sum_v lp[b,t,v]).
+ * target (rows, ld_t) int64, mask (rows, ld_t) f32; only the first T columns are read. */
+int rfn_xe_loss_f32(const float* logprobs, const int64_t* target, const float* mask, int ld_t,
+                    int rows, int T, int V, float eps, float* out, rfn_stream_t stream);
+
+/* ReviewNetRewardCriterion's sequence + entropy terms, non-PPO (misc/utils.py:50-72):
+ * out[0] = -(1/rows) sum m l R + (entropy_reg/rows) sum_{b,t} m0 sum_v p log p. */
+int rfn_rl_loss_f32(const float* sample_logprobs, const int64_t* seq, const float* reward,
+                    const float* logprobs_all, int ld_lp_rows, int rows, int T, int V,
+                    float entropy_reg, float* out, rfn_stream_t stream);
+
+/* nn.MultiLabelMarginLoss (mean reduction) scaled by `weight`, the discriminative term of both
+ * criteria (misc/utils.py:76-82, :186-190): out[0] (+)= weight * mean_rows(margin loss).
+ * pred (rows,K) f32, target (rows,K) int64, class ids first, -1 terminated. */
+int rfn_multilabel_margin_f32(const float* pred, const int64_t* target, int rows, int K, float weight,
+                              int accumulate, float* out, rfn_stream_t stream);
+
+/* model_ensemble_feat_array_one_step's tail (eval_utils.py:282-288):
+ * lp = log_softmax((((0 + l_0) + l_1) + ...) / n) over n <= 8 logit tensors (rows,V). */
+int rfn_mean_log_softmax_f32(int n, const float* const* logits, int rows, int V, float* mean_scratch,
+                             float* lp, rfn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RFN_B200_H */

@@ -1,0 +1,137 @@
+"""ctypes binding of librfn_b200.so (the C ABI declared in include/rfn_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, this module
+raises.  PyTorch is used only for device memory and streams; every tensor crosses the boundary as a
+raw device pointer."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "librfn_b200.so")
+
+MAX_ENCODERS = 8
+MAX_BEAM = 8
+
+
+class RfnDims(C.Structure):
+    """struct rfn_dims -- the opt fields RecurrentFusionModel reads (misc/RecurrentFusionModel.py:120-151)."""
+    _fields_ = [
+        ("J", C.c_int32),
+        ("att_num", C.c_int32 * MAX_ENCODERS),
+        ("att_feat_size", C.c_int32 * MAX_ENCODERS),
+        ("fc_feat_size", C.c_int32 * MAX_ENCODERS),
+        ("rnn_size", C.c_int32),
+        ("att_hid_size", C.c_int32),
+        ("input_encoding_size", C.c_int32),
+        ("vocab_plus1", C.c_int32),
+        ("top_words_count", C.c_int32),
+        ("num_review_steps_0", C.c_int32),
+        ("num_review_steps", C.c_int32),
+        ("seq_length", C.c_int32),
+    ]
+
+
+_vp = C.c_void_p
+_i = C.c_int
+_f = C.c_float
+_sz = C.c_size_t
+_pp = C.POINTER(C.c_void_p)
+_dims = C.POINTER(RfnDims)
+
+_SIGNATURES = {
+    "rfn_last_error": (C.c_char_p, []),
+    "rfn_version": (_i, []),
+    "rfn_check_device": (_i, []),
+    "rfn_num_params": (_i, [_dims]),
+    "rfn_launch_count": (C.c_uint64, []),
+    "rfn_set_gemm_mode": (_i, [_i]),
+    "rfn_get_gemm_mode": (_i, []),
+    "rfn_linear_f32": (_i, [_i, _pp, C.POINTER(_i), _pp, C.POINTER(_i), _pp, _vp, _i, _i, _i, _i, _vp]),
+    "rfn_attention_step_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
+    "rfn_attention_core_f32": (_i, [_vp] * 10 + [_i] * 5 + [_vp, _sz, _vp]),
+    "rfn_lstm_cell_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "rfn_log_softmax_f32": (_i, [_vp, _i, _vp, _i, _i, _i, _vp]),
+    "rfn_workspace_bytes": (_sz, [_dims, _i, _i]),
+    "rfn_ensemble_workspace_bytes": (_sz, [_dims, _i, _i, _i]),
+    "rfn_thought_vectors": (_i, [_dims, _pp, _pp, _pp, _pp, _pp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "rfn_one_time_step": (_i, [_dims, _pp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
+    "rfn_decode_teacher_forced": (_i, [_dims, _pp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    "rfn_decode_sample": (_i, [_dims, _pp, _vp, _vp, _vp, _i, _vp, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "rfn_decode_beam": (_i, [_dims, _pp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "rfn_ensemble_decode_beam": (_i, [_dims, _i, C.POINTER(_pp), _pp, _pp, _pp, _i, _i, _vp, _vp, _vp, _vp, _vp,
+                                      _vp, _vp, _sz, _vp]),
+    "rfn_xe_loss_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
+    "rfn_multilabel_margin_f32": (_i, [_vp, _vp, _i, _i, _f, _i, _vp, _vp]),
+    "rfn_mean_log_softmax_f32": (_i, [_i, _pp, _i, _i, _vp, _vp, _vp]),
+    "rfn_rl_loss_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
+}
+
+_lib = None
+
+
+class RfnError(RuntimeError):
+    pass
+
+
+def exported_symbols():
+    """Every symbol include/rfn_b200.h declares (the CPU test-suite checks they all resolve)."""
+    return sorted(_SIGNATURES)
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RfnError(
+                f"{LIB_PATH} is missing: build it with `python -m recurrent_fusion_network_b200.build` "
+                "(there is no CPU or PyTorch fallback for this path)")
+        _lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(_lib, name)
+            fn.restype = res
+            fn.argtypes = args
+    return _lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = lib().rfn_last_error().decode("utf-8", "replace")
+        raise RfnError(f"{what or 'librfn_b200'} failed with status {status}: {msg}")
+
+
+def ptr(t) -> int:
+    """Raw device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_cuda, "librfn_b200 takes device tensors only"
+    return t.data_ptr()
+
+
+def ptr_array(tensors):
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = ptr(t)
+    return arr
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def make_dims(encoders, rnn_size, att_hid_size, input_encoding_size, vocab_plus1, top_words_count,
+              num_review_steps_0, num_review_steps, seq_length) -> RfnDims:
+    """encoders: sequence of (att_num, att_feat_size, fc_feat_size)."""
+    if len(encoders) > MAX_ENCODERS:
+        raise RfnError(f"at most {MAX_ENCODERS} encoders are supported")
+    d = RfnDims()
+    d.J = len(encoders)
+    for j, (n, a, f) in enumerate(encoders):
+        d.att_num[j], d.att_feat_size[j], d.fc_feat_size[j] = n, a, f
+    d.rnn_size, d.att_hid_size, d.input_encoding_size = rnn_size, att_hid_size, input_encoding_size
+    d.vocab_plus1, d.top_words_count = vocab_plus1, top_words_count
+    d.num_review_steps_0, d.num_review_steps, d.seq_length = num_review_steps_0, num_review_steps, seq_length
+    return d

@@ -1,0 +1,176 @@
+// Fused additive soft attention step (misc/AttentionModelCore.py:36-47):
+//   e[n] = w . tanh(P[n,:] + g) + wb ;  a = softmax_n(e) ;  z = sum_n a[n] A[n,:]
+// One CTA per (query row, D-slice).  P = att_2_att_h(A) comes from the GEMM engine; the feature map
+// A is streamed exactly once per CTA slice with 128-bit coalesced loads; reductions are
+// warp-shuffle based; no intermediate (rows,N,Ah) tensor is ever written (the reference
+// materialises three).
+#include "rfn_internal.cuh"
+
+namespace rfn {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+constexpr int ATT_THREADS = 256;
+
+__global__ void __launch_bounds__(ATT_THREADS)
+attention_step_kernel(const float* __restrict__ A, const float* __restrict__ P,
+                      const float* __restrict__ g, const float* __restrict__ w,
+                      const float* __restrict__ d_wb, float* __restrict__ z, int ldz,
+                      float* __restrict__ alpha, int N, int D, int Ah, int div) {
+  extern __shared__ __align__(16) float smem[];
+  float* s_g = smem;            // Ah
+  float* s_w = smem + Ah;       // Ah
+  float* s_e = smem + 2 * Ah;   // N
+  __shared__ float s_red[ATT_THREADS / 32];
+  __shared__ float s_bcast;
+
+  const int r = blockIdx.x;
+  const int ra = r / div;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = ATT_THREADS / 32;
+
+  for (int k = tid; k < Ah; k += ATT_THREADS) {
+    s_g[k] = g[(size_t)r * Ah + k];
+    s_w[k] = __ldg(w + k);
+  }
+  __syncthreads();
+  const float wb = __ldg(d_wb);
+
+  // ---- scores: one warp per attention location ---------------------------------------------
+  const float* Pr = P + (size_t)ra * N * Ah;
+  for (int n = warp; n < N; n += NW) {
+    const float* pn = Pr + (size_t)n * Ah;
+    float acc = 0.f;
+    for (int k = lane * 4; k < Ah; k += 128) {
+      const float4 p = *reinterpret_cast<const float4*>(pn + k);
+      const float4 gg = *reinterpret_cast<const float4*>(s_g + k);
+      const float4 ww = *reinterpret_cast<const float4*>(s_w + k);
+      acc = fmaf(ww.x, tanhf(p.x + gg.x), acc);
+      acc = fmaf(ww.y, tanhf(p.y + gg.y), acc);
+      acc = fmaf(ww.z, tanhf(p.z + gg.z), acc);
+      acc = fmaf(ww.w, tanhf(p.w + gg.w), acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) s_e[n] = acc + wb;
+  }
+  __syncthreads();
+
+  // ---- softmax over the N locations (no mask: SURVEY D3) ------------------------------------
+  float m = -INFINITY;
+  for (int n = tid; n < N; n += ATT_THREADS) m = fmaxf(m, s_e[n]);
+  m = warp_max(m);
+  if (lane == 0) s_red[warp] = m;
+  __syncthreads();
+  if (tid == 0) {
+    float v = s_red[0];
+    for (int i = 1; i < NW; ++i) v = fmaxf(v, s_red[i]);
+    s_bcast = v;
+  }
+  __syncthreads();
+  m = s_bcast;
+  float sum = 0.f;
+  for (int n = tid; n < N; n += ATT_THREADS) {
+    const float ex = expf(s_e[n] - m);
+    s_e[n] = ex;
+    sum += ex;
+  }
+  sum = warp_sum(sum);
+  __syncthreads();  // everyone has read s_bcast
+  if (lane == 0) s_red[warp] = sum;
+  __syncthreads();
+  if (tid == 0) {
+    float v = 0.f;
+    for (int i = 0; i < NW; ++i) v += s_red[i];
+    s_bcast = v;
+  }
+  __syncthreads();
+  const float total = s_bcast;
+  for (int n = tid; n < N; n += ATT_THREADS) {
+    const float an = s_e[n] / total;
+    s_e[n] = an;
+    if (alpha && blockIdx.y == 0) alpha[(size_t)r * N + n] = an;
+  }
+  __syncthreads();
+
+  // ---- context: z[d] = sum_n a[n] A[n,d], this CTA's slice of D ------------------------------
+  const int nvec = D >> 2;
+  const int per = (nvec + gridDim.y - 1) / gridDim.y;
+  const int v0 = blockIdx.y * per;
+  const int v1 = min(nvec, v0 + per);
+  const float4* Ar = reinterpret_cast<const float4*>(A + (size_t)ra * N * D);
+  for (int v = v0 + tid; v < v1; v += ATT_THREADS) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int n = 0;
+    for (; n + 4 <= N; n += 4) {
+      const float4 x0 = __ldg(Ar + (size_t)(n + 0) * nvec + v);
+      const float4 x1 = __ldg(Ar + (size_t)(n + 1) * nvec + v);
+      const float4 x2 = __ldg(Ar + (size_t)(n + 2) * nvec + v);
+      const float4 x3 = __ldg(Ar + (size_t)(n + 3) * nvec + v);
+      const float a0 = s_e[n], a1 = s_e[n + 1], a2 = s_e[n + 2], a3 = s_e[n + 3];
+      acc.x = fmaf(a0, x0.x, acc.x); acc.y = fmaf(a0, x0.y, acc.y); acc.z = fmaf(a0, x0.z, acc.z); acc.w = fmaf(a0, x0.w, acc.w);
+      acc.x = fmaf(a1, x1.x, acc.x); acc.y = fmaf(a1, x1.y, acc.y); acc.z = fmaf(a1, x1.z, acc.z); acc.w = fmaf(a1, x1.w, acc.w);
+      acc.x = fmaf(a2, x2.x, acc.x); acc.y = fmaf(a2, x2.y, acc.y); acc.z = fmaf(a2, x2.z, acc.z); acc.w = fmaf(a2, x2.w, acc.w);
+      acc.x = fmaf(a3, x3.x, acc.x); acc.y = fmaf(a3, x3.y, acc.y); acc.z = fmaf(a3, x3.z, acc.z); acc.w = fmaf(a3, x3.w, acc.w);
+    }
+    for (; n < N; ++n) {
+      const float4 x0 = __ldg(Ar + (size_t)n * nvec + v);
+      const float a0 = s_e[n];
+      acc.x = fmaf(a0, x0.x, acc.x); acc.y = fmaf(a0, x0.y, acc.y); acc.z = fmaf(a0, x0.z, acc.z); acc.w = fmaf(a0, x0.w, acc.w);
+    }
+    *reinterpret_cast<float4*>(z + (size_t)r * ldz + v * 4) = acc;
+  }
+}
+
+int attention_step(const float* A, const float* P, const float* g, const float* w, const float* d_wb,
+                   float* z, int ldz, float* alpha, int rows, int N, int D, int Ah, int div,
+                   cudaStream_t st) {
+  RFN_CHECK_ARG(A && P && g && w && d_wb && z, "attention_step: null pointer");
+  RFN_CHECK_ARG(rows >= 0 && N > 0 && div >= 1, "attention_step: bad rows/N/div");
+  RFN_CHECK_ARG(D % 4 == 0 && Ah % 4 == 0 && ldz % 4 == 0, "attention_step: D=%d Ah=%d ldz=%d must be multiples of 4", D, Ah, ldz);
+  if (rows == 0) return RFN_OK;
+  // few rows: split D over several CTAs so the feature map streams from more SMs
+  int dsplit = 1;
+  while (rows * dsplit < 296 && dsplit < 8 && (D / 4) / (dsplit * 2) >= 64) dsplit *= 2;
+  const size_t smem = (size_t)(2 * Ah + N) * sizeof(float);
+  RFN_CHECK_ARG(smem <= 200 * 1024, "attention_step: N=%d Ah=%d exceed shared memory", N, Ah);
+  if (smem > 48 * 1024)
+    RFN_CUDA(cudaFuncSetAttribute(attention_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  attention_step_kernel<<<dim3(rows, dsplit), ATT_THREADS, smem, st>>>(A, P, g, w, d_wb, z, ldz, alpha, N, D, Ah, div);
+  RFN_LAUNCH_CHECK();
+  return RFN_OK;
+}
+
+}  // namespace rfn
+
+extern "C" int rfn_attention_step_f32(const float* A, const float* P, const float* g, const float* w,
+                                      const float* d_wb, float* z, int ldz, float* alpha, int rows,
+                                      int N, int D, int Ah, int div, rfn_stream_t stream) {
+  return rfn::attention_step(A, P, g, w, d_wb, z, ldz, alpha, rows, N, D, Ah, div, (cudaStream_t)stream);
+}
+
+extern "C" int rfn_attention_core_f32(const float* h, const float* A, const float* U_w, const float* U_b,
+                                      const float* Wh_w, const float* Wh_b, const float* v_w,
+                                      const float* d_v_b, float* z, float* alpha, int rows, int N,
+                                      int D, int R, int Ah, void* workspace, size_t workspace_bytes,
+                                      rfn_stream_t stream) {
+  const size_t need = ((size_t)rows * N * Ah + (size_t)rows * Ah) * sizeof(float);
+  if (workspace_bytes < need || !workspace) {
+    rfn::set_error("rfn_attention_core_f32: workspace %zu < %zu bytes", workspace_bytes, need);
+    return RFN_ERR_WORKSPACE;
+  }
+  float* P = (float*)workspace;
+  float* g = P + (size_t)rows * N * Ah;
+  cudaStream_t st = (cudaStream_t)stream;
+  RFN_TRY(rfn::gemm(rfn::gemm1(A, D, U_w, U_b, D, P, Ah, rows * N, Ah), st));
+  RFN_TRY(rfn::gemm(rfn::gemm1(h, R, Wh_w, Wh_b, R, g, Ah, rows, Ah), st));
+  return rfn::attention_step(A, P, g, v_w, d_v_b, z, D, alpha, rows, N, D, Ah, 1, st);
+}

@@ -1,0 +1,113 @@
+// Internal declarations shared by the translation units of librfn_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "rfn_b200.h"
+
+namespace rfn {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int gemm_mode();
+
+#define RFN_CHECK_ARG(cond, ...)              \
+  do {                                        \
+    if (!(cond)) {                            \
+      rfn::set_error(__VA_ARGS__);            \
+      return RFN_ERR_INVALID;                 \
+    }                                         \
+  } while (0)
+
+#define RFN_CUDA(call)                                                              \
+  do {                                                                              \
+    cudaError_t e__ = (call);                                                       \
+    if (e__ != cudaSuccess) {                                                       \
+      rfn::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return RFN_ERR_CUDA;                                                          \
+    }                                                                               \
+  } while (0)
+
+#define RFN_LAUNCH_CHECK()                                                          \
+  do {                                                                              \
+    rfn::count_launch();                                                            \
+    cudaError_t e__ = cudaGetLastError();                                           \
+    if (e__ != cudaSuccess) {                                                       \
+      rfn::set_error("%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      return RFN_ERR_CUDA;                                                          \
+    }                                                                               \
+  } while (0)
+
+#define RFN_TRY(call)            \
+  do {                           \
+    int s__ = (call);            \
+    if (s__ != RFN_OK) return s__; \
+  } while (0)
+
+// ---- GEMM (y = sum_i x_i W_i^T + bias) -------------------------------------------------------
+struct GemmSrc {
+  const float* x;
+  const float* w;
+  const float* bias;
+  int ldx;
+  int ldw;
+  int K;
+};
+struct GemmArgs {
+  GemmSrc src[3];
+  int nsrc;
+  float* y;
+  int ldy;
+  int M;
+  int N;
+  int accumulate;
+};
+int gemm_simt(const GemmArgs& a, cudaStream_t st);
+// dispatches on rfn_set_gemm_mode() and problem shape
+int gemm(const GemmArgs& a, cudaStream_t st);
+inline GemmArgs gemm1(const float* x, int ldx, const float* w, const float* bias, int K, float* y,
+                      int ldy, int M, int N) {
+  GemmArgs a{};
+  a.src[0] = GemmSrc{x, w, bias, ldx, K, K};
+  a.nsrc = 1;
+  a.y = y;
+  a.ldy = ldy;
+  a.M = M;
+  a.N = N;
+  a.accumulate = 0;
+  return a;
+}
+
+// ---- attention / pointwise --------------------------------------------------------------------
+int attention_step(const float* A, const float* P, const float* g, const float* w, const float* d_wb,
+                   float* z, int ldz, float* alpha, int rows, int N, int D, int Ah, int div,
+                   cudaStream_t st);
+int lstm_cell(const float* G, const float* c_prev, float* h_out, float* c_out, float* h_out2,
+              int ldh2, float* h_out3, int ldh3, int rows, int R, cudaStream_t st);
+int embed_gather_i64(const int64_t* tok, int ld_tok, const float* embed, float* x, int rows, int E,
+                     int V1, cudaStream_t st);
+int embed_gather_i32(const int32_t* tok, const float* embed, float* x, int rows, int E, int V1,
+                     cudaStream_t st);
+// dst[r,:] = src[idx ? idx[r] : r / div, :]
+int gather_rows(const float* src, const int32_t* idx, int div, float* dst, int rows, int R,
+                cudaStream_t st);
+// out = (((0 + in_0) + in_1) + ...) / n  over n tensors spaced by `stride` floats
+int mean_tensors(const float* in, size_t stride, int n, float* out, int ld_out, size_t count, int R,
+                 int ld_in, cudaStream_t st);
+// out[r,k] = max_s in[r,s,k]
+int max_over_steps(const float* in, float* out, int rows, int S, int K, cudaStream_t st);
+
+// ---- vocab-side kernels -----------------------------------------------------------------------
+// per row: max, log(sum exp(x-max)), and the top-k log-probs (ties -> lower index)
+int vocab_stats_topk(const float* logits, int ld, int rows, int V, int k, float* rowmax,
+                     float* logsum, float* top_val, int32_t* top_idx, cudaStream_t st);
+int vocab_write_lp(const float* logits, int ld, const float* rowmax, const float* logsum, float* lp,
+                   size_t ld_out, int rows, int V, cudaStream_t st);
+// logits_out = (((0 + l_0) + l_1) ...) / n   (eval_utils.py:282-287)
+struct PtrList8 {
+  const float* p[8];
+};
+int mean_logits8(const PtrList8& ptrs, int n, float* out, size_t count, cudaStream_t st);
+
+}  // namespace rfn

@@ -1,0 +1,472 @@
+// Path-level host orchestration: stage 1 (fusion), stage 2 (review), decoder loops (teacher forced,
+// greedy / multinomial, batched beam, ensemble beam).  Pure launch sequencing on one stream: no
+// host<->device synchronisation, no allocation; everything lives in the caller's workspace.
+#include <algorithm>
+
+#include "rfn_internal.cuh"
+#include "rfn_vocab.cuh"
+
+namespace rfn {
+
+// ---- parameter indexing: the reference's state_dict registration order ---------------------------
+// (misc/RecurrentFusionModel.py:153-184)
+struct PIdx {
+  int J, S0, S1;
+  explicit PIdx(const rfn_dims& d) : J(d.J), S0(d.num_review_steps_0), S1(d.num_review_steps) {}
+  int fc2h(int j, int o) const { return 2 * j + o; }
+  int embed() const { return 2 * J; }
+  int logit(int o) const { return 2 * J + 1 + o; }
+  // o: 0 att_2_att_h.w 1 .b 2 h_2_att_h.w 3 .b 4 att_h_2_out.w 5 .b 6 H2h.w 7 .b 8 z2h.w 9 .b
+  int s1(int s, int j, int o) const { return 2 * J + 3 + (s * J + j) * 10 + o; }
+  int reason_ind(int j, int o) const { return 2 * J + 3 + 10 * S0 * J + 2 * j + o; }
+  int s2base(int s) const { return 2 * J + 3 + 10 * S0 * J + 2 * J + s * (2 + 8 * J); }
+  int s2_h2h(int s, int o) const { return s2base(s) + o; }
+  int s2_z2h(int s, int j, int o) const { return s2base(s) + 2 + 2 * j + o; }
+  int s2_att(int s, int j, int o) const { return s2base(s) + 2 + 2 * J + 6 * j + o; }
+  int reason(int o) const { return s2base(S1) + o; }
+  // o: 0 i2h.w 1 .b 2 h2h.w 3 .b 4 z2h.w 5 .b 6 att_2_att_h.w 7 .b 8 h_2_att_h.w 9 .b 10 att_h_2_out.w 11 .b
+  int dec(int o) const { return s2base(S1) + 2 + o; }
+};
+
+// ---- bump allocator over the caller's workspace (dry run computes the requirement) ---------------
+struct Bump {
+  char* base;
+  size_t off = 0;
+  explicit Bump(void* b) : base((char*)b) {}
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    T* p = base ? (T*)(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+static int check_dims(const rfn_dims* d) {
+  RFN_CHECK_ARG(d != nullptr, "dims is null");
+  RFN_CHECK_ARG(d->J >= 1 && d->J <= RFN_MAX_ENCODERS, "J=%d not in 1..%d", d->J, RFN_MAX_ENCODERS);
+  RFN_CHECK_ARG(d->rnn_size % 4 == 0 && d->att_hid_size % 4 == 0 && d->input_encoding_size % 4 == 0,
+                "rnn_size/att_hid_size/input_encoding_size must be multiples of 4");
+  for (int j = 0; j < d->J; ++j)
+    RFN_CHECK_ARG(d->att_feat_size[j] % 4 == 0 && d->fc_feat_size[j] % 4 == 0 && d->att_num[j] >= 1,
+                  "encoder %d: feature sizes must be multiples of 4", j);
+  RFN_CHECK_ARG(d->num_review_steps_0 >= 1 && d->num_review_steps >= 1 && d->seq_length >= 1 && d->seq_length <= 64,
+                "review steps >= 1 and 1 <= seq_length <= 64 required");
+  RFN_CHECK_ARG(d->vocab_plus1 >= 2 && d->top_words_count >= 1, "bad vocab / top_words_count");
+  return RFN_OK;
+}
+
+// ---- stages 1 + 2 ----------------------------------------------------------------------------------
+struct TVWork {
+  float *Hcat[2], *C, *g, *P, *z, *G, *TV, *hx, *rs;
+};
+static size_t carve_tv(const rfn_dims& d, int rows, bool need_tv, bool need_reason, Bump& b, TVWork& w) {
+  const int J = d.J, R = d.rnn_size, A = d.att_hid_size, S0 = d.num_review_steps_0, S1 = d.num_review_steps;
+  int Nmax = S0, Dmax = J * R;
+  for (int j = 0; j < J; ++j) { Nmax = std::max(Nmax, d.att_num[j]); Dmax = std::max(Dmax, d.att_feat_size[j]); }
+  w.Hcat[0] = b.take<float>((size_t)rows * J * R);
+  w.Hcat[1] = b.take<float>((size_t)rows * J * R);
+  w.C = b.take<float>((size_t)rows * J * R);
+  w.g = b.take<float>((size_t)rows * A);
+  w.P = b.take<float>((size_t)rows * Nmax * A);
+  w.z = b.take<float>((size_t)rows * Dmax);
+  w.G = b.take<float>((size_t)rows * 4 * R);
+  w.hx = b.take<float>((size_t)rows * R);
+  w.TV = need_tv ? b.take<float>((size_t)J * rows * S0 * R) : nullptr;
+  w.rs = need_reason ? b.take<float>((size_t)rows * std::max(S0, S1) * d.top_words_count) : nullptr;
+  return b.off;
+}
+
+static int thought_vectors(const rfn_dims& d, const float* const* prm, const float* const* fc,
+                           const float* const* init_h, const float* const* init_c, const float* const* att, int rows, float* TVc, float* h_out, float* c_out, float* TV_user,
+                           float* reason_pred, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int J = d.J, R = d.rnn_size, A = d.att_hid_size, S0 = d.num_review_steps_0, S1 = d.num_review_steps;
+  const int K = d.top_words_count;
+  const PIdx ix(d);
+  Bump b(ws);
+  TVWork w;
+  const size_t need = carve_tv(d, rows, TV_user == nullptr, reason_pred != nullptr, b, w);
+  if (need > ws_bytes) {
+    set_error("rfn_thought_vectors: workspace %zu < %zu bytes", ws_bytes, need);
+    return RFN_ERR_WORKSPACE;
+  }
+  float* TV = TV_user ? TV_user : w.TV;
+  const size_t tv_stride = (size_t)rows * S0 * R;
+
+  // A.0  h_j^0 = c_j^0 = fc2h_j(fc_j)                      (misc/RecurrentFusionModel.py:202-208)
+  for (int j = 0; j < J; ++j) {
+    float* cj = w.C + (size_t)j * rows * R;
+    const float* hj = cj;
+    if (fc) {
+      RFN_TRY(gemm(gemm1(fc[j], d.fc_feat_size[j], prm[ix.fc2h(j, 0)], prm[ix.fc2h(j, 1)], d.fc_feat_size[j], cj, R, rows, R), st));
+    } else {
+      RFN_CUDA(cudaMemcpyAsync(cj, init_c[j], (size_t)rows * R * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      hj = init_h[j];
+    }
+    RFN_CUDA(cudaMemcpy2DAsync(w.Hcat[0] + (size_t)j * R, (size_t)J * R * sizeof(float), hj, (size_t)R * sizeof(float),
+                               (size_t)R * sizeof(float), rows, cudaMemcpyDeviceToDevice, st));
+  }
+  // A.3  stage 1: S0 fusion steps, distinct weights per (s, j); Jacobi update over encoders
+  for (int s = 0; s < S0; ++s) {
+    const float* Hin = w.Hcat[s & 1];
+    float* Hout = w.Hcat[(s + 1) & 1];
+    for (int j = 0; j < J; ++j) {
+      const int N = d.att_num[j], D = d.att_feat_size[j];
+      float* cj = w.C + (size_t)j * rows * R;
+      // g = h_2_att_h(h_j)                                  (misc/AttentionModelCore.py:36)
+      RFN_TRY(gemm(gemm1(Hin + (size_t)j * R, J * R, prm[ix.s1(s, j, 2)], prm[ix.s1(s, j, 3)], R, w.g, A, rows, A), st));
+      // P = att_2_att_h(A_j)                                (:32-34)  -- the 89%-of-FLOPs contraction
+      RFN_TRY(gemm(gemm1(att[j], D, prm[ix.s1(s, j, 0)], prm[ix.s1(s, j, 1)], D, w.P, A, rows * N, A), st));
+      RFN_TRY(attention_step(att[j], w.P, w.g, prm[ix.s1(s, j, 4)], prm[ix.s1(s, j, 5)], w.z, D, nullptr, rows, N, D, A, 1, st));
+      // G = H2h(H) + z2h(z)                                 (misc/RecurrentFusionModel.py:53)
+      GemmArgs ga{};
+      ga.src[0] = GemmSrc{Hin, prm[ix.s1(s, j, 6)], prm[ix.s1(s, j, 7)], J * R, J * R, J * R};
+      ga.src[1] = GemmSrc{w.z, prm[ix.s1(s, j, 8)], prm[ix.s1(s, j, 9)], D, D, D};
+      ga.nsrc = 2; ga.y = w.G; ga.ldy = 4 * R; ga.M = rows; ga.N = 4 * R;
+      RFN_TRY(gemm(ga, st));
+      RFN_TRY(lstm_cell(w.G, cj, nullptr, cj, Hout + (size_t)j * R, J * R, TV + j * tv_stride + (size_t)s * R, S0 * R, rows, R, st));
+    }
+  }
+  const float* Hfin = w.Hcat[S0 & 1];
+  if (reason_pred) {
+    for (int j = 0; j < J; ++j) {  // reason_pred_j = max_s reason_linear_individual_j(h_j^s)   (:291,:303)
+      RFN_TRY(gemm(gemm1(TV + j * tv_stride, R, prm[ix.reason_ind(j, 0)], prm[ix.reason_ind(j, 1)], R, w.rs, K, rows * S0, K), st));
+      RFN_TRY(max_over_steps(w.rs, reason_pred + (size_t)j * rows * K, rows, S0, K, st));
+    }
+  }
+  // A.4  bridge: mean over encoders of (h, c)               (:307-309)
+  float* hb[2] = {h_out, w.hx};
+  float* h0 = hb[S1 & 1];
+  RFN_TRY(mean_tensors(Hfin, (size_t)R, J, h0, R, (size_t)rows * R, R, J * R, st));
+  RFN_TRY(mean_tensors(w.C, (size_t)rows * R, J, c_out, R, (size_t)rows * R, R, R, st));
+  // A.5  stage 2: S1 review steps over the J thought-vector sets
+  float* zs = w.z;  // J x (rows, R)
+  for (int s = 0; s < S1; ++s) {
+    const float* hin = hb[(S1 + s) & 1];
+    float* hout = hb[(S1 + s + 1) & 1];
+    for (int j = 0; j < J; ++j) {
+      RFN_TRY(gemm(gemm1(hin, R, prm[ix.s2_att(s, j, 2)], prm[ix.s2_att(s, j, 3)], R, w.g, A, rows, A), st));
+      RFN_TRY(gemm(gemm1(TV + j * tv_stride, R, prm[ix.s2_att(s, j, 0)], prm[ix.s2_att(s, j, 1)], R, w.P, A, rows * S0, A), st));
+      RFN_TRY(attention_step(TV + j * tv_stride, w.P, w.g, prm[ix.s2_att(s, j, 4)], prm[ix.s2_att(s, j, 5)],
+                             zs + (size_t)j * rows * R, R, nullptr, rows, S0, R, A, 1, st));
+    }
+    // G = h2h(h) + sum_j z_2_h[j](z_j)       (misc/LSTMSoftMultiAttentionFeatArrayNoInputCore.py:50-52)
+    int jn = 0;
+    bool first = true;
+    while (first || jn < J) {
+      GemmArgs ga{};
+      int n = 0;
+      if (first) ga.src[n++] = GemmSrc{hin, prm[ix.s2_h2h(s, 0)], prm[ix.s2_h2h(s, 1)], R, R, R};
+      while (n < 3 && jn < J) {
+        ga.src[n++] = GemmSrc{zs + (size_t)jn * rows * R, prm[ix.s2_z2h(s, jn, 0)], prm[ix.s2_z2h(s, jn, 1)], R, R, R};
+        ++jn;
+      }
+      ga.nsrc = n; ga.y = w.G; ga.ldy = 4 * R; ga.M = rows; ga.N = 4 * R; ga.accumulate = first ? 0 : 1;
+      RFN_TRY(gemm(ga, st));
+      first = false;
+    }
+    RFN_TRY(lstm_cell(w.G, c_out, hout, c_out, TVc + (size_t)s * R, S1 * R, nullptr, 0, rows, R, st));
+  }
+  if (reason_pred) {
+    RFN_TRY(gemm(gemm1(TVc, R, prm[ix.reason(0)], prm[ix.reason(1)], R, w.rs, K, rows * S1, K), st));
+    RFN_TRY(max_over_steps(w.rs, reason_pred + (size_t)J * rows * K, rows, S1, K, st));
+  }
+  return RFN_OK;
+}
+
+// ---- decoder ---------------------------------------------------------------------------------------
+struct DecWork {
+  float *Pdec, *hA, *hB, *cA, *cB, *x, *g, *z, *G, *logits, *rowmax, *logsum, *top_val;
+  int32_t *top_idx, *tok, *src, *any;
+  uint8_t* unfinished;
+  BeamState bs;
+};
+static size_t carve_dec(const rfn_dims& d, int rowsA, int rows, int beam, int n_logit_bufs, Bump& b, DecWork& w) {
+  const int R = d.rnn_size, A = d.att_hid_size, E = d.input_encoding_size, S1 = d.num_review_steps, V = d.vocab_plus1;
+  const int L = d.seq_length;
+  w.Pdec = b.take<float>((size_t)rowsA * S1 * A);
+  w.hA = b.take<float>((size_t)rows * R);
+  w.hB = b.take<float>((size_t)rows * R);
+  w.cA = b.take<float>((size_t)rows * R);
+  w.cB = b.take<float>((size_t)rows * R);
+  w.x = b.take<float>((size_t)rows * E);
+  w.g = b.take<float>((size_t)rows * A);
+  w.z = b.take<float>((size_t)rows * R);
+  w.G = b.take<float>((size_t)rows * 4 * R);
+  w.logits = b.take<float>((size_t)rows * V * n_logit_bufs);
+  w.rowmax = b.take<float>(rows);
+  w.logsum = b.take<float>(rows);
+  const int k = std::max(1, beam);
+  w.top_val = b.take<float>((size_t)rows * k);
+  w.top_idx = b.take<int32_t>((size_t)rows * k);
+  w.tok = b.take<int32_t>(rows);
+  w.src = b.take<int32_t>(rows);
+  w.any = b.take<int32_t>(L + 2);
+  w.unfinished = b.take<uint8_t>(rows);
+  if (beam > 0) {
+    const int images = rowsA;
+    const size_t cap = (size_t)beam * L;
+    w.bs.images = images; w.bs.beam = beam; w.bs.L = L;
+    w.bs.beam_seq = b.take<int32_t>((size_t)2 * images * beam * L);
+    w.bs.beam_lp = b.take<float>((size_t)2 * images * beam * L);
+    w.bs.beam_sum = b.take<float>((size_t)images * beam);
+    w.bs.finished = b.take<uint8_t>(images);
+    w.bs.done_seq = b.take<int32_t>((size_t)images * cap * L);
+    w.bs.done_lp = b.take<float>((size_t)images * cap * L);
+    w.bs.done_p = b.take<float>((size_t)images * cap);
+    w.bs.n_done = b.take<int32_t>(images);
+  }
+  return b.off;
+}
+
+// hoisted loop invariant: P_dec = att_2_att_h(TVc)   (the reference recomputes it every step,
+// misc/LSTMSoftAttentionCore.py:64-66)
+static int decoder_prepare(const rfn_dims& d, const float* const* prm, const float* TVc, int rowsA, float* Pdec, cudaStream_t st) {
+  const PIdx ix(d);
+  const int R = d.rnn_size, A = d.att_hid_size, S1 = d.num_review_steps;
+  return gemm(gemm1(TVc, R, prm[ix.dec(6)], prm[ix.dec(7)], R, Pdec, A, rowsA * S1, A), st);
+}
+
+// one LSTMSoftAttentionCore step + vocab projection  (misc/LSTMSoftAttentionCore.py:60-102, logit :349)
+static int decoder_step(const rfn_dims& d, const float* const* prm, const float* TVc, const float* Pdec, int div,
+                        const float* x, const float* hin, const float* cin, float* hout, float* cout, float* logits,
+                        DecWork& w, int rows, cudaStream_t st) {
+  const PIdx ix(d);
+  const int R = d.rnn_size, A = d.att_hid_size, E = d.input_encoding_size, S1 = d.num_review_steps, V = d.vocab_plus1;
+  RFN_TRY(gemm(gemm1(hin, R, prm[ix.dec(8)], prm[ix.dec(9)], R, w.g, A, rows, A), st));
+  RFN_TRY(attention_step(TVc, Pdec, w.g, prm[ix.dec(10)], prm[ix.dec(11)], w.z, R, nullptr, rows, S1, R, A, div, st));
+  GemmArgs ga{};
+  ga.src[0] = GemmSrc{x, prm[ix.dec(0)], prm[ix.dec(1)], E, E, E};
+  ga.src[1] = GemmSrc{hin, prm[ix.dec(2)], prm[ix.dec(3)], R, R, R};
+  ga.src[2] = GemmSrc{w.z, prm[ix.dec(4)], prm[ix.dec(5)], R, R, R};
+  ga.nsrc = 3; ga.y = w.G; ga.ldy = 4 * R; ga.M = rows; ga.N = 4 * R;
+  RFN_TRY(gemm(ga, st));
+  RFN_TRY(lstm_cell(w.G, cin, hout, cout, nullptr, 0, nullptr, 0, rows, R, st));
+  if (logits) RFN_TRY(gemm(gemm1(hout, R, prm[ix.logit(0)], prm[ix.logit(1)], R, logits, V, rows, V), st));
+  return RFN_OK;
+}
+
+static int ws_fail(const char* who, size_t have, size_t need) {
+  set_error("%s: workspace %zu < %zu bytes", who, have, need);
+  return RFN_ERR_WORKSPACE;
+}
+
+}  // namespace rfn
+
+using namespace rfn;
+
+extern "C" {
+
+size_t rfn_workspace_bytes(const rfn_dims* dims, int rows, int dec_rows) {
+  if (check_dims(dims) != RFN_OK || rows < 0 || dec_rows < 0) return 0;
+  Bump b1(nullptr);
+  TVWork tw;
+  const size_t a = carve_tv(*dims, rows, true, true, b1, tw);
+  const int beam = rows > 0 ? std::max(1, (dec_rows + rows - 1) / rows) : 1;
+  Bump b2(nullptr);
+  DecWork dw;
+  const size_t c = carve_dec(*dims, rows, dec_rows, std::min(beam, RFN_MAX_BEAM), 1, b2, dw);
+  return std::max(a, c) + 1024;
+}
+
+size_t rfn_ensemble_workspace_bytes(const rfn_dims* dims, int n_models, int images, int beam) {
+  if (check_dims(dims) != RFN_OK || n_models < 1 || images < 0 || beam < 1 || beam > RFN_MAX_BEAM) return 0;
+  Bump b(nullptr);
+  DecWork dw;
+  carve_dec(*dims, images, images * beam, beam, n_models + 1, b, dw);
+  const int R = dims->rnn_size, A = dims->att_hid_size, S1 = dims->num_review_steps;
+  const size_t rows = (size_t)images * beam;
+  const size_t per_model = (4 * rows * R + (size_t)images * S1 * A) * sizeof(float) + 5 * 256;
+  return b.off + per_model * n_models + 1024;
+}
+
+int rfn_thought_vectors(const rfn_dims* dims, const float* const* params, const float* const* fc,
+                        const float* const* init_h, const float* const* init_c, const float* const* att, int rows, float* TVc, float* h_out, float* c_out, float* TV, float* reason_pred, void* workspace,
+                        size_t workspace_bytes, rfn_stream_t stream) {
+  RFN_TRY(check_dims(dims));
+  RFN_CHECK_ARG(params && att && TVc && h_out && c_out && workspace, "rfn_thought_vectors: null pointer");
+  RFN_CHECK_ARG(fc || (init_h && init_c), "rfn_thought_vectors: need fc or init_h/init_c");
+  RFN_CHECK_ARG(rows >= 1, "rfn_thought_vectors: rows=%d", rows);
+  for (int j = 0; j < dims->J; ++j)
+    RFN_CHECK_ARG(att[j] && (fc ? fc[j] != nullptr : (init_h[j] && init_c[j])), "rfn_thought_vectors: null feature pointer %d", j);
+  return thought_vectors(*dims, params, fc, init_h, init_c, att, rows, TVc, h_out, c_out, TV, reason_pred, workspace, workspace_bytes,
+                         (cudaStream_t)stream);
+}
+
+int rfn_one_time_step(const rfn_dims* dims, const float* const* params, const float* xt, const float* TVc, int div,
+                      const float* h_in, const float* c_in, float* h_out, float* c_out, float* logits, int rows,
+                      void* workspace, size_t workspace_bytes, rfn_stream_t stream) {
+  RFN_TRY(check_dims(dims));
+  RFN_CHECK_ARG(params && xt && TVc && h_in && c_in && h_out && c_out && logits && workspace, "rfn_one_time_step: null pointer");
+  RFN_CHECK_ARG(rows >= 1 && div >= 1 && h_in != h_out, "rfn_one_time_step: rows/div invalid or h_in aliases h_out");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rowsA = (rows + div - 1) / div;
+  Bump b(workspace);
+  DecWork w{};
+  w.Pdec = b.take<float>((size_t)rowsA * dims->num_review_steps * dims->att_hid_size);
+  w.g = b.take<float>((size_t)rows * dims->att_hid_size);
+  w.z = b.take<float>((size_t)rows * dims->rnn_size);
+  w.G = b.take<float>((size_t)rows * 4 * dims->rnn_size);
+  if (b.off > workspace_bytes) return ws_fail("rfn_one_time_step", workspace_bytes, b.off);
+  RFN_TRY(decoder_prepare(*dims, params, TVc, rowsA, w.Pdec, st));
+  return decoder_step(*dims, params, TVc, w.Pdec, div, xt, h_in, c_in, h_out, c_out, logits, w, rows, st);
+}
+
+int rfn_decode_teacher_forced(const rfn_dims* dims, const float* const* params, const float* TVc, const float* h0,
+                              const float* c0, const int64_t* seq, int ld_seq, int T, int rows, float* logprobs,
+                              void* workspace, size_t workspace_bytes, rfn_stream_t stream) {
+  RFN_TRY(check_dims(dims));
+  RFN_CHECK_ARG(params && TVc && h0 && c0 && seq && logprobs && workspace, "rfn_decode_teacher_forced: null pointer");
+  RFN_CHECK_ARG(rows >= 1 && T >= 1 && T <= ld_seq, "rfn_decode_teacher_forced: rows=%d T=%d ld_seq=%d", rows, T, ld_seq);
+  cudaStream_t st = (cudaStream_t)stream;
+  const rfn_dims& d = *dims;
+  const PIdx ix(d);
+  const int R = d.rnn_size, V = d.vocab_plus1, E = d.input_encoding_size;
+  Bump b(workspace);
+  DecWork w{};
+  if (carve_dec(d, rows, rows, 0, 1, b, w) > workspace_bytes) return ws_fail("rfn_decode_teacher_forced", workspace_bytes, b.off);
+  RFN_TRY(decoder_prepare(d, params, TVc, rows, w.Pdec, st));
+  RFN_CUDA(cudaMemcpyAsync(w.hA, h0, (size_t)rows * R * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  RFN_CUDA(cudaMemcpyAsync(w.cA, c0, (size_t)rows * R * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  float* hb[2] = {w.hA, w.hB};
+  for (int t = 0; t < T; ++t) {
+    RFN_TRY(embed_gather_i64(seq + t, ld_seq, params[ix.embed()], w.x, rows, E, V, st));          // :276
+    RFN_TRY(decoder_step(d, params, TVc, w.Pdec, 1, w.x, hb[t & 1], w.cA, hb[(t + 1) & 1], w.cA, w.logits, w, rows, st));
+    RFN_TRY(log_softmax_rows(w.logits, V, logprobs + (size_t)t * V, T * V, rows, V, st));        // :278
+  }
+  return RFN_OK;
+}
+
+int rfn_decode_sample(const rfn_dims* dims, const float* const* params, const float* TVc, const float* h0,
+                      const float* c0, int rows, const float* uniforms, float temperature, int64_t* seq,
+                      float* seq_logprobs, float* lp_all, int32_t* d_T, void* workspace, size_t workspace_bytes,
+                      rfn_stream_t stream) {
+  RFN_TRY(check_dims(dims));
+  RFN_CHECK_ARG(params && TVc && h0 && c0 && seq && seq_logprobs && d_T && workspace, "rfn_decode_sample: null pointer");
+  RFN_CHECK_ARG(rows >= 1 && temperature > 0.f, "rfn_decode_sample: rows=%d temperature=%f", rows, temperature);
+  cudaStream_t st = (cudaStream_t)stream;
+  const rfn_dims& d = *dims;
+  const PIdx ix(d);
+  const int R = d.rnn_size, V = d.vocab_plus1, E = d.input_encoding_size, L = d.seq_length;
+  Bump b(workspace);
+  DecWork w{};
+  if (carve_dec(d, rows, rows, 0, 1, b, w) > workspace_bytes) return ws_fail("rfn_decode_sample", workspace_bytes, b.off);
+  RFN_TRY(decoder_prepare(d, params, TVc, rows, w.Pdec, st));
+  RFN_CUDA(cudaMemcpyAsync(w.hA, h0, (size_t)rows * R * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  RFN_CUDA(cudaMemcpyAsync(w.cA, c0, (size_t)rows * R * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  RFN_CUDA(cudaMemsetAsync(w.tok, 0, (size_t)rows * sizeof(int32_t), st));                       // t == 0: BOS (:617-618)
+  RFN_CUDA(cudaMemsetAsync(w.any, 0, (size_t)(L + 2) * sizeof(int32_t), st));
+  RFN_CUDA(cudaMemsetAsync(w.unfinished, 0, (size_t)rows, st));
+  float* hb[2] = {w.hA, w.hB};
+  for (int t = 0; t <= L; ++t) {
+    if (t >= 1)
+      RFN_TRY(sample_select(w.logits, V, V, w.rowmax, w.logsum, w.top_val, w.top_idx, uniforms, L, temperature, t, L,
+                            w.tok, w.unfinished, w.any, seq, seq_logprobs, rows, st));
+    RFN_TRY(embed_gather_i32(w.tok, params[ix.embed()], w.x, rows, E, V, st));                   // :637
+    RFN_TRY(decoder_step(d, params, TVc, w.Pdec, 1, w.x, hb[t & 1], w.cA, hb[(t + 1) & 1], w.cA, w.logits, w, rows, st));
+    RFN_TRY(vocab_stats_topk(w.logits, V, rows, V, 1, w.rowmax, w.logsum, w.top_val, w.top_idx, st));
+    if (lp_all) RFN_TRY(vocab_write_lp(w.logits, V, w.rowmax, w.logsum, lp_all + (size_t)t * V, (size_t)(L + 1) * V, rows, V, st));
+  }
+  return sample_finalize(w.any, L, d_T, st);
+}
+
+static int beam_init(DecWork& w, int images, int beam, int L, cudaStream_t st) {
+  const size_t rows = (size_t)images * beam;
+  RFN_CUDA(cudaMemsetAsync(w.bs.beam_seq, 0, 2 * rows * L * sizeof(int32_t), st));
+  RFN_CUDA(cudaMemsetAsync(w.bs.beam_lp, 0, 2 * rows * L * sizeof(float), st));
+  RFN_CUDA(cudaMemsetAsync(w.bs.beam_sum, 0, rows * sizeof(float), st));
+  RFN_CUDA(cudaMemsetAsync(w.bs.finished, 0, (size_t)images, st));
+  RFN_CUDA(cudaMemsetAsync(w.bs.n_done, 0, (size_t)images * sizeof(int32_t), st));
+  RFN_CUDA(cudaMemsetAsync(w.tok, 0, rows * sizeof(int32_t), st));
+  return RFN_OK;
+}
+
+int rfn_decode_beam(const rfn_dims* dims, const float* const* params, const float* TVc, const float* h0, const float* c0,
+                    int images, int beam, int64_t* seq, float* seq_logprobs, int32_t* done_seq, float* done_logps,
+                    float* done_p, int32_t* n_done, void* workspace, size_t workspace_bytes, rfn_stream_t stream) {
+  RFN_TRY(check_dims(dims));
+  RFN_CHECK_ARG(params && TVc && h0 && c0 && seq && seq_logprobs && workspace, "rfn_decode_beam: null pointer");
+  RFN_CHECK_ARG(images >= 1 && beam >= 1 && beam <= RFN_MAX_BEAM && beam <= dims->vocab_plus1,
+                "rfn_decode_beam: images=%d beam=%d (max %d)", images, beam, RFN_MAX_BEAM);
+  cudaStream_t st = (cudaStream_t)stream;
+  const rfn_dims& d = *dims;
+  const PIdx ix(d);
+  const int R = d.rnn_size, V = d.vocab_plus1, E = d.input_encoding_size, L = d.seq_length;
+  const int rows = images * beam;
+  Bump b(workspace);
+  DecWork w{};
+  if (carve_dec(d, images, rows, beam, 1, b, w) > workspace_bytes) return ws_fail("rfn_decode_beam", workspace_bytes, b.off);
+  RFN_TRY(decoder_prepare(d, params, TVc, images, w.Pdec, st));
+  RFN_TRY(beam_init(w, images, beam, L, st));
+  // expand each image's stage-2 state to `beam` identical rows (:376-394)
+  RFN_TRY(gather_rows(h0, nullptr, beam, w.hB, rows, R, st));
+  RFN_TRY(gather_rows(c0, nullptr, beam, w.cB, rows, R, st));
+  for (int t = 0; t <= L; ++t) {
+    if (t >= 1) {
+      RFN_TRY(beam_merge(w.bs, t, w.top_val, w.top_idx, w.src, w.tok, st));                      // :465-514
+      if (t == L) break;  // the reference runs one more, unused, decoder step (:526)
+      RFN_TRY(gather_rows(w.hA, w.src, 1, w.hB, rows, R, st));                                   // :499-501
+      RFN_TRY(gather_rows(w.cA, w.src, 1, w.cB, rows, R, st));
+    }
+    RFN_TRY(embed_gather_i32(w.tok, params[ix.embed()], w.x, rows, E, V, st));                   // :517-521
+    RFN_TRY(decoder_step(d, params, TVc, w.Pdec, beam, w.x, w.hB, w.cB, w.hA, w.cA, w.logits, w, rows, st));
+    RFN_TRY(vocab_stats_topk(w.logits, V, rows, V, beam, w.rowmax, w.logsum, w.top_val, w.top_idx, st));  // :463, :527
+  }
+  return beam_finalize(w.bs, seq, seq_logprobs, done_seq, done_logps, done_p, n_done, st);
+}
+
+int rfn_ensemble_decode_beam(const rfn_dims* dims, int n_models, const float* const* const* params_m,
+                             const float* const* TVc_m, const float* const* h0_m, const float* const* c0_m, int images,
+                             int beam, int64_t* seq, float* seq_logprobs, int32_t* done_seq, float* done_logps,
+                             float* done_p, int32_t* n_done, void* workspace, size_t workspace_bytes,
+                             rfn_stream_t stream) {
+  RFN_TRY(check_dims(dims));
+  RFN_CHECK_ARG(params_m && TVc_m && h0_m && c0_m && seq && seq_logprobs && workspace, "rfn_ensemble_decode_beam: null pointer");
+  RFN_CHECK_ARG(n_models >= 1 && n_models <= 8, "rfn_ensemble_decode_beam: n_models=%d not in 1..8", n_models);
+  RFN_CHECK_ARG(images >= 1 && beam >= 1 && beam <= RFN_MAX_BEAM, "rfn_ensemble_decode_beam: images=%d beam=%d", images, beam);
+  cudaStream_t st = (cudaStream_t)stream;
+  const rfn_dims& d = *dims;
+  const PIdx ix(d);
+  const int R = d.rnn_size, V = d.vocab_plus1, E = d.input_encoding_size, L = d.seq_length, A = d.att_hid_size;
+  const int S1 = d.num_review_steps;
+  const int rows = images * beam;
+  Bump b(workspace);
+  DecWork w{};
+  carve_dec(d, images, rows, beam, n_models + 1, b, w);
+  float *hA[8], *hB[8], *cA[8], *cB[8], *Pd[8];
+  for (int m = 0; m < n_models; ++m) {
+    hA[m] = b.take<float>((size_t)rows * R); hB[m] = b.take<float>((size_t)rows * R);
+    cA[m] = b.take<float>((size_t)rows * R); cB[m] = b.take<float>((size_t)rows * R);
+    Pd[m] = b.take<float>((size_t)images * S1 * A);
+  }
+  if (b.off > workspace_bytes) return ws_fail("rfn_ensemble_decode_beam", workspace_bytes, b.off);
+  float* mean = w.logits + (size_t)n_models * rows * V;
+  RFN_TRY(beam_init(w, images, beam, L, st));
+  for (int m = 0; m < n_models; ++m) {
+    RFN_TRY(decoder_prepare(d, params_m[m], TVc_m[m], images, Pd[m], st));
+    RFN_TRY(gather_rows(h0_m[m], nullptr, beam, hB[m], rows, R, st));
+    RFN_TRY(gather_rows(c0_m[m], nullptr, beam, cB[m], rows, R, st));
+  }
+  PtrList8 pl{};
+  for (int m = 0; m < n_models; ++m) pl.p[m] = w.logits + (size_t)m * rows * V;
+  for (int t = 0; t <= L; ++t) {
+    if (t >= 1) {
+      RFN_TRY(beam_merge(w.bs, t, w.top_val, w.top_idx, w.src, w.tok, st));
+      if (t == L) break;
+      for (int m = 0; m < n_models; ++m) {  // every model's state is forked with the same q (eval_utils.py:604-611)
+        RFN_TRY(gather_rows(hA[m], w.src, 1, hB[m], rows, R, st));
+        RFN_TRY(gather_rows(cA[m], w.src, 1, cB[m], rows, R, st));
+      }
+    }
+    for (int m = 0; m < n_models; ++m) {
+      RFN_TRY(embed_gather_i32(w.tok, params_m[m][ix.embed()], w.x, rows, E, V, st));
+      RFN_TRY(decoder_step(d, params_m[m], TVc_m[m], Pd[m], beam, w.x, hB[m], cB[m], hA[m], cA[m],
+                           w.logits + (size_t)m * rows * V, w, rows, st));
+    }
+    RFN_TRY(mean_logits8(pl, n_models, mean, (size_t)rows * V, st));                            // eval_utils.py:282-287
+    RFN_TRY(vocab_stats_topk(mean, V, rows, V, beam, w.rowmax, w.logsum, w.top_val, w.top_idx, st));
+  }
+  return beam_finalize(w.bs, seq, seq_logprobs, done_seq, done_logps, done_p, n_done, st);
+}
+
+}  // extern "C"
