@@ -70,6 +70,14 @@ uint64_t rfn_launch_count(void);
 int rfn_set_gemm_mode(int mode);
 int rfn_get_gemm_mode(void);
 
+/* Optional per-kernel-class timing: when enabled every launch is bracketed by CUDA events on its
+ * stream; rfn_profile_read() synchronises them and returns summed milliseconds and launch counts
+ * per class (rfn_profile_num_tags() classes, named by rfn_profile_tag_name()), then clears. */
+int rfn_profile_enable(int on);
+int rfn_profile_num_tags(void);
+const char* rfn_profile_tag_name(int tag);
+int rfn_profile_read(float* ms, uint64_t* launches, int n);
+
 /* ---- operator level (the per-timestep cores' building blocks) --------------------------- */
 
 /* y[M,N] = (accumulate ? y : 0) + sum_i x_i[M,K_i] . W_i[N,K_i]^T + sum_i bias_i[N]

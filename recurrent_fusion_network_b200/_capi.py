@@ -50,6 +50,10 @@ _SIGNATURES = {
     "rfn_launch_count": (C.c_uint64, []),
     "rfn_set_gemm_mode": (_i, [_i]),
     "rfn_get_gemm_mode": (_i, []),
+    "rfn_profile_enable": (_i, [_i]),
+    "rfn_profile_num_tags": (_i, []),
+    "rfn_profile_tag_name": (C.c_char_p, [_i]),
+    "rfn_profile_read": (_i, [C.POINTER(C.c_float), C.POINTER(C.c_uint64), _i]),
     "rfn_linear_f32": (_i, [_i, _pp, C.POINTER(_i), _pp, C.POINTER(_i), _pp, _vp, _i, _i, _i, _i, _vp]),
     "rfn_attention_step_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
     "rfn_attention_core_f32": (_i, [_vp] * 10 + [_i] * 5 + [_vp, _sz, _vp]),
@@ -135,3 +139,16 @@ def make_dims(encoders, rnn_size, att_hid_size, input_encoding_size, vocab_plus1
     d.vocab_plus1, d.top_words_count = vocab_plus1, top_words_count
     d.num_review_steps_0, d.num_review_steps, d.seq_length = num_review_steps_0, num_review_steps, seq_length
     return d
+
+
+def profile_enable(on: bool) -> None:
+    check(lib().rfn_profile_enable(1 if on else 0))
+
+
+def profile_read():
+    """-> {class name: (milliseconds, launches)} accumulated since the last read."""
+    n = lib().rfn_profile_num_tags()
+    ms = (C.c_float * n)()
+    cnt = (C.c_uint64 * n)()
+    check(lib().rfn_profile_read(ms, cnt, n), "rfn_profile_read")
+    return {lib().rfn_profile_tag_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}

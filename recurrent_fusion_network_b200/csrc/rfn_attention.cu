@@ -133,6 +133,7 @@ attention_step_kernel(const float* __restrict__ A, const float* __restrict__ P,
 int attention_step(const float* A, const float* P, const float* g, const float* w, const float* d_wb,
                    float* z, int ldz, float* alpha, int rows, int N, int D, int Ah, int div,
                    cudaStream_t st) {
+  ProfScope prof__(TAG_ATTN_SMALL, st);
   RFN_CHECK_ARG(A && P && g && w && d_wb && z, "attention_step: null pointer");
   RFN_CHECK_ARG(rows >= 0 && N > 0 && div >= 1, "attention_step: bad rows/N/div");
   RFN_CHECK_ARG(D % 4 == 0 && Ah % 4 == 0 && ldz % 4 == 0, "attention_step: D=%d Ah=%d ldz=%d must be multiples of 4", D, Ah, ldz);

@@ -1,6 +1,8 @@
 // Library-level entry points: error string, version, device check, launch accounting.
 #include <stdarg.h>
 #include <atomic>
+#include <mutex>
+#include <vector>
 
 #include "rfn_internal.cuh"
 
@@ -17,6 +19,40 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 int gemm_mode() { return g_gemm_mode.load(std::memory_order_relaxed); }
+
+// ---- optional per-kernel-class timing with CUDA events on the launching stream -------------------
+static std::atomic<int> g_prof_on{0};
+static thread_local int g_tag_override = -1;
+struct ProfRec { int tag; cudaEvent_t e0, e1; };
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof_recs;
+static std::vector<cudaEvent_t> g_prof_pool;
+
+static cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+bool prof_enabled() { return g_prof_on.load(std::memory_order_relaxed) != 0; }
+TagScope::TagScope(int tag) : prev(g_tag_override) { g_tag_override = tag; }
+TagScope::~TagScope() { g_tag_override = prev; }
+ProfScope::ProfScope(int default_tag, cudaStream_t st) : st_(st), idx_(-1) {
+  if (!prof_enabled()) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r;
+  r.tag = g_tag_override >= 0 ? g_tag_override : default_tag;
+  r.e0 = prof_event();
+  r.e1 = prof_event();
+  cudaEventRecord(r.e0, st);
+  g_prof_recs.push_back(r);
+  idx_ = (int)g_prof_recs.size() - 1;
+}
+ProfScope::~ProfScope() {
+  if (idx_ < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEventRecord(g_prof_recs[idx_].e1, st_);
+}
 }  // namespace rfn
 
 extern "C" {
@@ -44,6 +80,34 @@ int rfn_set_gemm_mode(int mode) {
   return RFN_OK;
 }
 int rfn_get_gemm_mode(void) { return rfn::gemm_mode(); }
+
+int rfn_profile_enable(int on) {
+  rfn::g_prof_on.store(on ? 1 : 0);
+  return RFN_OK;
+}
+int rfn_profile_num_tags(void) { return rfn::TAG_COUNT; }
+const char* rfn_profile_tag_name(int tag) {
+  static const char* names[rfn::TAG_COUNT] = {"misc", "gemm_att2att_stage1", "attention_step_stage1", "gemm_gates",
+                                              "gemm_logit", "gemm_other", "attention_step_small", "lstm_cell",
+                                              "vocab_stats_select", "beam_merge"};
+  return (tag >= 0 && tag < rfn::TAG_COUNT) ? names[tag] : "?";
+}
+int rfn_profile_read(float* ms, uint64_t* launches, int n) {
+  RFN_CHECK_ARG(ms && launches && n >= rfn::TAG_COUNT, "rfn_profile_read: need %d slots", rfn::TAG_COUNT);
+  for (int i = 0; i < n; ++i) { ms[i] = 0.f; launches[i] = 0; }
+  std::lock_guard<std::mutex> lk(rfn::g_prof_mu);
+  for (auto& r : rfn::g_prof_recs) {
+    RFN_CUDA(cudaEventSynchronize(r.e1));
+    float t = 0.f;
+    RFN_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+    ms[r.tag] += t;
+    launches[r.tag] += 1;
+    rfn::g_prof_pool.push_back(r.e0);
+    rfn::g_prof_pool.push_back(r.e1);
+  }
+  rfn::g_prof_recs.clear();
+  return RFN_OK;
+}
 
 int rfn_num_params(const rfn_dims* d) {
   if (!d) return RFN_ERR_INVALID;

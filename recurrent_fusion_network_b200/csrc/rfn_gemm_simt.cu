@@ -123,6 +123,7 @@ gemm_tn_simt_kernel(GemmArgs a) {
 }
 
 int gemm_simt(const GemmArgs& a, cudaStream_t st) {
+  ProfScope prof__(TAG_GEMM_OTHER, st);
   RFN_CHECK_ARG(a.nsrc >= 1 && a.nsrc <= 3, "gemm: n_src %d not in 1..3", a.nsrc);
   RFN_CHECK_ARG(a.M >= 0 && a.N > 0 && a.y != nullptr, "gemm: bad M/N/y");
   if (a.M == 0) return RFN_OK;

@@ -116,14 +116,23 @@ static int thought_vectors(const rfn_dims& d, const float* const* prm, const flo
       // g = h_2_att_h(h_j)                                  (misc/AttentionModelCore.py:36)
       RFN_TRY(gemm(gemm1(Hin + (size_t)j * R, J * R, prm[ix.s1(s, j, 2)], prm[ix.s1(s, j, 3)], R, w.g, A, rows, A), st));
       // P = att_2_att_h(A_j)                                (:32-34)  -- the 89%-of-FLOPs contraction
-      RFN_TRY(gemm(gemm1(att[j], D, prm[ix.s1(s, j, 0)], prm[ix.s1(s, j, 1)], D, w.P, A, rows * N, A), st));
-      RFN_TRY(attention_step(att[j], w.P, w.g, prm[ix.s1(s, j, 4)], prm[ix.s1(s, j, 5)], w.z, D, nullptr, rows, N, D, A, 1, st));
+      {
+        TagScope ts(TAG_GEMM_ATT2ATT);
+        RFN_TRY(gemm(gemm1(att[j], D, prm[ix.s1(s, j, 0)], prm[ix.s1(s, j, 1)], D, w.P, A, rows * N, A), st));
+      }
+      {
+        TagScope ts(TAG_ATTN_S1);
+        RFN_TRY(attention_step(att[j], w.P, w.g, prm[ix.s1(s, j, 4)], prm[ix.s1(s, j, 5)], w.z, D, nullptr, rows, N, D, A, 1, st));
+      }
       // G = H2h(H) + z2h(z)                                 (misc/RecurrentFusionModel.py:53)
       GemmArgs ga{};
       ga.src[0] = GemmSrc{Hin, prm[ix.s1(s, j, 6)], prm[ix.s1(s, j, 7)], J * R, J * R, J * R};
       ga.src[1] = GemmSrc{w.z, prm[ix.s1(s, j, 8)], prm[ix.s1(s, j, 9)], D, D, D};
       ga.nsrc = 2; ga.y = w.G; ga.ldy = 4 * R; ga.M = rows; ga.N = 4 * R;
-      RFN_TRY(gemm(ga, st));
+      {
+        TagScope ts(TAG_GEMM_GATES);
+        RFN_TRY(gemm(ga, st));
+      }
       RFN_TRY(lstm_cell(w.G, cj, nullptr, cj, Hout + (size_t)j * R, J * R, TV + j * tv_stride + (size_t)s * R, S0 * R, rows, R, st));
     }
   }
@@ -162,7 +171,10 @@ static int thought_vectors(const rfn_dims& d, const float* const* prm, const flo
         ++jn;
       }
       ga.nsrc = n; ga.y = w.G; ga.ldy = 4 * R; ga.M = rows; ga.N = 4 * R; ga.accumulate = first ? 0 : 1;
-      RFN_TRY(gemm(ga, st));
+      {
+        TagScope ts(TAG_GEMM_GATES);
+        RFN_TRY(gemm(ga, st));
+      }
       first = false;
     }
     RFN_TRY(lstm_cell(w.G, c_out, hout, c_out, TVc + (size_t)s * R, S1 * R, nullptr, 0, rows, R, st));
@@ -240,9 +252,15 @@ static int decoder_step(const rfn_dims& d, const float* const* prm, const float*
   ga.src[1] = GemmSrc{hin, prm[ix.dec(2)], prm[ix.dec(3)], R, R, R};
   ga.src[2] = GemmSrc{w.z, prm[ix.dec(4)], prm[ix.dec(5)], R, R, R};
   ga.nsrc = 3; ga.y = w.G; ga.ldy = 4 * R; ga.M = rows; ga.N = 4 * R;
-  RFN_TRY(gemm(ga, st));
+  {
+    TagScope ts(TAG_GEMM_GATES);
+    RFN_TRY(gemm(ga, st));
+  }
   RFN_TRY(lstm_cell(w.G, cin, hout, cout, nullptr, 0, nullptr, 0, rows, R, st));
-  if (logits) RFN_TRY(gemm(gemm1(hout, R, prm[ix.logit(0)], prm[ix.logit(1)], R, logits, V, rows, V), st));
+  if (logits) {
+    TagScope ts(TAG_GEMM_LOGIT);
+    RFN_TRY(gemm(gemm1(hout, R, prm[ix.logit(0)], prm[ix.logit(1)], R, logits, V, rows, V), st));
+  }
   return RFN_OK;
 }
 

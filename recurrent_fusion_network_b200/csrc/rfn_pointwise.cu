@@ -31,6 +31,7 @@ __global__ void lstm_cell_kernel(const float* __restrict__ G, const float* c_pre
 
 int lstm_cell(const float* G, const float* c_prev, float* h_out, float* c_out, float* h_out2, int ldh2,
               float* h_out3, int ldh3, int rows, int R, cudaStream_t st) {
+  ProfScope prof__(TAG_CELL, st);
   RFN_CHECK_ARG(G && c_prev && c_out, "lstm_cell: null pointer");
   if (rows == 0) return RFN_OK;
   const size_t total = (size_t)rows * R;
@@ -54,6 +55,7 @@ __global__ void embed_gather_kernel(const TokT* __restrict__ tok, int ld_tok, co
 
 int embed_gather_i64(const int64_t* tok, int ld_tok, const float* embed, float* x, int rows, int E, int V1,
                      cudaStream_t st) {
+  ProfScope prof__(TAG_MISC, st);
   if (rows == 0) return RFN_OK;
   const size_t total = (size_t)rows * E;
   const int blocks = (int)min((size_t)148 * 8, (total + 255) / 256);
@@ -62,6 +64,7 @@ int embed_gather_i64(const int64_t* tok, int ld_tok, const float* embed, float* 
   return RFN_OK;
 }
 int embed_gather_i32(const int32_t* tok, const float* embed, float* x, int rows, int E, int V1, cudaStream_t st) {
+  ProfScope prof__(TAG_MISC, st);
   if (rows == 0) return RFN_OK;
   const size_t total = (size_t)rows * E;
   const int blocks = (int)min((size_t)148 * 8, (total + 255) / 256);
@@ -80,6 +83,7 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, const int32_t*
   }
 }
 int gather_rows(const float* src, const int32_t* idx, int div, float* dst, int rows, int R, cudaStream_t st) {
+  ProfScope prof__(TAG_MISC, st);
   if (rows == 0) return RFN_OK;
   const size_t total = (size_t)rows * R;
   const int blocks = (int)min((size_t)148 * 8, (total + 255) / 256);
@@ -101,6 +105,7 @@ __global__ void mean_tensors_kernel(const float* __restrict__ in, size_t stride,
 }
 int mean_tensors(const float* in, size_t stride, int n, float* out, int ld_out, size_t count, int R, int ld_in,
                  cudaStream_t st) {
+  ProfScope prof__(TAG_MISC, st);
   if (count == 0) return RFN_OK;
   const int blocks = (int)min((size_t)148 * 8, (count + 255) / 256);
   mean_tensors_kernel<<<blocks, 256, 0, st>>>(in, stride, n, out, ld_out, count, R, ld_in);
@@ -119,6 +124,7 @@ __global__ void max_over_steps_kernel(const float* __restrict__ in, float* __res
   }
 }
 int max_over_steps(const float* in, float* out, int rows, int S, int K, cudaStream_t st) {
+  ProfScope prof__(TAG_MISC, st);
   if (rows == 0) return RFN_OK;
   const size_t total = (size_t)rows * K;
   const int blocks = (int)min((size_t)148 * 8, (total + 255) / 256);
@@ -135,6 +141,7 @@ __global__ void mean_logits_kernel(PtrList8 ptrs, int n, float* __restrict__ out
   }
 }
 int mean_logits8(const PtrList8& ptrs, int n, float* out, size_t count, cudaStream_t st) {
+  ProfScope prof__(TAG_MISC, st);
   if (count == 0) return RFN_OK;
   const int blocks = (int)min((size_t)148 * 16, (count + 255) / 256);
   mean_logits_kernel<<<blocks, 256, 0, st>>>(ptrs, n, out, count);

@@ -111,6 +111,7 @@ vocab_stats_topk_kernel(const float* __restrict__ logits, int ld, int V, int k,
 
 int vocab_stats_topk(const float* logits, int ld, int rows, int V, int k, float* rowmax, float* logsum,
                      float* top_val, int32_t* top_idx, cudaStream_t st) {
+  ProfScope prof__(TAG_VOCAB, st);
   RFN_CHECK_ARG(logits && rowmax && logsum, "vocab_stats_topk: null pointer");
   RFN_CHECK_ARG(k >= 0 && k <= RFN_MAX_BEAM && k <= V, "vocab_stats_topk: k=%d not in 0..%d", k, RFN_MAX_BEAM);
   if (rows == 0) return RFN_OK;
@@ -134,6 +135,7 @@ __global__ void vocab_write_lp_kernel(const float* __restrict__ logits, int ld, 
 }
 int vocab_write_lp(const float* logits, int ld, const float* rowmax, const float* logsum, float* lp, size_t ld_out,
                    int rows, int V, cudaStream_t st) {
+  ProfScope prof__(TAG_VOCAB, st);
   if (rows == 0) return RFN_OK;
   vocab_write_lp_kernel<<<rows, 256, 0, st>>>(logits, ld, rowmax, logsum, lp, ld_out, V);
   RFN_LAUNCH_CHECK();
@@ -179,6 +181,7 @@ log_softmax_rows_kernel(const float* __restrict__ logits, int ld_in, float* __re
   for (int v = tid; v < V; v += VT) o[v] = (x[v] - m) - ls;
 }
 int log_softmax_rows(const float* logits, int ld_in, float* lp, int ld_out, int rows, int V, cudaStream_t st) {
+  ProfScope prof__(TAG_VOCAB, st);
   RFN_CHECK_ARG(logits && lp && V > 0, "log_softmax: bad arguments");
   if (rows == 0) return RFN_OK;
   log_softmax_rows_kernel<<<rows, VT, 0, st>>>(logits, ld_in, lp, ld_out, V);
@@ -266,6 +269,7 @@ int sample_select(const float* logits, int ld, int V, const float* rowmax, const
                   const int32_t* top_idx, const float* uniforms, int ld_u, float temperature, int t, int L,
                   int32_t* tok_next, uint8_t* unfinished, int32_t* any_unfinished, int64_t* seq, float* seq_lp,
                   int rows, cudaStream_t st) {
+  ProfScope prof__(TAG_VOCAB, st);
   if (rows == 0) return RFN_OK;
   sample_select_kernel<<<rows, VT, 0, st>>>(logits, ld, V, rowmax, logsum, top_val, top_idx, uniforms, ld_u,
                                             temperature, t, L, tok_next, unfinished, any_unfinished, seq, seq_lp);
@@ -273,6 +277,7 @@ int sample_select(const float* logits, int ld, int V, const float* rowmax, const
   return RFN_OK;
 }
 int sample_finalize(const int32_t* any_unfinished, int L, int32_t* d_T, cudaStream_t st) {
+  ProfScope prof__(TAG_VOCAB, st);
   sample_finalize_kernel<<<1, 1, 0, st>>>(any_unfinished, L, d_T);
   RFN_LAUNCH_CHECK();
   return RFN_OK;
@@ -392,6 +397,7 @@ __global__ void beam_finalize_kernel(BeamState bs, int64_t* __restrict__ seq, fl
 
 int beam_merge(const BeamState& bs, int t, const float* top_val, const int32_t* top_idx, int32_t* src_row,
                int32_t* next_tok, cudaStream_t st) {
+  ProfScope prof__(TAG_BEAM, st);
   if (bs.images == 0) return RFN_OK;
   beam_merge_kernel<<<(bs.images + 63) / 64, 64, 0, st>>>(bs, t, top_val, top_idx, src_row, next_tok);
   RFN_LAUNCH_CHECK();
@@ -399,6 +405,7 @@ int beam_merge(const BeamState& bs, int t, const float* top_val, const int32_t* 
 }
 int beam_finalize(const BeamState& bs, int64_t* seq, float* seq_lp, int32_t* done_seq, float* done_lp, float* done_p,
                   int32_t* n_done, cudaStream_t st) {
+  ProfScope prof__(TAG_BEAM, st);
   if (bs.images == 0) return RFN_OK;
   beam_finalize_kernel<<<(bs.images + 63) / 64, 64, 0, st>>>(bs, seq, seq_lp, done_seq, done_lp, done_p, n_done);
   RFN_LAUNCH_CHECK();
@@ -436,6 +443,7 @@ xe_loss_kernel(const float* __restrict__ lp, const int64_t* __restrict__ target,
 
 int xe_loss(const float* logprobs, const int64_t* target, const float* mask, int ld_t, int rows, int T, int V,
             float eps, float* out, cudaStream_t st) {
+  ProfScope prof__(TAG_VOCAB, st);
   RFN_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
   if (rows * T == 0) return RFN_OK;
   xe_loss_kernel<<<rows * T, VT, 0, st>>>(logprobs, target, mask, ld_t, T, V, eps, 1.f / (float)rows, out);
@@ -472,6 +480,7 @@ rl_loss_kernel(const float* __restrict__ slp, const int64_t* __restrict__ seq, c
 
 int rl_loss(const float* slp, const int64_t* seq, const float* reward, const float* lp_all, int ld_lp_rows, int rows,
             int T, int V, float entropy_reg, float* out, cudaStream_t st) {
+  ProfScope prof__(TAG_VOCAB, st);
   RFN_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
   if (rows * T == 0) return RFN_OK;
   rl_loss_kernel<<<rows * T, VT, 0, st>>>(slp, seq, reward, lp_all, ld_lp_rows, T, V, entropy_reg, 1.f / (float)rows, out);
@@ -524,6 +533,7 @@ multilabel_margin_kernel(const float* __restrict__ x, const int64_t* __restrict_
 
 int multilabel_margin(const float* pred, const int64_t* target, int rows, int K, float weight, int accumulate,
                       float* out, cudaStream_t st) {
+  ProfScope prof__(TAG_VOCAB, st);
   if (!accumulate) RFN_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
   if (rows == 0) return RFN_OK;
   multilabel_margin_kernel<<<rows, VT, (size_t)K, st>>>(pred, target, K, weight / ((float)K * (float)rows), out);

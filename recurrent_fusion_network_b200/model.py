@@ -296,7 +296,7 @@ class _DoneBeams(Sequence):
     """done_beams[k] -> list of {'seq','logps','p'} sorted by -p (misc/RecurrentFusionModel.py:529)."""
 
     def __init__(self, done_seq, done_lp, done_p, n_done):
-        self._s, self._l, self._p, self._n = done_seq, done_lp, done_p, n_done
+        self._s, self._l, self._p, self._n = done_seq, done_lp, done_p, n_done   # done_lp stays on the device
 
     def __len__(self):
         return len(self._n)
@@ -304,6 +304,8 @@ class _DoneBeams(Sequence):
     def __getitem__(self, k):
         if isinstance(k, slice):
             return [self[i] for i in range(*k.indices(len(self)))]
+        if self._l.is_cuda:
+            self._l = self._l.cpu()   # copied on first access only
         return [{"seq": self._s[k, i], "logps": self._l[k, i], "p": float(self._p[k, i])} for i in range(int(self._n[k]))]
 
 
@@ -394,7 +396,7 @@ class RecurrentFusionModel(nn.Module):
     def _dropout_active(self, p):
         return self.training and p > 0
 
-    def _check_feats(self, fc_feats, att_feats):
+    def _check_feats(self, fc_feats, att_feats, allow_host=False):
         J = self.num_feat_array
         if len(fc_feats) != J or len(att_feats) != J:
             raise _capi.RfnError(f"expected {J} fc / att feature tensors")
@@ -402,7 +404,8 @@ class RecurrentFusionModel(nn.Module):
         att = [_f32c(t) for t in att_feats]
         rows = fc[0].shape[0]
         for j in range(J):
-            _require_cuda(fc[j]); _require_cuda(att[j])
+            if not allow_host:
+                _require_cuda(fc[j]); _require_cuda(att[j])
             if tuple(fc[j].shape) != (rows, self.fc_feat_size[j]) or \
                     tuple(att[j].shape) != (rows, self.att_num[j], self.att_feat_size[j]):
                 raise _capi.RfnError(f"encoder {j}: feature shapes {tuple(fc[j].shape)} / {tuple(att[j].shape)} "
@@ -535,9 +538,70 @@ class RecurrentFusionModel(nn.Module):
                                "(torch.cat of an empty list, misc/RecurrentFusionModel.py:655)")
         return seq[:, :T], slp[:, :T], (lp_all[:, :T + 1] if want_all else None), self._reason_list(reason)
 
+    def _device(self):
+        return next(self.parameters()).device
+
+    def _chunks(self, fc, att, rows, step):
+        """Yields (k0, k1, fc_chunk, att_chunk) with the chunk resident on the device.  Host (pinned)
+        inputs are streamed over PCIe on a side stream, double buffered, so the copy of chunk i+1
+        overlaps the decode of chunk i (dataloader.py hands the reference host arrays, train.py:116-133)."""
+        if fc[0].is_cuda:
+            for k0 in range(0, rows, step):
+                k1 = min(rows, k0 + step)
+                yield k0, k1, [f[k0:k1] for f in fc], [a[k0:k1] for a in att]
+            return
+        dev = self._device()
+        cur = torch.cuda.current_stream(dev)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        cs = self._copy_stream
+        n_buf = min(step, rows)
+        key = (n_buf, dev)
+        if getattr(self, "_staging_key", None) != key:
+            self._staging = [([torch.empty(n_buf, *f.shape[1:], dtype=torch.float32, device=dev) for f in fc],
+                              [torch.empty(n_buf, *a.shape[1:], dtype=torch.float32, device=dev) for a in att])
+                             for _ in range(2)]
+            self._staging_key = key
+        staging = self._staging
+        spans = [(k0, min(rows, k0 + step)) for k0 in range(0, rows, step)]
+        ready, free = [None, None], [None, None]
+
+        def issue(i):
+            k0, k1 = spans[i]
+            b = i % 2
+            with torch.cuda.stream(cs):
+                if free[b] is not None:
+                    cs.wait_event(free[b])
+                else:
+                    cs.wait_stream(cur)
+                for j in range(len(fc)):
+                    staging[b][0][j][:k1 - k0].copy_(fc[j][k0:k1], non_blocking=True)
+                    staging[b][1][j][:k1 - k0].copy_(att[j][k0:k1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+                ready[b] = ev
+
+        issue(0)
+        for i, (k0, k1) in enumerate(spans):
+            if i + 1 < len(spans):
+                issue(i + 1)
+            b = i % 2
+            cur.wait_event(ready[b])
+            yield k0, k1, [t[:k1 - k0] for t in staging[b][0]], [t[:k1 - k0] for t in staging[b][1]]
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            free[b] = ev
+
+    def beam_search(self, fc_feats, att_feats, beam_size=3, want_reason=True):
+        """Batched device beam search returning DEVICE tensors only:
+        (seq (B,L) i64, seqLogprobs (B,L), done_seq (B,beam*L,L) i32, done_logps, done_p (B,beam*L), n_done (B),
+        reason_pred (J+1,B,K) or None).  sample_beam() wraps this into the reference's return structure."""
+        with torch.no_grad():
+            fc, att, rows = self._check_feats(fc_feats, att_feats, allow_host=True)
+            return self._beam_tensors(fc, att, rows, beam_size, want_reason)
+
     def _beam_tensors(self, fc, att, rows, beam_size, want_reason=True):
-        """Batched device beam search; returns device tensors only (no per-image Python objects)."""
-        dev = fc[0].device
+        dev = self._device()
         L, K, J = self.seq_length, self.top_words_count, self.num_feat_array
         cap = beam_size * L
         seq = torch.empty(rows, L, dtype=torch.int64, device=dev)
@@ -548,11 +612,9 @@ class RecurrentFusionModel(nn.Module):
         n_done = torch.zeros(rows, dtype=torch.int32, device=dev)
         reason = torch.empty(J + 1, rows, K, dtype=torch.float32, device=dev) if want_reason else None
         step = max(1, int(self.chunk_images))
-        for k0 in range(0, rows, step):
-            k1 = min(rows, k0 + step)
+        for k0, k1, fck, attk in self._chunks(fc, att, rows, step):
             n = k1 - k0
-            TVc, rsn, h, c = self._thought_vectors([f[k0:k1] for f in fc], [a[k0:k1] for a in att], n,
-                                                   want_reason=want_reason, dec_rows=n * beam_size)
+            TVc, rsn, h, c = self._thought_vectors(fck, attk, n, want_reason=want_reason, dec_rows=n * beam_size)
             if want_reason:
                 reason[:, k0:k1] = rsn
             ws = self._ws(n, n * beam_size, dev)
@@ -569,7 +631,7 @@ class RecurrentFusionModel(nn.Module):
             raise _capi.RfnError(f"beam_size {beam_size} > {_capi.MAX_BEAM} is not built")
         self._inference_guard("sample_beam")
         with torch.no_grad():
-            fc, att, rows = self._check_feats(fc_feats, att_feats)
+            fc, att, rows = self._check_feats(fc_feats, att_feats, allow_host=True)
             seq, slp, done_seq, done_lp, done_p, n_done, reason = self._beam_tensors(fc, att, rows, beam_size)
             # the caption gather: one D2H of the finished-beam lists
             n_cpu = n_done.cpu()
@@ -579,5 +641,5 @@ class RecurrentFusionModel(nn.Module):
             top_seq = [ds_cpu[k, :nl[k]] for k in range(rows)]
             dpl = dp_cpu.tolist()
             top_prob = [dpl[k][:nl[k]] for k in range(rows)]
-            self.done_beams = _DoneBeams(ds_cpu, done_lp.cpu(), dp_cpu, nl)
+            self.done_beams = _DoneBeams(ds_cpu, done_lp, dp_cpu, nl)
             return seq, slp, top_seq, top_prob, _ReasonPredBatch(reason, beam_size)
