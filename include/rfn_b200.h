@@ -88,6 +88,12 @@ int rfn_linear_f32(int n_src, const float* const* x, const int* ldx, const float
                    const int* K, const float* const* bias, float* y, int ldy, int M, int N,
                    int accumulate, rfn_stream_t stream);
 
+/* Same contraction on an explicitly chosen engine (0 = fp32 SIMT, 1 = tcgen05 3xTF32, 2 = tcgen05
+ * single-pass TF32) regardless of the row-count heuristic; used by the engine parity tests. */
+int rfn_linear_f32_engine(int engine, int n_src, const float* const* x, const int* ldx,
+                          const float* const* W, const int* K, const float* const* bias, float* y,
+                          int ldy, int M, int N, int accumulate, rfn_stream_t stream);
+
 /* Additive soft attention given P = att_2_att_h(A) (misc/AttentionModelCore.py:36-47):
  *   e[r,n] = w . tanh(P[r/div, n, :] + g[r, :]) + wb ; a = softmax_n(e) ; z[r,:] = sum_n a[r,n] A[r/div,n,:]
  * A (rowsA,N,D), P (rowsA,N,Ah), g (rows,Ah) = h_2_att_h(h), w (Ah), d_wb device scalar,

@@ -55,6 +55,7 @@ _SIGNATURES = {
     "rfn_profile_tag_name": (C.c_char_p, [_i]),
     "rfn_profile_read": (_i, [C.POINTER(C.c_float), C.POINTER(C.c_uint64), _i]),
     "rfn_linear_f32": (_i, [_i, _pp, C.POINTER(_i), _pp, C.POINTER(_i), _pp, _vp, _i, _i, _i, _i, _vp]),
+    "rfn_linear_f32_engine": (_i, [_i, _i, _pp, C.POINTER(_i), _pp, C.POINTER(_i), _pp, _vp, _i, _i, _i, _i, _vp]),
     "rfn_attention_step_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
     "rfn_attention_core_f32": (_i, [_vp] * 10 + [_i] * 5 + [_vp, _sz, _vp]),
     "rfn_lstm_cell_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
@@ -98,6 +99,9 @@ def lib() -> C.CDLL:
             fn = getattr(_lib, name)
             fn.restype = res
             fn.argtypes = args
+        mode = os.environ.get("RFN_GEMM_MODE")
+        if mode is not None:
+            check(_lib.rfn_set_gemm_mode(int(mode)), "rfn_set_gemm_mode")
     return _lib
 
 

@@ -25,7 +25,8 @@ __global__ void __launch_bounds__(ATT_THREADS)
 attention_step_kernel(const float* __restrict__ A, const float* __restrict__ P,
                       const float* __restrict__ g, const float* __restrict__ w,
                       const float* __restrict__ d_wb, float* __restrict__ z, int ldz,
-                      float* __restrict__ alpha, int N, int D, int Ah, int div) {
+                      float* __restrict__ alpha, int N, int D, int Ah, int div,
+                      const float* __restrict__ scores, int nslices, size_t slice_stride) {
   extern __shared__ __align__(16) float smem[];
   float* s_g = smem;            // Ah
   float* s_w = smem + Ah;       // Ah
@@ -38,16 +39,25 @@ attention_step_kernel(const float* __restrict__ A, const float* __restrict__ P,
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = ATT_THREADS / 32;
 
-  for (int k = tid; k < Ah; k += ATT_THREADS) {
-    s_g[k] = g[(size_t)r * Ah + k];
-    s_w[k] = __ldg(w + k);
-  }
-  __syncthreads();
   const float wb = __ldg(d_wb);
+  if (scores) {
+    // scores were reduced by the tcgen05 GEMM epilogue; only the bias is missing
+    for (int n = tid; n < N; n += ATT_THREADS) {
+      float e = 0.f;
+      for (int sl = 0; sl < nslices; ++sl) e += scores[(size_t)sl * slice_stride + (size_t)r * N + n];  // fixed order
+      s_e[n] = e + wb;
+    }
+  } else {
+    for (int k = tid; k < Ah; k += ATT_THREADS) {
+      s_g[k] = g[(size_t)r * Ah + k];
+      s_w[k] = __ldg(w + k);
+    }
+    __syncthreads();
+  }
 
   // ---- scores: one warp per attention location ---------------------------------------------
   const float* Pr = P + (size_t)ra * N * Ah;
-  for (int n = warp; n < N; n += NW) {
+  for (int n = warp; n < N && !scores; n += NW) {
     const float* pn = Pr + (size_t)n * Ah;
     float acc = 0.f;
     for (int k = lane * 4; k < Ah; k += 128) {
@@ -145,7 +155,25 @@ int attention_step(const float* A, const float* P, const float* g, const float* 
   RFN_CHECK_ARG(smem <= 200 * 1024, "attention_step: N=%d Ah=%d exceed shared memory", N, Ah);
   if (smem > 48 * 1024)
     RFN_CUDA(cudaFuncSetAttribute(attention_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  attention_step_kernel<<<dim3(rows, dsplit), ATT_THREADS, smem, st>>>(A, P, g, w, d_wb, z, ldz, alpha, N, D, Ah, div);
+  attention_step_kernel<<<dim3(rows, dsplit), ATT_THREADS, smem, st>>>(A, P, g, w, d_wb, z, ldz, alpha, N, D, Ah, div, nullptr, 0, 0);
+  RFN_LAUNCH_CHECK();
+  return RFN_OK;
+}
+
+int attention_from_scores(const float* A, const float* scores, int nslices, const float* d_wb, float* z, int ldz,
+                          float* alpha, int rows, int N, int D, int div, cudaStream_t st) {
+  ProfScope prof__(TAG_ATTN_SMALL, st);
+  RFN_CHECK_ARG(A && scores && d_wb && z, "attention_from_scores: null pointer");
+  RFN_CHECK_ARG(rows >= 0 && N > 0 && div >= 1 && D % 4 == 0 && ldz % 4 == 0, "attention_from_scores: bad shape");
+  if (rows == 0) return RFN_OK;
+  int dsplit = 1;
+  while (rows * dsplit < 296 && dsplit < 8 && (D / 4) / (dsplit * 2) >= 64) dsplit *= 2;
+  const size_t smem = (size_t)N * sizeof(float);
+  RFN_CHECK_ARG(smem <= 200 * 1024, "attention_from_scores: N=%d exceeds shared memory", N);
+  if (smem > 48 * 1024)
+    RFN_CUDA(cudaFuncSetAttribute(attention_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  attention_step_kernel<<<dim3(rows, dsplit), ATT_THREADS, smem, st>>>(A, nullptr, nullptr, nullptr, d_wb, z, ldz, alpha, N, D, 0,
+                                                                       div, scores, nslices, (size_t)rows * N);
   RFN_LAUNCH_CHECK();
   return RFN_OK;
 }

@@ -1,12 +1,32 @@
 // GEMM engine selection.  The north star asks for tensor cores "only when batch x beam is large
-// enough to be a real dense contraction; otherwise warp-level FMA": small-M problems always take
-// the SIMT kernel, large-M problems take the engine chosen with rfn_set_gemm_mode().
+// enough to be a real dense contraction; otherwise warp-level FMA": problems with fewer than
+// 128 rows always take the SIMT kernel; larger ones take the engine chosen with
+// rfn_set_gemm_mode() (0 = fp32 SIMT, 1 = tcgen05 3xTF32, 2 = tcgen05 single-pass TF32).
 #include "rfn_internal.cuh"
 
 namespace rfn {
 
+int gemm_engine(const GemmArgs& a, int engine, cudaStream_t st) {
+  if (engine == 0) return gemm_simt(a, st);
+  return gemm_tc(a, engine == 1 ? 3 : 1, nullptr, 0, nullptr, nullptr, 0, st);
+}
+
 int gemm(const GemmArgs& a, cudaStream_t st) {
+  const int mode = gemm_mode();
+  if (mode >= 1 && a.M >= 128 && gemm_tc_supported(a)) return gemm_engine(a, mode, st);
   return gemm_simt(a, st);
 }
 
 }  // namespace rfn
+
+extern "C" int rfn_linear_f32_engine(int engine, int n_src, const float* const* x, const int* ldx, const float* const* W,
+                                     const int* K, const float* const* bias, float* y, int ldy, int M, int N,
+                                     int accumulate, rfn_stream_t stream) {
+  RFN_CHECK_ARG(engine >= 0 && engine <= 2, "rfn_linear_f32_engine: engine %d not in {0,1,2}", engine);
+  RFN_CHECK_ARG(n_src >= 1 && n_src <= 3 && x && ldx && W && K, "rfn_linear_f32_engine: bad source arrays");
+  rfn::GemmArgs a{};
+  a.nsrc = n_src;
+  for (int s = 0; s < n_src; ++s) a.src[s] = rfn::GemmSrc{x[s], W[s], bias ? bias[s] : nullptr, ldx[s], K[s], K[s]};
+  a.y = y; a.ldy = ldy; a.M = M; a.N = N; a.accumulate = accumulate;
+  return rfn::gemm_engine(a, engine, (cudaStream_t)stream);
+}

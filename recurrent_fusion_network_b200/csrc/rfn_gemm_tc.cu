@@ -1,0 +1,458 @@
+// tcgen05 tensor-core GEMM engine for sm_100a:  y[M,N] = sum_i x_i[M,K_i] . W_i[N,K_i]^T + bias.
+//
+// Design (one CTA = one 128 x BN output tile, accumulator in TMEM):
+//   warp 0        TMA producer: cp.async.bulk.tensor loads of raw fp32 tiles (K-major, 128-byte rows,
+//                 SWIZZLE_128B) of x and W into a multi-stage shared-memory ring, mbarrier complete_tx.
+//   warps 4..7    3xTF32 splitter: rewrite every landed tile in place as hi = tf32(x) and write
+//                 lo = x - hi beside it (element-wise, so the hardware swizzle is preserved), then
+//                 fence.proxy.async and hand the stage to the MMA warp.  Afterwards the same warps run
+//                 the epilogue: tcgen05.ld the accumulator out of TMEM, add bias, store -- or the fused
+//                 additive-attention epilogue score[m] += sum_n w[n] tanh(acc + b[n] + g[m/Natt, n])
+//                 so that U_a A never reaches HBM.
+//   warp 1        MMA issuer: one elected lane issues tcgen05.mma.kind::tf32 from shared-memory
+//                 descriptors; per 8-wide K step three MMAs (lo.hi, hi.lo, hi.hi) accumulate the
+//                 fp32-equivalent product; tcgen05.commit releases the stage / publishes the tile.
+//   PASSES == 1   single-pass TF32 (no splitter): the reduced-precision mode.
+// Both operands are K-major so activations (row-major) and nn.Linear weights (out,in) are consumed
+// exactly as torch stores them; ragged M / N / K edges are zero-filled by TMA.
+#include <cuda.h>
+
+#include "rfn_internal.cuh"
+
+namespace rfn {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;                    // fp32 elements per 128-byte swizzled row
+constexpr int TC_A_BYTES = TC_BM * 128;      // 16 KB
+constexpr int TC_THREADS = 320;             // warp 0 TMA, warp 1 MMA, warps 2..9 workers
+
+struct TcArgs {
+  CUtensorMap tm_x[3];
+  CUtensorMap tm_w[3];
+  int K[3];
+  const float* bias[3];
+  int nsrc;
+  float* y;
+  int ldy;
+  int M, N;
+  int accumulate;
+  // fused attention-score epilogue (epi == 1)
+  int epi;
+  const float* g;   // (rows, ldg)   h_2_att_h(h)
+  const float* wv;  // (N)           att_h_2_out.weight
+  float* score;     // (N / (BN/2), M) partial scores, one slice per worker column range
+  int natt;         // attention locations per feature row: g row = m / natt
+  int ldg;
+};
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, TF32 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
+      "%24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B: rows of 128 bytes, 8-row groups 1024 bytes
+// apart (SBO), version 1 (Blackwell), layout type 2.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D fp32, A/B tf32, both K-major, M = 128, N = BN
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int bn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+template <int BN, int PASSES>
+struct TcSmem {
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int TILE_BYTES = TC_A_BYTES + B_BYTES;          // one landed fp32 tile pair
+  static constexpr int STAGE_BYTES = TILE_BYTES * (PASSES == 3 ? 2 : 1);
+};
+
+// The tensor core adds into its fp32 accumulator with truncation (measured on B200: -0.5 ulp per
+// tcgen05.mma, so a K = 2048 chain drifts by 1.5e-5 relative).  The fp32-equivalent mode therefore
+// keeps tensor-core chains short: every CH k-blocks the MMA warp switches to the other of two TMEM
+// accumulators and the worker warps drain the finished one into round-to-nearest fp32 registers.
+template <int BN, int STAGES, int PASSES, int CH>
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcArgs a) {
+  using S = TcSmem<BN, PASSES>;
+  constexpr int NWORK = 8;                       // worker warps 2..9
+  constexpr int COLS = BN / 2;                   // columns per worker thread (two warps share a lane quarter)
+  constexpr bool DRAIN = (PASSES == 3);
+  constexpr int NBUF = DRAIN ? 2 : 1;
+  constexpr int TMEM_COLS = (BN * NBUF <= 128) ? 128 : (BN * NBUF <= 256 ? 256 : 512);
+  static_assert(BN * NBUF <= 512 && COLS % 32 == 0, "accumulators must fit the 512 TMEM columns");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + STAGES * S::STAGE_BYTES);
+  uint64_t* full = bars;                 // TMA landed
+  uint64_t* conv = bars + STAGES;        // hi/lo split done
+  uint64_t* empty = bars + 2 * STAGES;   // MMAs that read the stage retired
+  uint64_t* cfull = bars + 3 * STAGES;   // [2] accumulator chunk complete
+  uint64_t* drained = cfull + 2;         // [2] accumulator buffer drained into registers
+  uint32_t* tmem_slot = (uint32_t*)(drained + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * TC_BM;
+
+  int total_kb = 0;
+  for (int s = 0; s < a.nsrc; ++s) total_kb += (a.K[s] + TC_BK - 1) / TC_BK;
+  const int nchunk = DRAIN ? (total_kb + CH - 1) / CH : 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < a.nsrc; ++s) { tma_prefetch_desc(&a.tm_x[s]); tma_prefetch_desc(&a.tm_w[s]); }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&full[s]), 1);
+      mbar_init(smem_u32(&conv[s]), NWORK);
+      mbar_init(smem_u32(&empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&cfull[b]), 1);
+      mbar_init(smem_u32(&drained[b]), NWORK);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int s = 0; s < a.nsrc; ++s) {
+        const int nkb = (a.K[s] + TC_BK - 1) / TC_BK;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int st = it % STAGES;
+          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          mbar_wait(smem_u32(&empty[st]), ph ^ 1u);
+          const uint32_t fb = smem_u32(&full[st]);
+          mbar_arrive_expect_tx(fb, (uint32_t)S::TILE_BYTES);
+          uint8_t* stage = smem + st * S::STAGE_BYTES;
+          tma_load_2d(&a.tm_x[s], fb, smem_u32(stage), kb * TC_BK, m0);
+          tma_load_2d(&a.tm_w[s], fb, smem_u32(stage + TC_A_BYTES), kb * TC_BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc_tf32(BN);
+    for (int it = 0; it < total_kb; ++it) {
+      const int st = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      const int c = DRAIN ? it / CH : 0;
+      const int b = c & 1;
+      const bool chunk_start = DRAIN ? (it % CH == 0) : (it == 0);
+      if (DRAIN && chunk_start && c >= 2) mbar_wait(smem_u32(&drained[b]), (uint32_t)((c >> 1) - 1) & 1u);
+      mbar_wait(smem_u32(DRAIN ? &conv[st] : &full[st]), ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t td = tmem_base + (uint32_t)(b * BN);
+        const uint32_t sa = smem_u32(smem + st * S::STAGE_BYTES);
+        const uint64_t da_hi = make_desc_sw128(sa);
+        const uint64_t db_hi = make_desc_sw128(sa + TC_A_BYTES);
+        const uint64_t da_lo = make_desc_sw128(sa + S::TILE_BYTES);
+        const uint64_t db_lo = make_desc_sw128(sa + S::TILE_BYTES + TC_A_BYTES);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; ++k) {
+          const uint64_t adv = (uint64_t)(k * 2);  // 8 tf32 = 32 bytes = 2 x 16-byte units inside the swizzle atom
+          const uint32_t acc0 = (chunk_start && k == 0) ? 0u : 1u;
+          if (PASSES == 3) {
+            umma_tf32(td, da_lo + adv, db_hi + adv, idesc, acc0);  // small terms first
+            umma_tf32(td, da_hi + adv, db_lo + adv, idesc, 1u);
+            umma_tf32(td, da_hi + adv, db_hi + adv, idesc, 1u);
+          } else {
+            umma_tf32(td, da_hi + adv, db_hi + adv, idesc, acc0);
+          }
+        }
+        umma_commit(smem_u32(&empty[st]));   // stage reusable once these MMAs retire
+        const bool chunk_end = DRAIN ? (it % CH == CH - 1 || it == total_kb - 1) : (it == total_kb - 1);
+        if (chunk_end) umma_commit(smem_u32(&cfull[b]));
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== workers: 3xTF32 splitter + accumulator drain + epilogue =====================
+    const int wq = warp & 3;                   // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;          // which half of the BN columns this warp owns
+    const int wt = threadIdx.x - 64;           // 0..255
+    const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(half * COLS);
+    float acc[COLS];
+#pragma unroll
+    for (int i = 0; i < COLS; ++i) acc[i] = 0.f;
+
+    auto drain = [&](int d) {
+      const int b = d & 1;
+      mbar_wait(smem_u32(&cfull[b]), (uint32_t)(d >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < COLS; c0 += 32) {
+        float v[32];
+        tmem_ld32(trow + (uint32_t)(b * BN + c0), v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[c0 + i] += v[i];   // round-to-nearest fp32 add
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&drained[b]));
+    };
+
+    int next_drain = 0;
+    if (DRAIN) {
+      for (int it = 0; it < total_kb; ++it) {
+        const int st = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(smem_u32(&full[st]), ph);
+        uint4* hi = reinterpret_cast<uint4*>(smem + st * S::STAGE_BYTES);
+        uint4* lo = reinterpret_cast<uint4*>(smem + st * S::STAGE_BYTES + S::TILE_BYTES);
+#pragma unroll 4
+        for (int i = wt; i < S::TILE_BYTES / 16; i += NWORK * 32) {
+          const uint4 v = hi[i];
+          uint4 h, l;
+          h.x = v.x & 0xffffe000u; h.y = v.y & 0xffffe000u; h.z = v.z & 0xffffe000u; h.w = v.w & 0xffffe000u;
+          l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
+          l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
+          l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
+          l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
+          hi[i] = h;
+          lo[i] = l;
+        }
+        fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&conv[st]));
+        // chunks whose last k-block retired (implied by this stage having been refilled) drain for free
+        while (next_drain < nchunk && min((next_drain + 1) * CH, total_kb) - 1 <= it - STAGES) drain(next_drain++);
+      }
+    }
+    while (next_drain < nchunk) drain(next_drain++);
+
+    // ----- epilogue -----
+    const int m = m0 + wq * 32 + lane;
+    const int nb = n0 + half * COLS;
+    if (a.epi == 0) {
+      if (m < a.M) {
+        float* yr = a.y + (size_t)m * a.ldy;
+#pragma unroll
+        for (int q = 0; q < COLS / 4; ++q) {
+          const int n = nb + q * 4;
+          if (n + 3 < a.N) {
+            float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int s = 0; s < a.nsrc; ++s)
+              if (a.bias[s]) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(a.bias[s] + n));
+                bsum.x += t.x; bsum.y += t.y; bsum.z += t.z; bsum.w += t.w;
+              }
+            float4 o = make_float4(acc[q * 4] + bsum.x, acc[q * 4 + 1] + bsum.y, acc[q * 4 + 2] + bsum.z, acc[q * 4 + 3] + bsum.w);
+            if (a.accumulate) {
+              const float4 t = *reinterpret_cast<const float4*>(yr + n);
+              o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+            }
+            *reinterpret_cast<float4*>(yr + n) = o;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (n + e < a.N) {
+                float bs = 0.f;
+                for (int s = 0; s < a.nsrc; ++s)
+                  if (a.bias[s]) bs += __ldg(a.bias[s] + n + e);
+                float o = acc[q * 4 + e] + bs;
+                if (a.accumulate) o += yr[n + e];
+                yr[n + e] = o;
+              }
+            }
+          }
+        }
+      }
+    } else {
+      // fused additive-attention score (misc/AttentionModelCore.py:37-42):
+      //   score[tile][m] = sum_{n in this thread's columns} w[n] * tanh(acc[m,n] + U_b[n] + g[m / natt, n])
+      // partials are stored per column slice and summed in a fixed order by the attention kernel
+      const int mg = (m < a.M ? m : a.M - 1) / a.natt;
+      const float* gr = a.g + (size_t)mg * a.ldg;
+      float part = 0.f;
+#pragma unroll
+      for (int q = 0; q < COLS / 4; ++q) {
+        const int n = nb + q * 4;
+        if (n + 3 < a.N) {
+          const float4 b4 = a.bias[0] ? __ldg(reinterpret_cast<const float4*>(a.bias[0] + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 gg = *reinterpret_cast<const float4*>(gr + n);
+          const float4 ww = __ldg(reinterpret_cast<const float4*>(a.wv + n));
+          part = fmaf(ww.x, tanhf(acc[q * 4 + 0] + b4.x + gg.x), part);
+          part = fmaf(ww.y, tanhf(acc[q * 4 + 1] + b4.y + gg.y), part);
+          part = fmaf(ww.z, tanhf(acc[q * 4 + 2] + b4.z + gg.z), part);
+          part = fmaf(ww.w, tanhf(acc[q * 4 + 3] + b4.w + gg.w), part);
+        }
+      }
+      const int slice = blockIdx.x * 2 + half;   // N / COLS slices in total
+      if (m < a.M) a.score[(size_t)slice * a.M + m] = part;
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor map over a row-major (rows, K) matrix with leading dimension ld: box = 32 floats x box_rows
+static int make_map(CUtensorMap* tm, const float* base, int rows, int K, int ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return RFN_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%d K=%d ld=%d", (int)r, rows, K, ld);
+    return RFN_ERR_CUDA;
+  }
+  return RFN_OK;
+}
+
+template <int BN, int STAGES, int PASSES, int CH>
+static int launch_tc(const TcArgs& t, cudaStream_t st) {
+  using S = TcSmem<BN, PASSES>;
+  const size_t smem = (size_t)STAGES * S::STAGE_BYTES + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    RFN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, PASSES, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  dim3 grid((t.N + BN - 1) / BN, (t.M + TC_BM - 1) / TC_BM);
+  gemm_tc_kernel<BN, STAGES, PASSES, CH><<<grid, TC_THREADS, smem, st>>>(t);
+  RFN_LAUNCH_CHECK();
+  return RFN_OK;
+}
+
+bool gemm_tc_supported(const GemmArgs& a) {
+  if (a.N % 4 != 0 || a.ldy % 4 != 0 || ((uintptr_t)a.y % 16) != 0) return false;
+  for (int s = 0; s < a.nsrc; ++s) {
+    const GemmSrc& g = a.src[s];
+    if (g.K % 4 != 0 || g.ldx % 4 != 0 || g.ldw % 4 != 0) return false;
+    if (((uintptr_t)g.x % 16) != 0 || ((uintptr_t)g.w % 16) != 0) return false;
+    if (g.bias && ((uintptr_t)g.bias % 16) != 0) return false;
+  }
+  return true;
+}
+
+// passes: 3 = 3xTF32 (fp32-equivalent), 1 = single-pass TF32.  score != nullptr selects the fused
+// attention-score epilogue (then y is unused); it receives tc_score_slices(N) partial rows of M.
+int tc_score_slices(int N) { return ((N + 255) / 256) * 2; }
+
+int gemm_tc(const GemmArgs& a, int passes, const float* g, int ldg, const float* wv, float* score, int natt,
+            cudaStream_t st) {
+  ProfScope prof__(TAG_GEMM_OTHER, st);
+  RFN_CHECK_ARG(gemm_tc_supported(a), "gemm_tc: operands must be 16-byte aligned with K, N, ld multiples of 4");
+  if (a.M == 0) return RFN_OK;
+  TcArgs t{};
+  t.nsrc = a.nsrc;
+  const int bn = (score || a.N > 128) ? 256 : 128;
+  for (int s = 0; s < a.nsrc; ++s) {
+    RFN_TRY(make_map(&t.tm_x[s], a.src[s].x, a.M, a.src[s].K, a.src[s].ldx, TC_BM));
+    RFN_TRY(make_map(&t.tm_w[s], a.src[s].w, a.N, a.src[s].K, a.src[s].ldw, bn));
+    t.K[s] = a.src[s].K;
+    t.bias[s] = a.src[s].bias;
+  }
+  t.y = a.y; t.ldy = a.ldy; t.M = a.M; t.N = a.N; t.accumulate = a.accumulate;
+  t.epi = score ? 1 : 0;
+  t.g = g; t.ldg = ldg; t.wv = wv; t.score = score; t.natt = natt > 0 ? natt : 1;
+  if (passes == 3) return bn == 256 ? launch_tc<256, 2, 3, 4>(t, st) : launch_tc<128, 3, 3, 4>(t, st);
+  return bn == 256 ? launch_tc<256, 4, 1, 1>(t, st) : launch_tc<128, 6, 1, 1>(t, st);
+}
+
+}  // namespace rfn

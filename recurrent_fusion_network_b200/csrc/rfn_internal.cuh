@@ -82,6 +82,13 @@ struct GemmArgs {
   int accumulate;
 };
 int gemm_simt(const GemmArgs& a, cudaStream_t st);
+// tcgen05 engine: passes 3 = 3xTF32 (fp32-equivalent), 1 = single-pass TF32; score != nullptr selects
+// the fused attention-score epilogue score[m] += sum_n wv[n] tanh(acc + bias + g[m / natt, n])
+bool gemm_tc_supported(const GemmArgs& a);
+int gemm_tc(const GemmArgs& a, int passes, const float* g, int ldg, const float* wv, float* score, int natt,
+            cudaStream_t st);
+int gemm_engine(const GemmArgs& a, int engine, cudaStream_t st);
+int tc_score_slices(int N);
 // dispatches on rfn_set_gemm_mode() and problem shape
 int gemm(const GemmArgs& a, cudaStream_t st);
 inline GemmArgs gemm1(const float* x, int ldx, const float* w, const float* bias, int K, float* y,
@@ -101,6 +108,9 @@ inline GemmArgs gemm1(const float* x, int ldx, const float* w, const float* bias
 int attention_step(const float* A, const float* P, const float* g, const float* w, const float* d_wb,
                    float* z, int ldz, float* alpha, int rows, int N, int D, int Ah, int div,
                    cudaStream_t st);
+// same, from pre-reduced scores e[r,n] (without the att_h_2_out bias) produced by the fused GEMM epilogue
+int attention_from_scores(const float* A, const float* scores, int nslices, const float* d_wb, float* z, int ldz,
+                          float* alpha, int rows, int N, int D, int div, cudaStream_t st);
 int lstm_cell(const float* G, const float* c_prev, float* h_out, float* c_out, float* h_out2,
               int ldh2, float* h_out3, int ldh3, int rows, int R, cudaStream_t st);
 int embed_gather_i64(const int64_t* tok, int ld_tok, const float* embed, float* x, int rows, int E,

@@ -116,11 +116,21 @@ static int thought_vectors(const rfn_dims& d, const float* const* prm, const flo
       // g = h_2_att_h(h_j)                                  (misc/AttentionModelCore.py:36)
       RFN_TRY(gemm(gemm1(Hin + (size_t)j * R, J * R, prm[ix.s1(s, j, 2)], prm[ix.s1(s, j, 3)], R, w.g, A, rows, A), st));
       // P = att_2_att_h(A_j)                                (:32-34)  -- the 89%-of-FLOPs contraction
-      {
-        TagScope ts(TAG_GEMM_ATT2ATT);
-        RFN_TRY(gemm(gemm1(att[j], D, prm[ix.s1(s, j, 0)], prm[ix.s1(s, j, 1)], D, w.P, A, rows * N, A), st));
-      }
-      {
+      GemmArgs pa = gemm1(att[j], D, prm[ix.s1(s, j, 0)], prm[ix.s1(s, j, 1)], D, w.P, A, rows * N, A);
+      if (gemm_mode() >= 1 && rows * N >= 128 && gemm_tc_supported(pa)) {
+        // tensor engine: e[r,n] = w . tanh(U A + b + g) is reduced in the GEMM epilogue, P never hits HBM
+        float* score = w.P;  // (slices, rows * N) partial scores, slices <= A / 128
+        {
+          TagScope ts(TAG_GEMM_ATT2ATT);
+          RFN_TRY(gemm_tc(pa, gemm_mode() == 1 ? 3 : 1, w.g, A, prm[ix.s1(s, j, 4)], score, N, st));
+        }
+        TagScope ts(TAG_ATTN_S1);
+        RFN_TRY(attention_from_scores(att[j], score, tc_score_slices(A), prm[ix.s1(s, j, 5)], w.z, D, nullptr, rows, N, D, 1, st));
+      } else {
+        {
+          TagScope ts(TAG_GEMM_ATT2ATT);
+          RFN_TRY(gemm(pa, st));
+        }
         TagScope ts(TAG_ATTN_S1);
         RFN_TRY(attention_step(att[j], w.P, w.g, prm[ix.s1(s, j, 4)], prm[ix.s1(s, j, 5)], w.z, D, nullptr, rows, N, D, A, 1, st));
       }

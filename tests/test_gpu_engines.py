@@ -1,0 +1,81 @@
+"""GPU: the tcgen05 GEMM engines (3xTF32 and single-pass TF32) against the fp32 SIMT engine and an
+fp64 reference of the same contraction; the fused attention-score epilogue against the oracle."""
+import ctypes as C
+
+import pytest
+import torch
+
+from oracle import rfnet_oracle as O
+from tests._gpu_util import build_model, cuda_list, maxdiff
+
+pytestmark = pytest.mark.gpu
+
+
+def _linear_engine(engine, xs, ws, bs, M, N, accumulate_into=None):
+    from recurrent_fusion_network_b200 import _capi
+    from recurrent_fusion_network_b200._capi import check, lib, ptr, ptr_array, stream
+    n = len(xs)
+    y = accumulate_into if accumulate_into is not None else torch.empty(M, N, device="cuda")
+    ld = (C.c_int * n)(*[x.stride(0) for x in xs])
+    ks = (C.c_int * n)(*[x.shape[1] for x in xs])
+    check(lib().rfn_linear_f32_engine(engine, n, ptr_array(xs), ld, ptr_array(ws), ks, ptr_array(bs), ptr(y), y.stride(0),
+                                      M, N, 1 if accumulate_into is not None else 0, stream()), "rfn_linear_f32_engine")
+    return y
+
+
+SHAPES = [(128, 256, [32]), (128, 128, [64]), (256, 512, [2048]), (200, 512, [2208]), (1000, 2048, [2560, 1280]),
+          (300, 9488, [512]), (129, 132, [36, 64, 128]), (64, 40, [24]), (5, 512, [512])]
+
+
+@pytest.mark.parametrize("M,N,Ks", SHAPES)
+@pytest.mark.parametrize("engine,tol", [(1, 3e-6), (2, 3e-3)])
+def test_tc_engine_matches_fp64(engine, tol, M, N, Ks):
+    g = torch.Generator().manual_seed(M + N)
+    xs = [torch.randn(M, k, generator=g) for k in Ks]
+    ws = [(torch.rand(N, k, generator=g) * 2 - 1) * 0.1 for k in Ks]
+    bs = [torch.randn(N, generator=g) for _ in Ks]
+    want = sum(x.double() @ w.double().t() + b.double() for x, w, b in zip(xs, ws, bs))
+    got = _linear_engine(engine, cuda_list(xs), cuda_list(ws), cuda_list(bs), M, N)
+    torch.cuda.synchronize()
+    scale = float(want.abs().max())
+    err = maxdiff(got, want)
+    assert err <= tol * scale, f"engine {engine}: err {err:.3g} vs scale {scale:.3g}"
+    if engine == 1:
+        ref = _linear_engine(0, cuda_list(xs), cuda_list(ws), cuda_list(bs), M, N)
+        # 3xTF32 must be as good as the fp32 SIMT engine (both ~1e-6 relative to fp64)
+        assert err <= 4 * maxdiff(ref, want) + 1e-6 * scale
+        acc = _linear_engine(engine, cuda_list(xs), cuda_list(ws), cuda_list(bs), M, N, accumulate_into=ref.clone())
+        assert maxdiff(acc, 2 * want) <= 2 * tol * scale
+
+
+def test_strided_operands():
+    """x with a leading dimension larger than K (the H-concat slices of stage 1)."""
+    g = torch.Generator().manual_seed(1)
+    big = torch.randn(300, 2560, generator=g).cuda()
+    x = big[:, 512:1024]
+    w = ((torch.rand(512, 512, generator=g) * 2 - 1) * 0.1).cuda()
+    b = torch.randn(512, generator=g).cuda()
+    want = x.double() @ w.double().t() + b.double()
+    for engine, tol in ((0, 3e-6), (1, 3e-6)):
+        got = _linear_engine(engine, [x], [w], [b], 300, 512)
+        assert maxdiff(got, want) <= tol * float(want.abs().max())
+
+
+@pytest.mark.parametrize("mode,tol", [(1, 2e-5), (2, 5e-3)])
+def test_stage1_with_fused_score_epilogue(mode, tol):
+    """Full thought-vector pass with the tensor engine (fused tanh-score epilogue) vs the oracle."""
+    from recurrent_fusion_network_b200 import _capi
+    cfg = O.config1(196)
+    sd = O.make_state_dict(cfg, seed=1234)
+    fc, att = O.make_inputs(cfg, 6, seed=5)
+    m = build_model(cfg, sd)
+    _capi.check(_capi.lib().rfn_set_gemm_mode(mode))
+    try:
+        with torch.no_grad():
+            TVc, rp, st = m.get_thought_vectors(cuda_list(fc), cuda_list(att), m.get_init_state(cuda_list(fc)))
+            torch.cuda.synchronize()
+        TVc_o, rp_o, st_o = O.get_thought_vectors(sd, cfg, att, O.get_init_state(sd, cfg, fc))
+        assert maxdiff(TVc, TVc_o) <= tol
+        assert maxdiff(st[0][0], st_o[0]) <= tol
+    finally:
+        _capi.lib().rfn_set_gemm_mode(0)
