@@ -70,6 +70,10 @@ uint64_t rfn_launch_count(void);
 int rfn_set_gemm_mode(int mode);
 int rfn_get_gemm_mode(void);
 
+/* 1 (default): the J independent encoder cells of a fusion step run on internal side streams forked
+ * from / joined into the caller's stream; 0: everything is serialised on the caller's stream. */
+int rfn_set_concurrency(int on);
+
 /* Optional per-kernel-class timing: when enabled every launch is bracketed by CUDA events on its
  * stream; rfn_profile_read() synchronises them and returns summed milliseconds and launch counts
  * per class (rfn_profile_num_tags() classes, named by rfn_profile_tag_name()), then clears. */

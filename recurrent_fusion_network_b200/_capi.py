@@ -50,6 +50,7 @@ _SIGNATURES = {
     "rfn_launch_count": (C.c_uint64, []),
     "rfn_set_gemm_mode": (_i, [_i]),
     "rfn_get_gemm_mode": (_i, []),
+    "rfn_set_concurrency": (_i, [_i]),
     "rfn_profile_enable": (_i, [_i]),
     "rfn_profile_num_tags": (_i, []),
     "rfn_profile_tag_name": (C.c_char_p, [_i]),

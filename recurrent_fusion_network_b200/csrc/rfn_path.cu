@@ -2,6 +2,8 @@
 // greedy / multinomial, batched beam, ensemble beam).  Pure launch sequencing on one stream: no
 // host<->device synchronisation, no allocation; everything lives in the caller's workspace.
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 
 #include "rfn_internal.cuh"
 #include "rfn_vocab.cuh"
@@ -56,31 +58,108 @@ static int check_dims(const rfn_dims* d) {
   return RFN_OK;
 }
 
+// ---- side streams: the J encoder cells of a fusion step are independent (Jacobi update), so their
+// kernel chains run concurrently, forked from and joined back into the caller's stream with events ----
+struct SidePool {
+  int dev = -1;
+  cudaStream_t s[RFN_MAX_ENCODERS];
+  cudaEvent_t fork;
+  cudaEvent_t join[RFN_MAX_ENCODERS];
+};
+static std::atomic<int> g_concurrency{1};
+static SidePool* side_pool() {
+  static std::mutex mu;
+  static SidePool pools[16];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  SidePool& p = pools[dev];
+  if (p.dev != dev) {
+    for (int i = 0; i < RFN_MAX_ENCODERS; ++i) {
+      if (cudaStreamCreateWithFlags(&p.s[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+      if (cudaEventCreateWithFlags(&p.join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    if (cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    p.dev = dev;
+  }
+  return &p;
+}
+
+template <typename F>
+static int for_each_encoder(int J, cudaStream_t st, F&& fn) {
+  SidePool* sp = (g_concurrency.load() && J > 1) ? side_pool() : nullptr;
+  if (!sp) {
+    for (int j = 0; j < J; ++j) RFN_TRY(fn(j, st));
+    return RFN_OK;
+  }
+  RFN_CUDA(cudaEventRecord(sp->fork, st));
+  for (int j = 0; j < J; ++j) {
+    RFN_CUDA(cudaStreamWaitEvent(sp->s[j], sp->fork, 0));
+    RFN_TRY(fn(j, sp->s[j]));
+    RFN_CUDA(cudaEventRecord(sp->join[j], sp->s[j]));
+  }
+  for (int j = 0; j < J; ++j) RFN_CUDA(cudaStreamWaitEvent(st, sp->join[j], 0));
+  return RFN_OK;
+}
+
 // ---- stages 1 + 2 ----------------------------------------------------------------------------------
 struct TVWork {
-  float *Hcat[2], *C, *g, *P, *z, *G, *TV, *hx, *rs;
+  float *Hcat[2], *C, *TV, *hx, *rs;
+  float *g[RFN_MAX_ENCODERS], *P[RFN_MAX_ENCODERS], *z[RFN_MAX_ENCODERS], *G[RFN_MAX_ENCODERS];
 };
+static size_t p_floats(const rfn_dims& d, int rows, int N) {
+  // SIMT engine: P = att_2_att_h(A) is materialised (rows*N, A); tensor engine: partial scores only
+  const size_t full = (size_t)rows * N * d.att_hid_size;
+  if (gemm_mode() == 0) return full;
+  return std::max((size_t)tc_score_slices(d.att_hid_size) * rows * N, std::min(full, (size_t)128 * d.att_hid_size));
+}
 static size_t carve_tv(const rfn_dims& d, int rows, bool need_tv, bool need_reason, Bump& b, TVWork& w) {
   const int J = d.J, R = d.rnn_size, A = d.att_hid_size, S0 = d.num_review_steps_0, S1 = d.num_review_steps;
-  int Nmax = S0, Dmax = J * R;
-  for (int j = 0; j < J; ++j) { Nmax = std::max(Nmax, d.att_num[j]); Dmax = std::max(Dmax, d.att_feat_size[j]); }
   w.Hcat[0] = b.take<float>((size_t)rows * J * R);
   w.Hcat[1] = b.take<float>((size_t)rows * J * R);
   w.C = b.take<float>((size_t)rows * J * R);
-  w.g = b.take<float>((size_t)rows * A);
-  w.P = b.take<float>((size_t)rows * Nmax * A);
-  w.z = b.take<float>((size_t)rows * Dmax);
-  w.G = b.take<float>((size_t)rows * 4 * R);
   w.hx = b.take<float>((size_t)rows * R);
+  for (int j = 0; j < J; ++j) {
+    w.g[j] = b.take<float>((size_t)rows * A);
+    w.P[j] = b.take<float>(p_floats(d, rows, std::max(d.att_num[j], S0)));
+    w.z[j] = b.take<float>((size_t)rows * std::max(d.att_feat_size[j], R));
+    w.G[j] = b.take<float>((size_t)rows * 4 * R);
+  }
   w.TV = need_tv ? b.take<float>((size_t)J * rows * S0 * R) : nullptr;
   w.rs = need_reason ? b.take<float>((size_t)rows * std::max(S0, S1) * d.top_words_count) : nullptr;
   return b.off;
 }
 
+// z = Att(h, A) for one attention module (misc/AttentionModelCore.py:31-48): g = h_2_att_h(h); then either
+// the tensor engine with the fused tanh-score epilogue (U_a A never reaches HBM) or GEMM + fused step kernel
+static int attention_module(const rfn_dims& d, const float* h, int ldh, const float* Afeat, int N, int D,
+                            const float* U_w, const float* U_b, const float* Wh_w, const float* Wh_b, const float* v_w,
+                            const float* v_b, float* g, float* P, float* z, int ldz, int rows, int tag_gemm, int tag_attn,
+                            cudaStream_t st) {
+  const int R = d.rnn_size, A = d.att_hid_size;
+  RFN_TRY(gemm(gemm1(h, ldh, Wh_w, Wh_b, R, g, A, rows, A), st));                          // :36
+  GemmArgs pa = gemm1(Afeat, D, U_w, U_b, D, P, A, rows * N, A);                            // :32-34
+  if (gemm_mode() >= 1 && rows * N >= 128 && gemm_tc_supported(pa)) {
+    {
+      TagScope ts(tag_gemm);
+      RFN_TRY(gemm_tc(pa, gemm_mode() == 1 ? 3 : 1, g, A, v_w, P, N, st));
+    }
+    TagScope ts(tag_attn);
+    return attention_from_scores(Afeat, P, tc_score_slices(A), v_b, z, ldz, nullptr, rows, N, D, 1, st);
+  }
+  {
+    TagScope ts(tag_gemm);
+    RFN_TRY(gemm(pa, st));
+  }
+  TagScope ts(tag_attn);
+  return attention_step(Afeat, P, g, v_w, v_b, z, ldz, nullptr, rows, N, D, A, 1, st);
+}
+
 static int thought_vectors(const rfn_dims& d, const float* const* prm, const float* const* fc,
-                           const float* const* init_h, const float* const* init_c, const float* const* att, int rows, float* TVc, float* h_out, float* c_out, float* TV_user,
-                           float* reason_pred, void* ws, size_t ws_bytes, cudaStream_t st) {
-  const int J = d.J, R = d.rnn_size, A = d.att_hid_size, S0 = d.num_review_steps_0, S1 = d.num_review_steps;
+                           const float* const* init_h, const float* const* init_c, const float* const* att, int rows,
+                           float* TVc, float* h_out, float* c_out, float* TV_user, float* reason_pred, void* ws,
+                           size_t ws_bytes, cudaStream_t st) {
+  const int J = d.J, R = d.rnn_size, S0 = d.num_review_steps_0, S1 = d.num_review_steps;
   const int K = d.top_words_count;
   const PIdx ix(d);
   Bump b(ws);
@@ -94,57 +173,41 @@ static int thought_vectors(const rfn_dims& d, const float* const* prm, const flo
   const size_t tv_stride = (size_t)rows * S0 * R;
 
   // A.0  h_j^0 = c_j^0 = fc2h_j(fc_j)                      (misc/RecurrentFusionModel.py:202-208)
-  for (int j = 0; j < J; ++j) {
+  RFN_TRY(for_each_encoder(J, st, [&](int j, cudaStream_t sj) -> int {
     float* cj = w.C + (size_t)j * rows * R;
     const float* hj = cj;
     if (fc) {
-      RFN_TRY(gemm(gemm1(fc[j], d.fc_feat_size[j], prm[ix.fc2h(j, 0)], prm[ix.fc2h(j, 1)], d.fc_feat_size[j], cj, R, rows, R), st));
+      RFN_TRY(gemm(gemm1(fc[j], d.fc_feat_size[j], prm[ix.fc2h(j, 0)], prm[ix.fc2h(j, 1)], d.fc_feat_size[j], cj, R, rows, R), sj));
     } else {
-      RFN_CUDA(cudaMemcpyAsync(cj, init_c[j], (size_t)rows * R * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      RFN_CUDA(cudaMemcpyAsync(cj, init_c[j], (size_t)rows * R * sizeof(float), cudaMemcpyDeviceToDevice, sj));
       hj = init_h[j];
     }
     RFN_CUDA(cudaMemcpy2DAsync(w.Hcat[0] + (size_t)j * R, (size_t)J * R * sizeof(float), hj, (size_t)R * sizeof(float),
-                               (size_t)R * sizeof(float), rows, cudaMemcpyDeviceToDevice, st));
-  }
+                               (size_t)R * sizeof(float), rows, cudaMemcpyDeviceToDevice, sj));
+    return RFN_OK;
+  }));
   // A.3  stage 1: S0 fusion steps, distinct weights per (s, j); Jacobi update over encoders
   for (int s = 0; s < S0; ++s) {
     const float* Hin = w.Hcat[s & 1];
     float* Hout = w.Hcat[(s + 1) & 1];
-    for (int j = 0; j < J; ++j) {
+    RFN_TRY(for_each_encoder(J, st, [&](int j, cudaStream_t sj) -> int {
       const int N = d.att_num[j], D = d.att_feat_size[j];
       float* cj = w.C + (size_t)j * rows * R;
-      // g = h_2_att_h(h_j)                                  (misc/AttentionModelCore.py:36)
-      RFN_TRY(gemm(gemm1(Hin + (size_t)j * R, J * R, prm[ix.s1(s, j, 2)], prm[ix.s1(s, j, 3)], R, w.g, A, rows, A), st));
-      // P = att_2_att_h(A_j)                                (:32-34)  -- the 89%-of-FLOPs contraction
-      GemmArgs pa = gemm1(att[j], D, prm[ix.s1(s, j, 0)], prm[ix.s1(s, j, 1)], D, w.P, A, rows * N, A);
-      if (gemm_mode() >= 1 && rows * N >= 128 && gemm_tc_supported(pa)) {
-        // tensor engine: e[r,n] = w . tanh(U A + b + g) is reduced in the GEMM epilogue, P never hits HBM
-        float* score = w.P;  // (slices, rows * N) partial scores, slices <= A / 128
-        {
-          TagScope ts(TAG_GEMM_ATT2ATT);
-          RFN_TRY(gemm_tc(pa, gemm_mode() == 1 ? 3 : 1, w.g, A, prm[ix.s1(s, j, 4)], score, N, st));
-        }
-        TagScope ts(TAG_ATTN_S1);
-        RFN_TRY(attention_from_scores(att[j], score, tc_score_slices(A), prm[ix.s1(s, j, 5)], w.z, D, nullptr, rows, N, D, 1, st));
-      } else {
-        {
-          TagScope ts(TAG_GEMM_ATT2ATT);
-          RFN_TRY(gemm(pa, st));
-        }
-        TagScope ts(TAG_ATTN_S1);
-        RFN_TRY(attention_step(att[j], w.P, w.g, prm[ix.s1(s, j, 4)], prm[ix.s1(s, j, 5)], w.z, D, nullptr, rows, N, D, A, 1, st));
-      }
+      // z = Att(h_j, A_j)   -- att_2_att_h is the 89%-of-FLOPs contraction
+      RFN_TRY(attention_module(d, Hin + (size_t)j * R, J * R, att[j], N, D, prm[ix.s1(s, j, 0)], prm[ix.s1(s, j, 1)],
+                               prm[ix.s1(s, j, 2)], prm[ix.s1(s, j, 3)], prm[ix.s1(s, j, 4)], prm[ix.s1(s, j, 5)], w.g[j],
+                               w.P[j], w.z[j], D, rows, TAG_GEMM_ATT2ATT, TAG_ATTN_S1, sj));
       // G = H2h(H) + z2h(z)                                 (misc/RecurrentFusionModel.py:53)
       GemmArgs ga{};
       ga.src[0] = GemmSrc{Hin, prm[ix.s1(s, j, 6)], prm[ix.s1(s, j, 7)], J * R, J * R, J * R};
-      ga.src[1] = GemmSrc{w.z, prm[ix.s1(s, j, 8)], prm[ix.s1(s, j, 9)], D, D, D};
-      ga.nsrc = 2; ga.y = w.G; ga.ldy = 4 * R; ga.M = rows; ga.N = 4 * R;
+      ga.src[1] = GemmSrc{w.z[j], prm[ix.s1(s, j, 8)], prm[ix.s1(s, j, 9)], D, D, D};
+      ga.nsrc = 2; ga.y = w.G[j]; ga.ldy = 4 * R; ga.M = rows; ga.N = 4 * R;
       {
         TagScope ts(TAG_GEMM_GATES);
-        RFN_TRY(gemm(ga, st));
+        RFN_TRY(gemm(ga, sj));
       }
-      RFN_TRY(lstm_cell(w.G, cj, nullptr, cj, Hout + (size_t)j * R, J * R, TV + j * tv_stride + (size_t)s * R, S0 * R, rows, R, st));
-    }
+      return lstm_cell(w.G[j], cj, nullptr, cj, Hout + (size_t)j * R, J * R, TV + j * tv_stride + (size_t)s * R, S0 * R, rows, R, sj);
+    }));
   }
   const float* Hfin = w.Hcat[S0 & 1];
   if (reason_pred) {
@@ -159,16 +222,14 @@ static int thought_vectors(const rfn_dims& d, const float* const* prm, const flo
   RFN_TRY(mean_tensors(Hfin, (size_t)R, J, h0, R, (size_t)rows * R, R, J * R, st));
   RFN_TRY(mean_tensors(w.C, (size_t)rows * R, J, c_out, R, (size_t)rows * R, R, R, st));
   // A.5  stage 2: S1 review steps over the J thought-vector sets
-  float* zs = w.z;  // J x (rows, R)
   for (int s = 0; s < S1; ++s) {
     const float* hin = hb[(S1 + s) & 1];
     float* hout = hb[(S1 + s + 1) & 1];
-    for (int j = 0; j < J; ++j) {
-      RFN_TRY(gemm(gemm1(hin, R, prm[ix.s2_att(s, j, 2)], prm[ix.s2_att(s, j, 3)], R, w.g, A, rows, A), st));
-      RFN_TRY(gemm(gemm1(TV + j * tv_stride, R, prm[ix.s2_att(s, j, 0)], prm[ix.s2_att(s, j, 1)], R, w.P, A, rows * S0, A), st));
-      RFN_TRY(attention_step(TV + j * tv_stride, w.P, w.g, prm[ix.s2_att(s, j, 4)], prm[ix.s2_att(s, j, 5)],
-                             zs + (size_t)j * rows * R, R, nullptr, rows, S0, R, A, 1, st));
-    }
+    RFN_TRY(for_each_encoder(J, st, [&](int j, cudaStream_t sj) -> int {
+      return attention_module(d, hin, R, TV + j * tv_stride, S0, R, prm[ix.s2_att(s, j, 0)], prm[ix.s2_att(s, j, 1)],
+                              prm[ix.s2_att(s, j, 2)], prm[ix.s2_att(s, j, 3)], prm[ix.s2_att(s, j, 4)], prm[ix.s2_att(s, j, 5)],
+                              w.g[j], w.P[j], w.z[j], R, rows, TAG_GEMM_OTHER, TAG_ATTN_SMALL, sj);
+    }));
     // G = h2h(h) + sum_j z_2_h[j](z_j)       (misc/LSTMSoftMultiAttentionFeatArrayNoInputCore.py:50-52)
     int jn = 0;
     bool first = true;
@@ -177,17 +238,17 @@ static int thought_vectors(const rfn_dims& d, const float* const* prm, const flo
       int n = 0;
       if (first) ga.src[n++] = GemmSrc{hin, prm[ix.s2_h2h(s, 0)], prm[ix.s2_h2h(s, 1)], R, R, R};
       while (n < 3 && jn < J) {
-        ga.src[n++] = GemmSrc{zs + (size_t)jn * rows * R, prm[ix.s2_z2h(s, jn, 0)], prm[ix.s2_z2h(s, jn, 1)], R, R, R};
+        ga.src[n++] = GemmSrc{w.z[jn], prm[ix.s2_z2h(s, jn, 0)], prm[ix.s2_z2h(s, jn, 1)], R, R, R};
         ++jn;
       }
-      ga.nsrc = n; ga.y = w.G; ga.ldy = 4 * R; ga.M = rows; ga.N = 4 * R; ga.accumulate = first ? 0 : 1;
+      ga.nsrc = n; ga.y = w.G[0]; ga.ldy = 4 * R; ga.M = rows; ga.N = 4 * R; ga.accumulate = first ? 0 : 1;
       {
         TagScope ts(TAG_GEMM_GATES);
         RFN_TRY(gemm(ga, st));
       }
       first = false;
     }
-    RFN_TRY(lstm_cell(w.G, c_out, hout, c_out, TVc + (size_t)s * R, S1 * R, nullptr, 0, rows, R, st));
+    RFN_TRY(lstm_cell(w.G[0], c_out, hout, c_out, TVc + (size_t)s * R, S1 * R, nullptr, 0, rows, R, st));
   }
   if (reason_pred) {
     RFN_TRY(gemm(gemm1(TVc, R, prm[ix.reason(0)], prm[ix.reason(1)], R, w.rs, K, rows * S1, K), st));
@@ -284,6 +345,11 @@ static int ws_fail(const char* who, size_t have, size_t need) {
 using namespace rfn;
 
 extern "C" {
+
+int rfn_set_concurrency(int on) {
+  g_concurrency.store(on ? 1 : 0);
+  return RFN_OK;
+}
 
 size_t rfn_workspace_bytes(const rfn_dims* dims, int rows, int dec_rows) {
   if (check_dims(dims) != RFN_OK || rows < 0 || dec_rows < 0) return 0;

@@ -400,6 +400,7 @@ class RecurrentFusionModel(nn.Module):
         J = self.num_feat_array
         if len(fc_feats) != J or len(att_feats) != J:
             raise _capi.RfnError(f"expected {J} fc / att feature tensors")
+        _require_cuda(next(self.parameters()))
         fc = [_f32c(t) for t in fc_feats]
         att = [_f32c(t) for t in att_feats]
         rows = fc[0].shape[0]
