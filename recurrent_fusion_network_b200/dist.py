@@ -1,0 +1,109 @@
+"""Multi-GPU plumbing of the path: one process per GPU, images sharded contiguously, weights replicated.
+
+Inference needs no collective besides the final caption gather.  Training (when the
+gradient path is used) is plain data parallelism: every loss term of the reference is normalised by the
+LOCAL row count (misc/utils.py:72,177,184,188), so with equal rows per rank the MEAN of the rank gradients
+equals the single-process gradient on the concatenated batch; the element-wise clamp of
+misc/utils.py:292-296 must be applied AFTER the average."""
+from typing import Callable, Iterable, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_total: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous shard [k0, k1) of n_total images for `rank` (last ranks may be short or empty)."""
+    per = (n_total + world - 1) // world
+    k0 = min(n_total, rank * per)
+    return k0, min(n_total, k0 + per)
+
+
+def gather_captions(seq: torch.Tensor, seq_logprobs: torch.Tensor, n_total: int, group=None):
+    """All-gather the per-shard captions into (n_total, L) tensors on every rank.
+
+    seq (n_local, L) int64 and seq_logprobs (n_local, L) float32 live on the backend's device (CUDA for
+    NCCL, CPU for gloo).  Ragged shards are padded to the common per-rank size and trimmed again."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return seq, seq_logprobs
+    world = dist.get_world_size(group)
+    per = (n_total + world - 1) // world
+    L = seq.shape[1]
+    n_local = seq.shape[0]
+    pad_s = torch.zeros(per, L, dtype=seq.dtype, device=seq.device)
+    pad_l = torch.zeros(per, L, dtype=seq_logprobs.dtype, device=seq.device)
+    pad_s[:n_local] = seq
+    pad_l[:n_local] = seq_logprobs
+    out_s = torch.empty(world * per, L, dtype=seq.dtype, device=seq.device)
+    out_l = torch.empty(world * per, L, dtype=seq_logprobs.dtype, device=seq.device)
+    dist.all_gather_into_tensor(out_s, pad_s, group=group)
+    dist.all_gather_into_tensor(out_l, pad_l, group=group)
+    return out_s[:n_total], out_l[:n_total]
+
+
+def sharded_decode(decode: Callable, fc_feats: Sequence[torch.Tensor], att_feats: Sequence[torch.Tensor],
+                   group=None, device: Optional[torch.device] = None):
+    """Decode this rank's contiguous shard of the images with `decode(fc_shard, att_shard) -> (seq, seq_logprobs)`
+    and gather every rank's captions.  `fc_feats` / `att_feats` hold ALL images (e.g. host arrays); only the
+    local shard is touched."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n_total = fc_feats[0].shape[0]
+    k0, k1 = shard_range(n_total, world, rank)
+    if k1 > k0:
+        seq, slp = decode([f[k0:k1] for f in fc_feats], [a[k0:k1] for a in att_feats])
+    else:
+        seq = slp = None
+    if seq is None:  # empty shard: contribute zero rows of the right width
+        L = _broadcast_width(None, group)
+        dev = device or torch.device("cpu")
+        seq = torch.zeros(0, L, dtype=torch.int64, device=dev)
+        slp = torch.zeros(0, L, dtype=torch.float32, device=dev)
+    else:
+        _broadcast_width(seq.shape[1], group)
+    return gather_captions(seq, slp, n_total, group)
+
+
+def _broadcast_width(L, group):
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return L
+    objs = [L if dist.get_rank(group) == 0 else None]
+    dist.broadcast_object_list(objs, src=0, group=group)
+    return objs[0]
+
+
+def average_gradients(params: Iterable[torch.nn.Parameter], group=None, bucket_bytes: int = 256 << 20,
+                      grad_clip: Optional[float] = None) -> None:
+    """Bucketed all-reduce(sum)/world of the gradients, then the reference's element-wise clamp.
+    1.958 GB of fp32 gradients per step for the full model; buckets bound launch latency."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        if grad_clip is not None:
+            for p in params:
+                if p.grad is not None:
+                    p.grad.clamp_(-grad_clip, grad_clip)
+        return
+    world = dist.get_world_size(group)
+    bucket, size = [], 0
+
+    def flush():
+        nonlocal bucket, size
+        if not bucket:
+            return
+        flat = torch.cat([g.reshape(-1) for g in bucket])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(world)
+        if grad_clip is not None:
+            flat.clamp_(-grad_clip, grad_clip)
+        off = 0
+        for g in bucket:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+        bucket, size = [], 0
+
+    for p in params:
+        if p.grad is None:
+            continue
+        bucket.append(p.grad)
+        size += p.grad.numel() * p.grad.element_size()
+        if size >= bucket_bytes:
+            flush()
+    flush()
