@@ -150,8 +150,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   constexpr int NBUF = DRAIN ? 2 : 1;
   constexpr int TMEM_COLS = (BN * NBUF <= 128) ? 128 : (BN * NBUF <= 256 ? 256 : 512);
   static_assert(BN * NBUF <= 512 && COLS % 32 == 0, "accumulators must fit the 512 TMEM columns");
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // round up to the 1024-byte alignment SWIZZLE_128B needs, keeping the pointer in the shared window
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = (uint64_t*)(smem + STAGES * S::STAGE_BYTES);
   uint64_t* full = bars;                 // TMA landed
   uint64_t* conv = bars + STAGES;        // hi/lo split done
@@ -214,25 +215,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       const int b = c & 1;
       const bool chunk_start = DRAIN ? (it % CH == 0) : (it == 0);
       if (DRAIN && chunk_start && c >= 2) mbar_wait(smem_u32(&drained[b]), (uint32_t)((c >> 1) - 1) & 1u);
-      mbar_wait(smem_u32(DRAIN ? &conv[st] : &full[st]), ph);
+      // The tensor core truncates TF32 inputs (low 13 mantissa bits ignored; measured), so the raw fp32
+      // tile IS the hi operand: hi.hi starts as soon as TMA lands, the cross terms wait for the splitter.
+      mbar_wait(smem_u32(&full[st]), ph);
       tc_fence_after();
+      const uint32_t td = tmem_base + (uint32_t)(b * BN);
+      const uint32_t sa = smem_u32(smem + st * S::STAGE_BYTES);
+      const uint64_t da_hi = make_desc_sw128(sa);
+      const uint64_t db_hi = make_desc_sw128(sa + TC_A_BYTES);
       if (lane == 0) {
-        const uint32_t td = tmem_base + (uint32_t)(b * BN);
-        const uint32_t sa = smem_u32(smem + st * S::STAGE_BYTES);
-        const uint64_t da_hi = make_desc_sw128(sa);
-        const uint64_t db_hi = make_desc_sw128(sa + TC_A_BYTES);
-        const uint64_t da_lo = make_desc_sw128(sa + S::TILE_BYTES);
-        const uint64_t db_lo = make_desc_sw128(sa + S::TILE_BYTES + TC_A_BYTES);
 #pragma unroll
         for (int k = 0; k < TC_BK / 8; ++k) {
           const uint64_t adv = (uint64_t)(k * 2);  // 8 tf32 = 32 bytes = 2 x 16-byte units inside the swizzle atom
-          const uint32_t acc0 = (chunk_start && k == 0) ? 0u : 1u;
-          if (PASSES == 3) {
-            umma_tf32(td, da_lo + adv, db_hi + adv, idesc, acc0);  // small terms first
+          umma_tf32(td, da_hi + adv, db_hi + adv, idesc, (chunk_start && k == 0) ? 0u : 1u);
+        }
+      }
+      if (PASSES == 3) {
+        mbar_wait(smem_u32(&conv[st]), ph);
+        tc_fence_after();
+      }
+      if (lane == 0) {
+        if (PASSES == 3) {
+          const uint64_t da_lo = make_desc_sw128(sa + S::TILE_BYTES);
+          const uint64_t db_lo = make_desc_sw128(sa + S::TILE_BYTES + TC_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k) {
+            const uint64_t adv = (uint64_t)(k * 2);
+            umma_tf32(td, da_lo + adv, db_hi + adv, idesc, 1u);
             umma_tf32(td, da_hi + adv, db_lo + adv, idesc, 1u);
-            umma_tf32(td, da_hi + adv, db_hi + adv, idesc, 1u);
-          } else {
-            umma_tf32(td, da_hi + adv, db_hi + adv, idesc, acc0);
           }
         }
         umma_commit(smem_u32(&empty[st]));   // stage reusable once these MMAs retire
@@ -273,18 +283,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         const int st = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
         mbar_wait(smem_u32(&full[st]), ph);
-        uint4* hi = reinterpret_cast<uint4*>(smem + st * S::STAGE_BYTES);
+        const uint4* hi = reinterpret_cast<const uint4*>(smem + st * S::STAGE_BYTES);
         uint4* lo = reinterpret_cast<uint4*>(smem + st * S::STAGE_BYTES + S::TILE_BYTES);
 #pragma unroll 4
         for (int i = wt; i < S::TILE_BYTES / 16; i += NWORK * 32) {
-          const uint4 v = hi[i];
-          uint4 h, l;
-          h.x = v.x & 0xffffe000u; h.y = v.y & 0xffffe000u; h.z = v.z & 0xffffe000u; h.w = v.w & 0xffffe000u;
-          l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
-          l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
-          l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
-          l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
-          hi[i] = h;
+          const uint4 v = hi[i];   // raw fp32; the MMA reads it as hi = trunc_tf32(x)
+          uint4 l;
+          l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xffffe000u));
+          l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & 0xffffe000u));
+          l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & 0xffffe000u));
+          l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & 0xffffe000u));
           lo[i] = l;
         }
         fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async proxy
