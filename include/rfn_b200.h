@@ -215,6 +215,59 @@ int rfn_multilabel_margin_f32(const float* pred, const int64_t* target, int rows
 int rfn_mean_log_softmax_f32(int n, const float* const* logits, int rows, int V, float* mean_scratch,
                              float* lp, rfn_stream_t stream);
 
+/* ---- backward operators (XE / RL training: SURVEY.md 8a rows a7, a8, a12) ------------------------
+ * Called by recurrent_fusion_network_b200/autograd.py, whose torch.autograd.Function wrappers
+ * stand where the reference relies on autograd through nn.Linear / tanh / softmax / bmm. */
+
+/* C[M,N] (+)= op(A)[M,K] . op(B)[K,N]; a_kmajor: A stored (M,K) row-major else (K,M); b_kmajor: B stored
+ * (N,K) row-major else (K,N).  dX = dY . W is (1,0); dW += dY^T . X is (0,0). */
+int rfn_gemm_general_f32(int a_kmajor, int b_kmajor, const float* A, int lda, const float* B, int ldb,
+                         float* C, int ldc, int M, int N, int K, int accumulate, rfn_stream_t stream);
+/* db[n] (+)= sum_m dY[m,n]  (bias gradient) */
+int rfn_colsum_f32(const float* dY, int ld, int M, int N, float* db, int accumulate, rfn_stream_t stream);
+/* backward of rfn_attention_step_f32: from dz and the saved alpha -> dP (rows,N,Ah), dg (rows,Ah),
+ * dw (Ah, +=), dwb (1, +=), and dA (rowsA,N,D, +=) when the attended set needs a gradient (thought vectors). */
+int rfn_attention_step_bwd_f32(const float* A, const float* P, const float* g, const float* w,
+                               const float* alpha, const float* dz, int lddz, float* dP, float* dg,
+                               float* dw, float* dwb, float* dA, int rows, int N, int D, int Ah, int div,
+                               rfn_stream_t stream);
+/* backward of rfn_lstm_cell_f32: (dh, dc_next may be NULL) -> dG (rows,4R), dc_prev (rows,R) */
+int rfn_lstm_cell_bwd_f32(const float* G, const float* c_prev, const float* dh, const float* dc_next,
+                          float* dG, float* dc_prev, int rows, int R, rfn_stream_t stream);
+/* dx = dlp - exp(lp) * sum_v dlp */
+int rfn_log_softmax_bwd_f32(const float* lp, size_t ld_lp, const float* dlp, size_t ld_d, float* dx,
+                            size_t ld_x, int rows, int V, rfn_stream_t stream);
+/* x[r,:] = embed[tok[r*ld_tok], :]  (nn.Embedding, misc/RecurrentFusionModel.py:276) and its backward */
+int rfn_embed_f32(const int64_t* tok, int ld_tok, const float* embed, float* x, int rows, int E, int V1,
+                  rfn_stream_t stream);
+int rfn_embed_bwd_f32(const int64_t* tok, int ld_tok, const float* dx, float* dE, int rows, int E, int V1,
+                      rfn_stream_t stream);
+/* out[r,k] = max_s in[r,s,k] (torch.max(reason_mat, 1), misc/RecurrentFusionModel.py:303) and its backward */
+int rfn_max_over_steps_f32(const float* in, float* out, int rows, int S, int K, rfn_stream_t stream);
+int rfn_max_over_steps_bwd_f32(const float* in, const float* dout, float* din, int rows, int S, int K,
+                               rfn_stream_t stream);
+/* out = alpha * x + beta * y  (y may be NULL) */
+int rfn_axpby_f32(float alpha, const float* x, float beta, const float* y, float* out, size_t n,
+                  rfn_stream_t stream);
+/* out = scale * x * m  (nn.Dropout with an explicit keep-mask m, scale = 1/(1-p)) */
+int rfn_mul_scale_f32(float scale, const float* x, const float* m, float* out, size_t n, rfn_stream_t stream);
+/* one token per log-prob row: arg-max (uniforms NULL; ties -> lower index, torch.max) or the inverse CDF of
+ * exp(lp/temperature) against uniforms[r] (misc/RecurrentFusionModel.py:619-635); lp_out = lp[r, tok]. */
+int rfn_select_token_f32(const float* lp, size_t ld, int rows, int V, const float* uniforms, float temperature,
+                         int64_t* tok, float* lp_out, rfn_stream_t stream);
+/* out[r] = x[r, idx[r]] (logprobs.gather, :632) and its backward (dx zero except column idx[r]) */
+int rfn_gather_cols_f32(const float* x, size_t ld, const int64_t* idx, float* out, int rows, rfn_stream_t stream);
+int rfn_scatter_cols_f32(const float* dout, const int64_t* idx, float* dx, size_t ld, int rows, int V,
+                         rfn_stream_t stream);
+/* gradients of the criteria w.r.t. their log-prob inputs (gout: device scalar, upstream gradient) */
+int rfn_xe_loss_bwd_f32(const int64_t* target, const float* mask, int ld_t, int rows, int T, int V, float eps,
+                        const float* gout, float* dlp, rfn_stream_t stream);
+int rfn_rl_loss_bwd_f32(const int64_t* seq, const float* reward, const float* lp_all, int ld_lp_rows, int rows,
+                        int T, int T1, int V, float entropy_reg, const float* gout, float* dslp,
+                        float* dlp_all, rfn_stream_t stream);
+int rfn_multilabel_margin_bwd_f32(const float* pred, const int64_t* target, int rows, int K, float weight,
+                                  const float* gout, float* dx, rfn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,6 +73,23 @@ _SIGNATURES = {
     "rfn_xe_loss_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
     "rfn_multilabel_margin_f32": (_i, [_vp, _vp, _i, _i, _f, _i, _vp, _vp]),
     "rfn_mean_log_softmax_f32": (_i, [_i, _pp, _i, _i, _vp, _vp, _vp]),
+    "rfn_gemm_general_f32": (_i, [_i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
+    "rfn_colsum_f32": (_i, [_vp, _i, _i, _i, _vp, _i, _vp]),
+    "rfn_attention_step_bwd_f32": (_i, [_vp] * 6 + [_i] + [_vp] * 5 + [_i] * 5 + [_vp]),
+    "rfn_lstm_cell_bwd_f32": (_i, [_vp] * 6 + [_i, _i, _vp]),
+    "rfn_log_softmax_bwd_f32": (_i, [_vp, _sz, _vp, _sz, _vp, _sz, _i, _i, _vp]),
+    "rfn_embed_f32": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _vp]),
+    "rfn_embed_bwd_f32": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _vp]),
+    "rfn_max_over_steps_f32": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "rfn_max_over_steps_bwd_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "rfn_axpby_f32": (_i, [_f, _vp, _f, _vp, _vp, _sz, _vp]),
+    "rfn_mul_scale_f32": (_i, [_f, _vp, _vp, _vp, _sz, _vp]),
+    "rfn_select_token_f32": (_i, [_vp, _sz, _i, _i, _vp, _f, _vp, _vp, _vp]),
+    "rfn_gather_cols_f32": (_i, [_vp, _sz, _vp, _vp, _i, _vp]),
+    "rfn_scatter_cols_f32": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp]),
+    "rfn_xe_loss_bwd_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
+    "rfn_rl_loss_bwd_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
+    "rfn_multilabel_margin_bwd_f32": (_i, [_vp, _vp, _i, _i, _f, _vp, _vp, _vp]),
     "rfn_rl_loss_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
 }
 

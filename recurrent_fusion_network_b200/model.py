@@ -48,10 +48,14 @@ def _require_cuda(t: torch.Tensor):
                              "move the model and its inputs to the GPU")
 
 
-def _no_grad_only(*tensors):
-    if torch.is_grad_enabled() and any(t.requires_grad for t in tensors if isinstance(t, torch.Tensor)):
-        return False
-    return True
+def _taping(*tensors):
+    """True when autograd must record: the call then goes through autograd.py's Function wrappers."""
+    return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
+
+
+def _dropout(x, p, training):
+    from . import autograd as AG
+    return AG.dropout(x, p, training)
 
 
 class _Workspace:
@@ -76,6 +80,9 @@ def linear(srcs, rows: int, out_features: int, out: Optional[torch.Tensor] = Non
     """y = sum_i x_i W_i^T + b_i through rfn_linear_f32.  srcs: list of (x, nn.Linear-like)."""
     xs = [_f32c(x) for x, _ in srcs]
     _require_cuda(xs[0])
+    if out is None and _taping(*xs, *[m.weight for _, m in srcs]):
+        from . import autograd as AG
+        return AG.linear(list(zip(xs, [m for _, m in srcs])))
     n = len(srcs)
     y = out if out is not None else torch.empty(rows, out_features, dtype=torch.float32, device=xs[0].device)
     done = 0
@@ -93,6 +100,9 @@ def linear(srcs, rows: int, out_features: int, out: Optional[torch.Tensor] = Non
 
 
 def lstm_cell(G: torch.Tensor, c_prev: torch.Tensor):
+    if _taping(G, c_prev):
+        from . import autograd as AG
+        return AG.CellFn.apply(G, c_prev)
     rows, R = c_prev.shape
     h = torch.empty_like(c_prev)
     c = torch.empty_like(c_prev)
@@ -104,6 +114,9 @@ def _attention(att_mod, pre_h: torch.Tensor, att_seq: torch.Tensor) -> torch.Ten
     """AttentionModelCore.forward through rfn_attention_core_f32."""
     pre_h, att_seq = _f32c(pre_h), _f32c(att_seq)
     _require_cuda(pre_h)
+    if _taping(pre_h, att_seq, att_mod.att_2_att_h.weight):
+        from . import autograd as AG
+        return AG.attention(att_mod, pre_h, att_seq)
     rows, N, D = att_seq.shape
     R = pre_h.shape[1]
     Ah = att_mod.att_2_att_h.weight.shape[0]
@@ -159,7 +172,7 @@ class LSTMFusionNoInputCore(nn.Module):
         z = self.att_model(pre_h, att_feat)
         G = linear([(H, self.H2h), (z, self.z2h)], pre_h.shape[0], 4 * self.rnn_size)
         next_h, next_c = lstm_cell(G, _f32c(pre_c))
-        next_h = self.dropout(next_h)
+        next_h = _dropout(next_h, self.drop_prob_fusion, self.training)
         return next_h, (next_h.unsqueeze(0), next_c.unsqueeze(0))
 
 
@@ -211,7 +224,7 @@ class LSTMSoftMultiAttentionFeatArrayNoInputCore(nn.Module):
         srcs = [(pre_h, self.h2h)] + [(zs[i], self.z_2_h[i]) for i in range(self.num_feat_array)]
         G = linear(srcs, pre_h.shape[0], 4 * self.rnn_size)
         next_h, next_c = lstm_cell(G, _f32c(pre_c))
-        next_h = self.dropout(next_h)
+        next_h = _dropout(next_h, self.drop_prob_lm, self.training)
         return next_h, (next_h.unsqueeze(0), next_c.unsqueeze(0))
 
 
@@ -239,7 +252,7 @@ class LSTMSoftAttentionCore(nn.Module):
         z = _attention(self, pre_h, att_seq)
         G = linear([(xt, self.i2h), (pre_h, self.h2h), (z, self.z2h)], pre_h.shape[0], 4 * self.rnn_size)
         next_h, next_c = lstm_cell(G, _f32c(pre_c))
-        next_h = self.dropout(next_h)
+        next_h = _dropout(next_h, self.drop_prob_lm, self.training)
         return next_h, (next_h.unsqueeze(0), next_c.unsqueeze(0))
 
 
@@ -270,7 +283,7 @@ class LSTMSoftAttentionNoInputCore(nn.Module):
         z = _attention(self, pre_h, att_seq)
         G = linear([(pre_h, self.h2h), (z, self.z2h)], pre_h.shape[0], 4 * self.rnn_size)
         next_h, next_c = lstm_cell(G, _f32c(pre_c))
-        next_h = self.dropout(next_h)
+        next_h = _dropout(next_h, self.drop_prob_lm, self.training)
         return next_h, (next_h.unsqueeze(0), next_c.unsqueeze(0))
 
 
@@ -396,6 +409,13 @@ class RecurrentFusionModel(nn.Module):
     def _dropout_active(self, p):
         return self.training and p > 0
 
+    def _needs_tape(self):
+        """Gradient recording (or train-mode dropout) sends the call through training.py's per-op loop."""
+        if self._dropout_active(self.drop_prob_fusion) or self._dropout_active(self.drop_prob_reason) or \
+                self._dropout_active(self.drop_prob_lm):
+            return True
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+
     def _check_feats(self, fc_feats, att_feats, allow_host=False):
         J = self.num_feat_array
         if len(fc_feats) != J or len(att_feats) != J:
@@ -483,7 +503,7 @@ class RecurrentFusionModel(nn.Module):
         return logits, (h.unsqueeze(0), c.unsqueeze(0))
 
     def forward(self, fc_feats, att_feats, seq):  # :198-281
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) or self.ss_prob > 0:
+        if self._needs_tape() or self.ss_prob > 0:
             from . import training
             return training.forward_xe(self, fc_feats, att_feats, seq)
         self._inference_guard("forward")
@@ -510,7 +530,7 @@ class RecurrentFusionModel(nn.Module):
         temperature = opt.get("temperature", 1.0)
         if beam_size > 1:
             return self.sample_beam(fc_feats, att_feats, opt)
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+        if self._needs_tape():
             from . import training
             return training.sample_with_grad(self, fc_feats, att_feats, opt)
         self._inference_guard("sample")

@@ -1,0 +1,118 @@
+"""Gradient-enabled versions of the path (train.py:154-163, train_rl.py:160-191): the same Python loop
+structure as the reference's forward()/sample(), every operation an autograd.Function over our kernels."""
+from __future__ import annotations
+
+import torch
+
+from . import autograd as AG
+
+
+def thought_vectors(model, att, state_list):
+    """Stages 1-2 with the tape on (misc/RecurrentFusionModel.py:283-331)."""
+    J = model.num_feat_array
+    tv_list = [[] for _ in range(J)]
+    reason_mat = [[] for _ in range(J)]
+    for i in range(model.num_review_steps_0):
+        output_list, state_list = model.review_steps_individual[i](att, state_list)
+        for j in range(J):
+            tv_list[j].append(output_list[j])
+            reason_mat[j].append(AG.linear([(output_list[j], model.reason_linear_individual[j])]))
+    thought_vectors_ = [torch.stack(tv_list[j], 1).contiguous() for j in range(J)]
+    reason_pred = [AG.MaxOverStepsFn.apply(torch.stack(reason_mat[j], 1).contiguous()) for j in range(J)]
+    h = AG.MeanFn.apply(*[st[0][-1] for st in state_list])
+    c = AG.MeanFn.apply(*[st[1][-1] for st in state_list])
+    state = (h.unsqueeze(0), c.unsqueeze(0))
+    comb, reason_comb = [], []
+    for i in range(model.num_review_steps):
+        output, state = model.review_steps[i](thought_vectors_, state)
+        comb.append(output)
+        reason_comb.append(AG.linear([(output, model.reason_linear)]))
+    TVc = torch.stack(comb, 1).contiguous()
+    reason_pred.append(AG.MaxOverStepsFn.apply(torch.stack(reason_comb, 1).contiguous()))
+    return TVc, reason_pred, state
+
+
+def _step(model, it, TVc, state):
+    xt = AG.EmbedFn.apply(it, model.embed.weight)
+    output, state = model.decoder(xt, TVc, state)
+    lp = AG.LogSoftmaxFn.apply(AG.linear([(output, model.logit)]))
+    return lp, state
+
+
+def forward_xe(model, fc_feats, att_feats, seq):
+    """RecurrentFusionModel.forward with gradients (misc/RecurrentFusionModel.py:198-281)."""
+    fc, att, rows = model._check_feats(fc_feats, att_feats)
+    seq = seq.to(device=fc[0].device, dtype=torch.int64)
+    state_list = model.get_init_state(fc)
+    TVc, reason_pred, state = thought_vectors(model, att, state_list)
+    outputs = []
+    col_any = (seq != 0).any(dim=0).cpu().tolist()
+    for i in range(seq.size(1)):
+        it = seq[:, i].clone()
+        if i >= 1 and model.ss_prob > 0.0:                              # scheduled sampling (:260-270)
+            sample_mask = torch.rand(rows, device=it.device) < model.ss_prob
+            if bool(sample_mask.any()):
+                u = torch.rand(rows, device=it.device)
+                sampled, _ = AG.select_token(outputs[-1], uniforms=u)
+                it = torch.where(sample_mask, sampled, it)
+        if i >= 1 and not col_any[i]:                                   # :274-275
+            break
+        lp, state = _step(model, it, TVc, state)
+        outputs.append(lp)
+    return torch.stack(outputs, 1).contiguous(), [r.squeeze() for r in reason_pred]
+
+
+def sample_with_grad(model, fc_feats, att_feats, opt):
+    """RecurrentFusionModel.sample with gradients through the log-probs (train_rl.py:160;
+    misc/RecurrentFusionModel.py:545-658)."""
+    sample_max = opt.get("sample_max", 1)
+    temperature = opt.get("temperature", 1.0)
+    fc, att, rows = model._check_feats(fc_feats, att_feats)
+    dev = fc[0].device
+    L = model.seq_length
+    uniforms = None
+    if not sample_max:
+        uniforms = opt.get("uniforms")
+        if uniforms is None:
+            uniforms = torch.rand(rows, L, device=dev)
+        uniforms = uniforms.to(dev).float()
+    state_list = model.get_init_state(fc)
+    TVc, reason_pred, state = thought_vectors(model, att, state_list)
+    seq, slps, lp_all = [], [], []
+    lp = None
+    unfinished = None
+    for t in range(L + 1):
+        if t == 0:
+            it = torch.zeros(rows, dtype=torch.int64, device=dev)
+        else:
+            it, _ = AG.select_token(lp, uniforms=None if sample_max else uniforms[:, t - 1].contiguous(),
+                                    temperature=temperature)
+            s_lp = AG.GatherColsFn.apply(lp, it)
+        x_tok = it
+        if t >= 1:
+            unfinished = (it > 0) if t == 1 else unfinished & (it > 0)
+            if not bool(unfinished.any()):
+                break
+            seq.append(it * unfinished.to(it.dtype))
+            slps.append(s_lp)
+        lp, state = _step(model, x_tok, TVc, state)
+        lp_all.append(lp)
+    if not seq:
+        raise RuntimeError("sample(): every row emitted <eos> at t=1 (the reference fails here too)")
+    return (torch.stack(seq, 1), torch.stack(slps, 1), torch.stack(lp_all, 1).contiguous(),
+            [r.squeeze() for r in reason_pred])
+
+
+def xe_criterion(crit, log_prob, target, mask, top_pred, top_true, reason_weight):
+    eps = float(crit.label_smoothing_epsilon) if crit.use_label_smoothing else 0.0
+    terms = [AG.XeLossFn.apply(log_prob, target, mask, eps)]
+    for p in top_pred:
+        terms.append(AG.MarginFn.apply(p, top_true, reason_weight / len(top_pred)))
+    return AG.AddScalarsFn.apply(*terms)[0]
+
+
+def rl_criterion(crit, input, seq, reward, logprobs_all, entropy_reg, top_pred, top_true, reason_weight):
+    terms = [AG.RlLossFn.apply(input, seq, reward, logprobs_all, entropy_reg)]
+    for p in top_pred:
+        terms.append(AG.MarginFn.apply(p, top_true, reason_weight / len(top_pred)))
+    return AG.AddScalarsFn.apply(*terms)[0]

@@ -1,0 +1,123 @@
+"""GPU: the gradient path (autograd.Function wrappers over our forward/backward kernels) against
+autograd through the oracle (which is bit-identical to the reference, tests/golden/PIN_LOG.txt):
+XE loss with label smoothing (config 2's criterion) and the self-critical RL loss (config 4's)."""
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+from oracle import rfnet_oracle as O
+from tests._gpu_util import build_model, cuda_list, maxdiff
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_grads(sd, fn):
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    loss = fn(leaves)
+    loss.backward()
+    return float(loss), {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()}
+
+
+def _compare_grads(model, want, rel=2e-4):
+    worst = 0.0
+    for k, p in model.named_parameters():
+        g = p.grad if p.grad is not None else torch.zeros_like(p)
+        w = want[k]
+        scale = float(w.abs().max()) + 1e-6
+        err = maxdiff(g, w) / scale
+        worst = max(worst, err)
+        assert err <= rel or maxdiff(g, w) <= 1e-6, f"{k}: rel err {err:.3g} (scale {scale:.3g})"
+    return worst
+
+
+@pytest.mark.parametrize("J,rows,seed", [(1, 3, 0), (2, 4, 1), (3, 5, 2)])
+def test_xe_gradients_match_oracle(J, rows, seed):
+    cfg = O.tiny_config(J)
+    sd = O.make_state_dict(cfg, seed=40 + seed, init_range=0.5, logit_scale=3.0)
+    fc, att = O.make_inputs(cfg, rows, seed=seed)
+    labels, masks, top = O.make_labels(cfg, rows, seed=seed + 5)
+
+    def oracle_loss(p):
+        lp, rp = O.forward_xe(p, cfg, fc, att, labels)
+        return O.xe_loss(lp, labels[:, 1:], masks[:, 1:], rp, top, 10.0, 0.1)
+
+    want_loss, want = _oracle_grads(sd, oracle_loss)
+    from recurrent_fusion_network_b200.criteria import ReviewNetEnsembleCriterion
+    m = build_model(cfg, sd).train()
+    crit = ReviewNetEnsembleCriterion(SimpleNamespace(use_label_smoothing=1, label_smoothing_epsilon=0.1, use_cuda=1))
+    lp, rp = m(cuda_list(fc), cuda_list(att), labels.cuda())
+    assert lp.requires_grad
+    loss = crit(lp, labels[:, 1:].cuda(), masks[:, 1:].cuda(), rp, top.cuda(), 10.0)
+    loss.backward()
+    assert abs(float(loss) - want_loss) <= 1e-4 * max(1.0, abs(want_loss))
+    _compare_grads(m, want)
+
+
+def test_rl_gradients_match_oracle():
+    cfg = O.tiny_config(2)
+    sd = O.make_state_dict(cfg, seed=1250, init_range=0.5, logit_scale=3.0, eos_bias=0.8)
+    rows = 4
+    fc, att = O.make_inputs(cfg, rows, seed=8)
+    _, _, top = O.make_labels(cfg, rows, seed=3)
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        s0, *_ = O.sample(sd, cfg, fc, att, sample_max=1)
+    reward = torch.randn(rows, 1, generator=g).expand(rows, s0.shape[1]).contiguous()
+
+    def oracle_loss(p):
+        s, sl, la, rp = O.sample(p, cfg, fc, att, sample_max=1)
+        return O.rl_loss(sl, s, reward, la, 0.01, rp, top, 10.0)
+
+    want_loss, want = _oracle_grads(sd, oracle_loss)
+    from recurrent_fusion_network_b200.criteria import ReviewNetRewardCriterion
+    m = build_model(cfg, sd).train()
+    rl = ReviewNetRewardCriterion(SimpleNamespace(use_label_smoothing=0, label_smoothing_epsilon=0.1))
+    s, sl, la, rp = m.sample(cuda_list(fc), cuda_list(att), {"sample_max": 1})
+    assert torch.equal(s.cpu(), s0) and sl.requires_grad and la.requires_grad
+    loss = rl(sl, s, reward.cuda(), la, 0.01, rp, top.cuda(), 10.0, None, SimpleNamespace(use_ppo=0))
+    loss.backward()
+    assert abs(float(loss) - want_loss) <= 1e-4 * max(1.0, abs(want_loss))
+    _compare_grads(m, want)
+
+
+def test_xe_gradients_config1_size():
+    """Reference sizes (R = A = E = 512, 2048-d features, 9488-way vocab), single encoder, 4 rows."""
+    cfg = O.config1(49)
+    sd = O.make_state_dict(cfg, seed=1234)
+    rows = 4
+    fc, att = O.make_inputs(cfg, rows, seed=2)
+    labels, masks, top = O.make_labels(cfg, rows, seed=9)
+
+    def oracle_loss(p):
+        lp, rp = O.forward_xe(p, cfg, fc, att, labels)
+        return O.xe_loss(lp, labels[:, 1:], masks[:, 1:], rp, top, 10.0, 0.1)
+
+    torch.set_num_threads(16)
+    want_loss, want = _oracle_grads(sd, oracle_loss)
+    from recurrent_fusion_network_b200.criteria import ReviewNetEnsembleCriterion
+    m = build_model(cfg, sd).train()
+    crit = ReviewNetEnsembleCriterion(SimpleNamespace(use_label_smoothing=1, label_smoothing_epsilon=0.1, use_cuda=1))
+    lp, rp = m(cuda_list(fc), cuda_list(att), labels.cuda())
+    loss = crit(lp, labels[:, 1:].cuda(), masks[:, 1:].cuda(), rp, top.cuda(), 10.0)
+    loss.backward()
+    assert abs(float(loss) - want_loss) <= 1e-4 * max(1.0, abs(want_loss))
+    _compare_grads(m, want, rel=5e-4)
+
+
+def test_train_mode_dropout_runs_and_eval_matches_inference_path():
+    cfg = O.tiny_config(2)
+    sd = O.make_state_dict(cfg, seed=3, init_range=0.5)
+    fc, att = O.make_inputs(cfg, 4, seed=1)
+    labels, _, _ = O.make_labels(cfg, 4, seed=2)
+    m = build_model(cfg, sd, drop_prob_lm=0.3)
+    with torch.no_grad():
+        a, _ = m(cuda_list(fc), cuda_list(att), labels.cuda())     # eval: fused C path
+    m.train()
+    lp, _ = m(cuda_list(fc), cuda_list(att), labels.cuda())        # train: per-op tape with dropout
+    assert lp.shape == a.shape and lp.requires_grad
+    assert maxdiff(lp, a) > 1e-4                                   # dropout changed the outputs
+    assert maxdiff(lp.exp().sum(-1), torch.ones(lp.shape[:2])) <= 1e-4
+    m.eval()
+    b, _ = m(cuda_list(fc), cuda_list(att), labels.cuda())         # eval + grad: tape without dropout
+    assert maxdiff(a, b) <= 2e-5
