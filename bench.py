@@ -234,10 +234,19 @@ def run_ours(args):
             d2h_box[0] = seq_h.numel() * 8 + n_local * (4 + cap * L * 4 + cap * 4)
             return gather(seq, slp)
 
+        model.chunk_images = args.e2e_chunk
         ms_e2e, _, _ = timed(step_e2e, max(1, min(args.steps, args.e2e_steps)), max(1, min(args.warmup, 2)))
+        model.chunk_images = args.chunk
+        del hfc, hatt
         e2e = dict(value=round(args.images / (ms_e2e / 1e3), 2), unit=UNIT, ms_per_step=round(ms_e2e, 2),
                    h2d_bytes_per_step=int(h2d * world), d2h_bytes_per_step=int(d2h_box[0] * world),
                    api="model.sample(fc_feats, att_feats, {'beam_size': 3}) on pinned host tensors")
+
+    # ---- secondary metric: XE teacher-forced training tokens/s (BASELINE.json configs[1]) -----------
+    xe = None
+    if args.train_steps > 0:
+        torch.cuda.empty_cache()
+        xe = xe_train_bench(model, device, world, rank, args.train_steps, timed)
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on a bounded sample --------
     cpu = None
@@ -257,10 +266,63 @@ def run_ours(args):
                                 parity="fp32 mode; tests/test_gpu_parity.py vs the reference fixtures"),
                     clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=dominant,
                     roofline_attention=roof_attn, roofline_gemm=roof_gemm, kernel_time_shares=shares,
-                    cpu_baseline=cpu, seq_checksum=seq_checksum)
+                    cpu_baseline=cpu, xe_train=xe, seq_checksum=seq_checksum)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def xe_train_bench(model, device, world, rank, steps, timed):
+    """BASELINE.json configs[1]: XE teacher-forced training of the full model, rows 80 per GPU (16 images x
+    seq_per_img 5, features replicated as dataloader.py:251-252 does), label smoothing, drop_prob_lm 0.3,
+    fwd + bwd + gradient all-reduce (mean) + clamp 1 + Adam(5e-4, wd 1e-5)  (train.py:154-163)."""
+    from types import SimpleNamespace
+    from recurrent_fusion_network_b200 import dist as D
+    from recurrent_fusion_network_b200.criteria import ReviewNetEnsembleCriterion
+    g = torch.Generator(device=device).manual_seed(100 + rank)
+    imgs, spi, L = 16, 5, model.seq_length
+    rows = imgs * spi
+    fc = [torch.randn(imgs, f, device=device, generator=g).repeat_interleave(spi, 0) for (_, _, f) in ENC]
+    att = [torch.randn(imgs, n, d, device=device, generator=g).repeat_interleave(spi, 0) for (n, d, _) in ENC]
+    cg = torch.Generator().manual_seed(200 + rank)
+    labels = torch.zeros(rows, L + 2, dtype=torch.int64)
+    masks = torch.zeros(rows, L + 2)
+    for b in range(rows):
+        n = int(torch.randint(5, L + 1, (1,), generator=cg))
+        labels[b, 1:n + 1] = torch.randint(1, 9488, (n,), generator=cg)
+        masks[b, :n + 2] = 1.0
+    top = torch.full((rows, 1000), -1, dtype=torch.int64)
+    for b in range(rows):
+        n = int(torch.randint(2, 30, (1,), generator=cg))
+        top[b, :n] = torch.randperm(1000, generator=cg)[:n]
+    labels, masks, top = labels.to(device), masks.to(device), top.to(device)
+    tokens = float(masks[:, 1:].sum()) * world
+    model.train()
+    model.drop_prob_lm = model.decoder.drop_prob_lm = 0.3
+    crit = ReviewNetEnsembleCriterion(SimpleNamespace(use_label_smoothing=1, label_smoothing_epsilon=0.1, use_cuda=1))
+    params = [p for p in model.parameters()]
+    opt = torch.optim.Adam(params, lr=5e-4, weight_decay=1e-5)
+    loss_box = [None]
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        lp, rp = model(fc, att, labels)
+        loss = crit(lp, labels[:, 1:], masks[:, 1:], rp, top, 10.0)
+        loss.backward()
+        D.average_gradients(params, grad_clip=1.0)   # NCCL all-reduce (mean) then the reference's clamp
+        opt.step()
+        loss_box[0] = loss.detach()
+        return loss_box[0], loss_box[0]
+
+    ms, launches, _ = timed(step, steps, 2)
+    model.eval()
+    model.drop_prob_lm = model.decoder.drop_prob_lm = 0.0
+    for p in params:
+        p.grad = None
+    return dict(metric="xe_train_tokens_per_sec", value=round(tokens / (ms / 1e3), 1), unit="target tokens/s",
+                ms_per_step=round(ms, 2), rows_per_gpu=rows, tokens_per_step=int(tokens), loss=round(float(loss_box[0]), 4),
+                note="as written (80 replicated rows; no row de-duplication); per-op autograd over our kernels, "
+                     "backward GEMMs on the fp32 SIMT engine", gpu_launches_per_step=launches // max(1, steps))
 
 
 def args_dtype(args):
@@ -326,8 +388,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images", type=int, default=5000)
-    ap.add_argument("--chunk", type=int, default=1024, help="images per device call")
-    ap.add_argument("--gemm-mode", type=int, default=int(os.environ.get("RFN_GEMM_MODE", "0")))
+    ap.add_argument("--chunk", type=int, default=5000, help="images per device call when the features are resident")
+    ap.add_argument("--e2e-chunk", type=int, default=1000, help="images per device call when streaming host features")
+    ap.add_argument("--gemm-mode", type=int, default=int(os.environ.get("RFN_GEMM_MODE", "1")))
+    ap.add_argument("--train-steps", type=int, default=3, help="XE training steps timed for the secondary metric (0 = skip)")
     ap.add_argument("--cpu-images", type=int, default=24)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")

@@ -65,8 +65,9 @@ int rfn_check_device(void);
 int rfn_num_params(const rfn_dims* dims);
 /* number of kernels this library has launched in the calling process (bench accounting) */
 uint64_t rfn_launch_count(void);
-/* selects the contraction engine for the large GEMMs: 0 = fp32 SIMT FMA,
- * 1 = tcgen05 3xTF32 (fp32-equivalent), 2 = tcgen05 bf16.  Small-row problems always use SIMT. */
+/* selects the contraction engine for GEMMs with >= 128 rows: 0 = fp32 SIMT FMA, 1 = tcgen05 3xTF32 with
+ * chunked round-to-nearest accumulation (fp32-equivalent; the default), 2 = tcgen05 single-pass TF32
+ * (reduced precision).  Problems with fewer rows always use the SIMT kernel. */
 int rfn_set_gemm_mode(int mode);
 int rfn_get_gemm_mode(void);
 

@@ -111,8 +111,18 @@ def test_review_net_core_alias():
 
 
 # ---- path level vs the REAL reference's outputs (golden fixtures) -----------------------------------
+@pytest.fixture(params=[1, 0], ids=["tc3xtf32", "simt"])
+def gemm_mode(request):
+    """Run under both fp32-grade engines: tcgen05 3xTF32 (default) and fp32 SIMT."""
+    from recurrent_fusion_network_b200 import _capi
+    prev = _capi.lib().rfn_get_gemm_mode()
+    _capi.check(_capi.lib().rfn_set_gemm_mode(request.param))
+    yield request.param
+    _capi.check(_capi.lib().rfn_set_gemm_mode(prev))
+
+
 @pytest.mark.parametrize("name", G.TINY + G.FULL)
-def test_path_matches_reference_fixture(name):
+def test_path_matches_reference_fixture(name, gemm_mode):
     cfg, sd, fc, att, labels, masks, top_words, d = G.load_case(name)
     stride = int(d["stride"])
     m = build_model(cfg, sd)
