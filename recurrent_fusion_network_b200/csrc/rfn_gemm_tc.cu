@@ -43,6 +43,12 @@ struct TcArgs {
   float* score;     // (N / (BN/2), M) partial scores, one slice per worker column range
   int natt;         // attention locations per feature row: g row = m / natt
   int ldg;
+  // fused vocabulary epilogue (epi == 2): per (column slice, row) max, sum exp(x - max) and top-k of x = acc + bias
+  float* st_max;    // (slices, M)
+  float* st_sum;    // (slices, M)
+  float* st_val;    // (slices, M, ktop)
+  int32_t* st_idx;  // (slices, M, ktop)
+  int ktop;
 };
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------
@@ -141,7 +147,7 @@ struct TcSmem {
 // tcgen05.mma, so a K = 2048 chain drifts by 1.5e-5 relative).  The fp32-equivalent mode therefore
 // keeps tensor-core chains short: every CH k-blocks the MMA warp switches to the other of two TMEM
 // accumulators and the worker warps drain the finished one into round-to-nearest fp32 registers.
-template <int BN, int STAGES, int PASSES, int CH>
+template <int BN, int STAGES, int PASSES, int CH, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcArgs a) {
   using S = TcSmem<BN, PASSES>;
   constexpr int NWORK = 8;                       // worker warps 2..9
@@ -307,7 +313,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     // ----- epilogue -----
     const int m = m0 + wq * 32 + lane;
     const int nb = n0 + half * COLS;
-    if (a.epi == 0) {
+    if (EPI == 0) {
       if (m < a.M) {
         float* yr = a.y + (size_t)m * a.ldy;
 #pragma unroll
@@ -341,7 +347,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
           }
         }
       }
-    } else {
+    } else if (EPI == 1) {
       // fused additive-attention score (misc/AttentionModelCore.py:37-42):
       //   score[tile][m] = sum_{n in this thread's columns} w[n] * tanh(acc[m,n] + U_b[n] + g[m / natt, n])
       // partials are stored per column slice and summed in a fixed order by the attention kernel
@@ -363,6 +369,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       }
       const int slice = blockIdx.x * 2 + half;   // N / COLS slices in total
       if (m < a.M) a.score[(size_t)slice * a.M + m] = part;
+    } else {
+      // fused vocabulary epilogue: logits never reach HBM.  Per thread (row m, COLS columns): running max,
+      // sum exp(x - max) and the top-k logits with ties -> lower index; vocab_merge_kernel combines the slices.
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < COLS; ++i) {
+        const int n = nb + i;
+        if (n < a.N) {
+          acc[i] += a.bias[0] ? __ldg(a.bias[0] + n) : 0.f;
+          mx = fmaxf(mx, acc[i]);
+        } else {
+          acc[i] = -INFINITY;
+        }
+      }
+      float se = 0.f;
+#pragma unroll
+      for (int i = 0; i < COLS; ++i)
+        if (nb + i < a.N) se += expf(acc[i] - mx);
+      const int slice = blockIdx.x * 2 + half;
+      if (m < a.M) {
+        a.st_max[(size_t)slice * a.M + m] = mx;
+        a.st_sum[(size_t)slice * a.M + m] = se;
+      }
+      float pv = INFINITY;
+      int pi = -1;
+      for (int r = 0; r < a.ktop; ++r) {   // k selection passes over the register tile
+        float bv = -INFINITY;
+        int bi = 0x7fffffff;
+#pragma unroll
+        for (int i = 0; i < COLS; ++i) {
+          const float v = acc[i];
+          const int n = nb + i;
+          const bool after = (v < pv) || (v == pv && n > pi);
+          if (after && (v > bv || (v == bv && n < bi))) { bv = v; bi = n; }
+        }
+        if (m < a.M) {
+          a.st_val[((size_t)slice * a.M + m) * a.ktop + r] = bv;
+          a.st_idx[((size_t)slice * a.M + m) * a.ktop + r] = bi;
+        }
+        pv = bv; pi = bi;
+      }
     }
     tc_fence_before();
   }
@@ -412,19 +459,28 @@ static int make_map(CUtensorMap* tm, const float* base, int rows, int K, int ld,
   return RFN_OK;
 }
 
-template <int BN, int STAGES, int PASSES, int CH>
-static int launch_tc(const TcArgs& t, cudaStream_t st) {
+template <int BN, int STAGES, int PASSES, int CH, int EPI>
+static int launch_tc_epi(const TcArgs& t, cudaStream_t st) {
   using S = TcSmem<BN, PASSES>;
   const size_t smem = (size_t)STAGES * S::STAGE_BYTES + 1024 + 256;
   static bool configured = false;
   if (!configured) {
-    RFN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, PASSES, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RFN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, PASSES, CH, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   dim3 grid((t.N + BN - 1) / BN, (t.M + TC_BM - 1) / TC_BM);
-  gemm_tc_kernel<BN, STAGES, PASSES, CH><<<grid, TC_THREADS, smem, st>>>(t);
+  gemm_tc_kernel<BN, STAGES, PASSES, CH, EPI><<<grid, TC_THREADS, smem, st>>>(t);
   RFN_LAUNCH_CHECK();
   return RFN_OK;
+}
+
+template <int BN, int STAGES, int PASSES, int CH>
+static int launch_tc(const TcArgs& t, cudaStream_t st) {
+  if (t.epi == 0) return launch_tc_epi<BN, STAGES, PASSES, CH, 0>(t, st);
+  if (BN == 256 && t.epi == 1) return launch_tc_epi<256, STAGES, PASSES, CH, 1>(t, st);
+  if (BN == 256 && t.epi == 2) return launch_tc_epi<256, STAGES, PASSES, CH, 2>(t, st);
+  set_error("gemm_tc: fused epilogues need the 256-wide tile");
+  return RFN_ERR_INVALID;
 }
 
 bool gemm_tc_supported(const GemmArgs& a) {
@@ -461,6 +517,24 @@ int gemm_tc(const GemmArgs& a, int passes, const float* g, int ldg, const float*
   t.g = g; t.ldg = ldg; t.wv = wv; t.score = score; t.natt = natt > 0 ? natt : 1;
   if (passes == 3) return bn == 256 ? launch_tc<256, 2, 3, 4>(t, st) : launch_tc<128, 3, 3, 4>(t, st);
   return bn == 256 ? launch_tc<256, 4, 1, 1>(t, st) : launch_tc<128, 6, 1, 1>(t, st);
+}
+
+// logits GEMM with the fused vocabulary epilogue: returns per-slice statistics instead of logits
+int gemm_tc_vocab(const GemmArgs& a, int passes, float* st_max, float* st_sum, float* st_val, int32_t* st_idx, int ktop,
+                  cudaStream_t st) {
+  ProfScope prof__(TAG_GEMM_LOGIT, st);
+  RFN_CHECK_ARG(gemm_tc_supported(a) && a.nsrc == 1 && ktop >= 1 && ktop <= RFN_MAX_BEAM, "gemm_tc_vocab: unsupported arguments");
+  if (a.M == 0) return RFN_OK;
+  TcArgs t{};
+  t.nsrc = 1;
+  RFN_TRY(make_map(&t.tm_x[0], a.src[0].x, a.M, a.src[0].K, a.src[0].ldx, TC_BM));
+  RFN_TRY(make_map(&t.tm_w[0], a.src[0].w, a.N, a.src[0].K, a.src[0].ldw, 256));
+  t.K[0] = a.src[0].K;
+  t.bias[0] = a.src[0].bias;
+  t.M = a.M; t.N = a.N;
+  t.epi = 2;
+  t.st_max = st_max; t.st_sum = st_sum; t.st_val = st_val; t.st_idx = st_idx; t.ktop = ktop;
+  return passes == 3 ? launch_tc<256, 2, 3, 4>(t, st) : launch_tc<256, 4, 1, 1>(t, st);
 }
 
 }  // namespace rfn

@@ -89,6 +89,12 @@ int gemm_tc(const GemmArgs& a, int passes, const float* g, int ldg, const float*
             cudaStream_t st);
 int gemm_engine(const GemmArgs& a, int engine, cudaStream_t st);
 int tc_score_slices(int N);
+// logits GEMM whose epilogue keeps only per-(slice,row) max / sum-exp / top-k (slices = tc_score_slices(N))
+int gemm_tc_vocab(const GemmArgs& a, int passes, float* st_max, float* st_sum, float* st_val, int32_t* st_idx, int ktop,
+                  cudaStream_t st);
+// combines the slices: rowmax, log-sum-exp and the top-k LOG-PROBS with ties -> lower index
+int vocab_merge(const float* st_max, const float* st_sum, const float* st_val, const int32_t* st_idx, int slices, int rows,
+                int k, float* rowmax, float* logsum, float* top_val, int32_t* top_idx, cudaStream_t st);
 // dispatches on rfn_set_gemm_mode() and problem shape
 int gemm(const GemmArgs& a, cudaStream_t st);
 inline GemmArgs gemm1(const float* x, int ldx, const float* w, const float* bias, int K, float* y,

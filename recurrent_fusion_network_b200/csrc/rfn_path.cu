@@ -260,7 +260,8 @@ static int thought_vectors(const rfn_dims& d, const float* const* prm, const flo
 // ---- decoder ---------------------------------------------------------------------------------------
 struct DecWork {
   float *Pdec, *hA, *hB, *cA, *cB, *x, *g, *z, *G, *logits, *rowmax, *logsum, *top_val;
-  int32_t *top_idx, *tok, *src, *any;
+  float *st_max, *st_sum, *st_val;   // per-slice statistics of the fused logits epilogue
+  int32_t *top_idx, *tok, *src, *any, *st_idx;
   uint8_t* unfinished;
   BeamState bs;
 };
@@ -282,6 +283,11 @@ static size_t carve_dec(const rfn_dims& d, int rowsA, int rows, int beam, int n_
   const int k = std::max(1, beam);
   w.top_val = b.take<float>((size_t)rows * k);
   w.top_idx = b.take<int32_t>((size_t)rows * k);
+  const size_t sl = (size_t)tc_score_slices(V);
+  w.st_max = b.take<float>(sl * rows);
+  w.st_sum = b.take<float>(sl * rows);
+  w.st_val = b.take<float>(sl * rows * k);
+  w.st_idx = b.take<int32_t>(sl * rows * k);
   w.tok = b.take<int32_t>(rows);
   w.src = b.take<int32_t>(rows);
   w.any = b.take<int32_t>(L + 2);
@@ -311,9 +317,11 @@ static int decoder_prepare(const rfn_dims& d, const float* const* prm, const flo
 }
 
 // one LSTMSoftAttentionCore step + vocab projection  (misc/LSTMSoftAttentionCore.py:60-102, logit :349)
+// fuse_topk > 0: the vocab projection keeps only row max / log-sum-exp / top-k (tensor engine, fused epilogue)
+// and fills w.rowmax / w.logsum / w.top_val / w.top_idx; returns 1 through *fused when that path was taken.
 static int decoder_step(const rfn_dims& d, const float* const* prm, const float* TVc, const float* Pdec, int div,
                         const float* x, const float* hin, const float* cin, float* hout, float* cout, float* logits,
-                        DecWork& w, int rows, cudaStream_t st) {
+                        DecWork& w, int rows, cudaStream_t st, int fuse_topk = 0, int* fused = nullptr) {
   const PIdx ix(d);
   const int R = d.rnn_size, A = d.att_hid_size, E = d.input_encoding_size, S1 = d.num_review_steps, V = d.vocab_plus1;
   RFN_TRY(gemm(gemm1(hin, R, prm[ix.dec(8)], prm[ix.dec(9)], R, w.g, A, rows, A), st));
@@ -328,9 +336,18 @@ static int decoder_step(const rfn_dims& d, const float* const* prm, const float*
     RFN_TRY(gemm(ga, st));
   }
   RFN_TRY(lstm_cell(w.G, cin, hout, cout, nullptr, 0, nullptr, 0, rows, R, st));
+  if (fused) *fused = 0;
   if (logits) {
-    TagScope ts(TAG_GEMM_LOGIT);
-    RFN_TRY(gemm(gemm1(hout, R, prm[ix.logit(0)], prm[ix.logit(1)], R, logits, V, rows, V), st));
+    GemmArgs la = gemm1(hout, R, prm[ix.logit(0)], prm[ix.logit(1)], R, logits, V, rows, V);
+    if (fuse_topk > 0 && gemm_mode() >= 1 && rows >= 128 && gemm_tc_supported(la)) {
+      RFN_TRY(gemm_tc_vocab(la, gemm_mode() == 1 ? 3 : 1, w.st_max, w.st_sum, w.st_val, w.st_idx, fuse_topk, st));
+      RFN_TRY(vocab_merge(w.st_max, w.st_sum, w.st_val, w.st_idx, tc_score_slices(V), rows, fuse_topk, w.rowmax, w.logsum,
+                          w.top_val, w.top_idx, st));
+      if (fused) *fused = 1;
+    } else {
+      TagScope ts(TAG_GEMM_LOGIT);
+      RFN_TRY(gemm(la, st));
+    }
   }
   return RFN_OK;
 }
@@ -503,8 +520,9 @@ int rfn_decode_beam(const rfn_dims* dims, const float* const* params, const floa
       RFN_TRY(gather_rows(w.cA, w.src, 1, w.cB, rows, R, st));
     }
     RFN_TRY(embed_gather_i32(w.tok, params[ix.embed()], w.x, rows, E, V, st));                   // :517-521
-    RFN_TRY(decoder_step(d, params, TVc, w.Pdec, beam, w.x, w.hB, w.cB, w.hA, w.cA, w.logits, w, rows, st));
-    RFN_TRY(vocab_stats_topk(w.logits, V, rows, V, beam, w.rowmax, w.logsum, w.top_val, w.top_idx, st));  // :463, :527
+    int fused = 0;   // vocab projection + log_softmax statistics + top-beam in one kernel when the tensor engine runs
+    RFN_TRY(decoder_step(d, params, TVc, w.Pdec, beam, w.x, w.hB, w.cB, w.hA, w.cA, w.logits, w, rows, st, beam, &fused));
+    if (!fused) RFN_TRY(vocab_stats_topk(w.logits, V, rows, V, beam, w.rowmax, w.logsum, w.top_val, w.top_idx, st));  // :463, :527
   }
   return beam_finalize(w.bs, seq, seq_logprobs, done_seq, done_logps, done_p, n_done, st);
 }

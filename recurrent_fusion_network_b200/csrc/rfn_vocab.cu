@@ -189,6 +189,63 @@ int log_softmax_rows(const float* logits, int ld_in, float* lp, int ld_out, int 
   return RFN_OK;
 }
 
+// Merge of the fused logits epilogue's per-slice statistics (one warp per row): same outputs as
+// vocab_stats_topk_kernel, same association lp = (x - max) - log(sum).
+__global__ void __launch_bounds__(128)
+vocab_merge_kernel(const float* __restrict__ st_max, const float* __restrict__ st_sum, const float* __restrict__ st_val,
+                   const int32_t* __restrict__ st_idx, int slices, int rows, int k, float* __restrict__ rowmax,
+                   float* __restrict__ logsum, float* __restrict__ top_val, int32_t* __restrict__ top_idx) {
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float m = -INFINITY;
+  for (int s = lane; s < slices; s += 32) m = fmaxf(m, st_max[(size_t)s * rows + r]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float sum = 0.f;
+  for (int s = lane; s < slices; s += 32) {
+    const float ms = st_max[(size_t)s * rows + r];
+    if (ms > -INFINITY) sum += st_sum[(size_t)s * rows + r] * expf(ms - m);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float ls = logf(sum);
+  if (lane == 0) { rowmax[r] = m; logsum[r] = ls; }
+  float pv = INFINITY;
+  int pi = -1;
+  const int ncand = slices * k;
+  for (int round = 0; round < k; ++round) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int c = lane; c < ncand; c += 32) {
+      const int s = c / k, j = c % k;
+      const float v = st_val[((size_t)s * rows + r) * k + j];
+      const int i = st_idx[((size_t)s * rows + r) * k + j];
+      const bool after = (v < pv) || (v == pv && i > pi);
+      if (after && (v > bv || (v == bv && i < bi))) { bv = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) {
+      top_val[(size_t)r * k + round] = (bv - m) - ls;
+      top_idx[(size_t)r * k + round] = bi;
+    }
+    pv = bv; pi = bi;
+  }
+}
+int vocab_merge(const float* st_max, const float* st_sum, const float* st_val, const int32_t* st_idx, int slices, int rows,
+                int k, float* rowmax, float* logsum, float* top_val, int32_t* top_idx, cudaStream_t st) {
+  ProfScope prof__(TAG_VOCAB, st);
+  if (rows == 0) return RFN_OK;
+  vocab_merge_kernel<<<(rows + 3) / 4, 128, 0, st>>>(st_max, st_sum, st_val, st_idx, slices, rows, k, rowmax, logsum, top_val, top_idx);
+  RFN_LAUNCH_CHECK();
+  return RFN_OK;
+}
+
 // ---- sample(): token selection + bookkeeping (misc/RecurrentFusionModel.py:616-649) ------------
 // Greedy: it = argmax (top-1).  Multinomial: inverse CDF of p = exp(lp / temperature) in index
 // order against an externally supplied uniform, accumulated in fp64 like the oracle.

@@ -79,3 +79,33 @@ def test_stage1_with_fused_score_epilogue(mode, tol):
         assert maxdiff(st[0][0], st_o[0]) <= tol
     finally:
         _capi.lib().rfn_set_gemm_mode(0)
+
+
+def test_fused_vocab_epilogue_beam_matches_oracle_and_simt():
+    """>= 128 decoder rows: the logits GEMM runs on the tensor engine with the fused
+    log-softmax-statistics + top-k epilogue (logits never written); compare with the oracle (tiny vocab)
+    and with the fp32 SIMT engine (9488-way vocab)."""
+    from recurrent_fusion_network_b200 import _capi
+    cfg = O.tiny_config(2)
+    sd = O.make_state_dict(cfg, seed=1250, init_range=0.5, logit_scale=3.0, eos_bias=0.8)
+    fc, att = O.make_inputs(cfg, 50, seed=4)
+    m = build_model(cfg, sd)
+    with torch.no_grad():
+        seq, slp, ts, tp, _ = m.sample_beam(cuda_list(fc), cuda_list(att), {"beam_size": 3})
+        o = O.sample_beam(sd, cfg, fc, att, beam_size=3)
+    assert torch.equal(seq.cpu(), o[0]) and maxdiff(slp, o[1]) <= 1e-4
+    assert [t.shape for t in ts] == [t.shape for t in o[2]]
+
+    cfg = O.config1(49)
+    sd = O.make_state_dict(cfg, seed=1234, sharpen=True)
+    fc, att = O.make_inputs(cfg, 48, seed=6)
+    m = build_model(cfg, sd)
+    res = {}
+    for mode in (1, 0):
+        _capi.check(_capi.lib().rfn_set_gemm_mode(mode))
+        with torch.no_grad():
+            res[mode] = m.sample_beam(cuda_list(fc), cuda_list(att), {"beam_size": 3})
+    _capi.check(_capi.lib().rfn_set_gemm_mode(1))
+    same = (res[0][0] == res[1][0]).all(dim=1)
+    assert int((~same).sum()) <= 1, "tensor-engine and SIMT captions differ on more than a near-tie"
+    assert maxdiff(res[0][1][same], res[1][1][same]) <= 1e-4
