@@ -70,6 +70,10 @@ uint64_t rfn_launch_count(void);
  * (reduced precision).  Problems with fewer rows always use the SIMT kernel. */
 int rfn_set_gemm_mode(int mode);
 int rfn_get_gemm_mode(void);
+/* 1: tensor-engine GEMMs with >= 256 rows and columns run as 2-CTA clusters (tcgen05 cta_group::2,
+ * 256 x 256 tiles, operands split across the pair); 0: one CTA per 128 x 256 tile. */
+int rfn_set_tc_cluster(int on);
+int rfn_get_tc_cluster(void);
 
 /* 1 (default): the J independent encoder cells of a fusion step run on internal side streams forked
  * from / joined into the caller's stream; 0: everything is serialised on the caller's stream. */

@@ -50,6 +50,8 @@ _SIGNATURES = {
     "rfn_launch_count": (C.c_uint64, []),
     "rfn_set_gemm_mode": (_i, [_i]),
     "rfn_get_gemm_mode": (_i, []),
+    "rfn_set_tc_cluster": (_i, [_i]),
+    "rfn_get_tc_cluster": (_i, []),
     "rfn_set_concurrency": (_i, [_i]),
     "rfn_profile_enable": (_i, [_i]),
     "rfn_profile_num_tags": (_i, []),
@@ -120,6 +122,9 @@ def lib() -> C.CDLL:
         mode = os.environ.get("RFN_GEMM_MODE")
         if mode is not None:
             check(_lib.rfn_set_gemm_mode(int(mode)), "rfn_set_gemm_mode")
+        cl = os.environ.get("RFN_TC_CLUSTER")
+        if cl is not None:
+            check(_lib.rfn_set_tc_cluster(int(cl)), "rfn_set_tc_cluster")
     return _lib
 
 

@@ -17,124 +17,14 @@
 // exactly as torch stores them; ragged M / N / K edges are zero-filled by TMA.
 #include <cuda.h>
 
+#include <atomic>
+
 #include "rfn_internal.cuh"
+#include "rfn_tc_ptx.cuh"
+#include "rfn_tc_args.cuh"
 
 namespace rfn {
 
-constexpr int TC_BM = 128;
-constexpr int TC_BK = 32;                    // fp32 elements per 128-byte swizzled row
-constexpr int TC_A_BYTES = TC_BM * 128;      // 16 KB
-constexpr int TC_THREADS = 320;             // warp 0 TMA, warp 1 MMA, warps 2..9 workers
-
-struct TcArgs {
-  CUtensorMap tm_x[3];
-  CUtensorMap tm_w[3];
-  int K[3];
-  const float* bias[3];
-  int nsrc;
-  float* y;
-  int ldy;
-  int M, N;
-  int accumulate;
-  // fused attention-score epilogue (epi == 1)
-  int epi;
-  const float* g;   // (rows, ldg)   h_2_att_h(h)
-  const float* wv;  // (N)           att_h_2_out.weight
-  float* score;     // (N / (BN/2), M) partial scores, one slice per worker column range
-  int natt;         // attention locations per feature row: g row = m / natt
-  int ldg;
-  // fused vocabulary epilogue (epi == 2): per (column slice, row) max, sum exp(x - max) and top-k of x = acc + bias
-  float* st_max;    // (slices, M)
-  float* st_sum;    // (slices, M)
-  float* st_val;    // (slices, M, ktop)
-  int32_t* st_idx;  // (slices, M, ktop)
-  int ktop;
-};
-
-// ---- PTX wrappers ----------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t"
-      "}" ::"r"(bar), "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(tm), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem] (+)= A[smem] . B[smem]^T, TF32 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
-      "%24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// shared-memory matrix descriptor, K-major, SWIZZLE_128B: rows of 128 bytes, 8-row groups 1024 bytes
-// apart (SBO), version 1 (Blackwell), layout type 2.
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// instruction descriptor: D fp32, A/B tf32, both K-major, M = 128, N = BN
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int bn) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-}
 
 template <int BN, int PASSES>
 struct TcSmem {
@@ -440,7 +330,7 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2-D fp32 tensor map over a row-major (rows, K) matrix with leading dimension ld: box = 32 floats x box_rows
-static int make_map(CUtensorMap* tm, const float* base, int rows, int K, int ld, int box_rows) {
+int tc_make_map(CUtensorMap* tm, const float* base, int rows, int K, int ld, int box_rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -483,6 +373,10 @@ static int launch_tc(const TcArgs& t, cudaStream_t st) {
   return RFN_ERR_INVALID;
 }
 
+static std::atomic<int> g_tc_cluster{0};
+int launch_tc2(const TcArgs& t, int passes, cudaStream_t st);   // rfn_gemm_tc2.cu
+static bool use_cluster(const GemmArgs& a) { return g_tc_cluster.load() != 0 && a.N >= 256 && a.M >= 256; }
+
 bool gemm_tc_supported(const GemmArgs& a) {
   if (a.N % 4 != 0 || a.ldy % 4 != 0 || ((uintptr_t)a.y % 16) != 0) return false;
   for (int s = 0; s < a.nsrc; ++s) {
@@ -505,16 +399,20 @@ int gemm_tc(const GemmArgs& a, int passes, const float* g, int ldg, const float*
   if (a.M == 0) return RFN_OK;
   TcArgs t{};
   t.nsrc = a.nsrc;
-  const int bn = (score || a.N > 128) ? 256 : 128;
+  // 128 x 256 tiles unless that leaves most of the 148 SMs idle (few rows): then 128 x 128 doubles the CTA count
+  const long tiles256 = (long)((a.M + TC_BM - 1) / TC_BM) * ((a.N + 255) / 256);
+  const int bn = score ? 256 : ((a.N > 128 && tiles256 >= 148) ? 256 : 128);
+  const bool cluster = use_cluster(a) && bn == 256;   // 2-CTA pairs: each CTA lands 128 rows of W
   for (int s = 0; s < a.nsrc; ++s) {
-    RFN_TRY(make_map(&t.tm_x[s], a.src[s].x, a.M, a.src[s].K, a.src[s].ldx, TC_BM));
-    RFN_TRY(make_map(&t.tm_w[s], a.src[s].w, a.N, a.src[s].K, a.src[s].ldw, bn));
+    RFN_TRY(tc_make_map(&t.tm_x[s], a.src[s].x, a.M, a.src[s].K, a.src[s].ldx, TC_BM));
+    RFN_TRY(tc_make_map(&t.tm_w[s], a.src[s].w, a.N, a.src[s].K, a.src[s].ldw, cluster ? 128 : bn));
     t.K[s] = a.src[s].K;
     t.bias[s] = a.src[s].bias;
   }
   t.y = a.y; t.ldy = a.ldy; t.M = a.M; t.N = a.N; t.accumulate = a.accumulate;
   t.epi = score ? 1 : 0;
   t.g = g; t.ldg = ldg; t.wv = wv; t.score = score; t.natt = natt > 0 ? natt : 1;
+  if (cluster) return launch_tc2(t, passes, st);
   if (passes == 3) return bn == 256 ? launch_tc<256, 2, 3, 4>(t, st) : launch_tc<128, 3, 3, 4>(t, st);
   return bn == 256 ? launch_tc<256, 4, 1, 1>(t, st) : launch_tc<128, 6, 1, 1>(t, st);
 }
@@ -527,14 +425,22 @@ int gemm_tc_vocab(const GemmArgs& a, int passes, float* st_max, float* st_sum, f
   if (a.M == 0) return RFN_OK;
   TcArgs t{};
   t.nsrc = 1;
-  RFN_TRY(make_map(&t.tm_x[0], a.src[0].x, a.M, a.src[0].K, a.src[0].ldx, TC_BM));
-  RFN_TRY(make_map(&t.tm_w[0], a.src[0].w, a.N, a.src[0].K, a.src[0].ldw, 256));
+  const bool cluster = use_cluster(a);
+  RFN_TRY(tc_make_map(&t.tm_x[0], a.src[0].x, a.M, a.src[0].K, a.src[0].ldx, TC_BM));
+  RFN_TRY(tc_make_map(&t.tm_w[0], a.src[0].w, a.N, a.src[0].K, a.src[0].ldw, cluster ? 128 : 256));
   t.K[0] = a.src[0].K;
   t.bias[0] = a.src[0].bias;
   t.M = a.M; t.N = a.N;
   t.epi = 2;
   t.st_max = st_max; t.st_sum = st_sum; t.st_val = st_val; t.st_idx = st_idx; t.ktop = ktop;
+  if (cluster) return launch_tc2(t, passes, st);
   return passes == 3 ? launch_tc<256, 2, 3, 4>(t, st) : launch_tc<256, 4, 1, 1>(t, st);
 }
 
 }  // namespace rfn
+
+extern "C" int rfn_set_tc_cluster(int on) {
+  rfn::g_tc_cluster.store(on ? 1 : 0);
+  return RFN_OK;
+}
+extern "C" int rfn_get_tc_cluster(void) { return rfn::g_tc_cluster.load(); }

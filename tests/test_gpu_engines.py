@@ -109,3 +109,27 @@ def test_fused_vocab_epilogue_beam_matches_oracle_and_simt():
     same = (res[0][0] == res[1][0]).all(dim=1)
     assert int((~same).sum()) <= 1, "tensor-engine and SIMT captions differ on more than a near-tie"
     assert maxdiff(res[0][1][same], res[1][1][same]) <= 1e-4
+
+
+@pytest.fixture
+def tc_cluster():
+    from recurrent_fusion_network_b200 import _capi
+    _capi.check(_capi.lib().rfn_set_tc_cluster(1))
+    yield
+    _capi.check(_capi.lib().rfn_set_tc_cluster(0))
+
+
+@pytest.mark.parametrize("M,N,Ks", [(256, 256, [32]), (256, 512, [2048]), (1000, 2048, [2560, 1280]), (300, 9488, [512]),
+                                    (777, 260, [36, 64, 128])])
+@pytest.mark.parametrize("engine,tol", [(1, 3e-6), (2, 3e-3)])
+def test_two_cta_cluster_engine(tc_cluster, engine, tol, M, N, Ks):
+    """cta_group::2 pairs (256 x 256 tiles, operands split across the two CTAs)."""
+    g = torch.Generator().manual_seed(M + N)
+    xs = [torch.randn(M, k, generator=g) for k in Ks]
+    ws = [(torch.rand(N, k, generator=g) * 2 - 1) * 0.1 for k in Ks]
+    bs = [torch.randn(N, generator=g) for _ in Ks]
+    want = sum(x.double() @ w.double().t() + b.double() for x, w, b in zip(xs, ws, bs))
+    got = _linear_engine(engine, cuda_list(xs), cuda_list(ws), cuda_list(bs), M, N)
+    torch.cuda.synchronize()
+    scale = float(want.abs().max())
+    assert maxdiff(got, want) <= tol * scale
