@@ -261,6 +261,7 @@ def run_ours(args):
                                          f"{args.images} synthetic images sharded over {world} GPU(s)",
                                 images=args.images, images_per_gpu=n_local, beam=BEAM, seq_length=L, vocab=9487,
                                 chunk_images=args.chunk, gemm_mode=args.gemm_mode,
+                                tc_cluster=int(_capi.lib().rfn_get_tc_cluster()),
                                 weights="reference-style random init, seed 1234",
                                 l2="per-step inputs (3.15 MB/image fp32 features) exceed the 126 MB L2",
                                 parity="fp32 mode; tests/test_gpu_parity.py vs the reference fixtures"),

@@ -373,7 +373,7 @@ static int launch_tc(const TcArgs& t, cudaStream_t st) {
   return RFN_ERR_INVALID;
 }
 
-static std::atomic<int> g_tc_cluster{0};
+static std::atomic<int> g_tc_cluster{1};   // default: 2-CTA clusters for large tensor-engine GEMMs
 int launch_tc2(const TcArgs& t, int passes, cudaStream_t st);   // rfn_gemm_tc2.cu
 static bool use_cluster(const GemmArgs& a) { return g_tc_cluster.load() != 0 && a.N >= 256 && a.M >= 256; }
 
