@@ -292,3 +292,51 @@ def test_full_size_properties():
         assert bool((z[:, 1:] | ~z[:, :-1]).all())   # once a row emits 0 it stays 0
         first = O.sample(sd, cfg, [f[:2] for f in fc], [a[:2] for a in att])
         assert_tokens_match_with_tie_policy(s[:2, :first[0].shape[1]], first[0], first[2], "full greedy")
+
+
+# ---- edge cases ----------------------------------------------------------------------------------------
+def test_single_row_and_ragged_shapes():
+    """rows == 1 (the reference's .squeeze() collapses (1,K) reason_pred to (K,)), a batch that is not a
+    multiple of anything, and N_j == 1."""
+    cfg = O.RFNConfig(encoders=(O.Encoder(1, 16, 24), O.Encoder(7, 24, 16)), rnn_size=32, att_hid_size=16,
+                      input_encoding_size=24, vocab_size=59, seq_length=5, num_review_steps_0=2, num_review_steps=3,
+                      top_words_count=20)
+    sd = O.make_state_dict(cfg, seed=11, init_range=0.5, logit_scale=3.0, eos_bias=0.5)
+    m = build_model(cfg, sd)
+    for rows in (1, 13):
+        fc, att = O.make_inputs(cfg, rows, seed=rows)
+        labels, masks, top = O.make_labels(cfg, rows, seed=rows + 1)
+        with torch.no_grad():
+            lp, rp = m(cuda_list(fc), cuda_list(att), labels.cuda())
+            lp_o, rp_o = O.forward_xe(sd, cfg, fc, att, labels)
+            assert maxdiff(lp, lp_o) <= LP_TOL
+            assert rp[0].shape == ((cfg.top_words_count,) if rows == 1 else (rows, cfg.top_words_count))
+            bs, bl, ts, tp, _ = m.sample_beam(cuda_list(fc), cuda_list(att), {"beam_size": 3})
+            o = O.sample_beam(sd, cfg, fc, att, beam_size=3)
+            assert torch.equal(bs.cpu(), o[0]) and maxdiff(bl, o[1]) <= LP_TOL
+            try:
+                s, sl, la, _ = m.sample(cuda_list(fc), cuda_list(att), {"sample_max": 1})
+                so, slo, lao, _ = O.sample(sd, cfg, fc, att)
+                assert torch.equal(s.cpu(), so) and maxdiff(la, lao) <= LP_TOL
+            except RuntimeError:
+                with pytest.raises(RuntimeError):   # all rows emitted <eos> at t=1: the reference fails too
+                    O.sample(sd, cfg, fc, att)
+
+
+def test_max_beam_width_and_bad_arguments():
+    from recurrent_fusion_network_b200 import _capi
+    cfg = O.tiny_config(2)
+    sd = O.make_state_dict(cfg, seed=1247, init_range=0.5, logit_scale=3.0, eos_bias=0.8)
+    fc, att = O.make_inputs(cfg, 3, seed=8)
+    m = build_model(cfg, sd)
+    with torch.no_grad():
+        seq, slp, ts, tp, _ = m.sample_beam(cuda_list(fc), cuda_list(att), {"beam_size": 8})
+        o = O.sample_beam(sd, cfg, fc, att, beam_size=8)
+        assert torch.equal(seq.cpu(), o[0]) and maxdiff(slp, o[1]) <= LP_TOL
+        assert [t.shape for t in ts] == [t.shape for t in o[2]]
+        with pytest.raises(_capi.RfnError):
+            m.sample_beam(cuda_list(fc), cuda_list(att), {"beam_size": 9})
+        with pytest.raises(_capi.RfnError):
+            m.sample(cuda_list(fc)[:1], cuda_list(att), {})                      # wrong encoder count
+        with pytest.raises(_capi.RfnError):
+            m.sample(cuda_list(fc), [a[:, :-1] for a in cuda_list(att)], {})     # wrong att_num
