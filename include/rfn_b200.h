@@ -264,6 +264,10 @@ int rfn_select_token_f32(const float* lp, size_t ld, int rows, int V, const floa
 int rfn_gather_cols_f32(const float* x, size_t ld, const int64_t* idx, float* out, int rows, rfn_stream_t stream);
 int rfn_scatter_cols_f32(const float* dout, const int64_t* idx, float* dx, size_t ld, int rows, int V,
                          rfn_stream_t stream);
+/* out[r,:] = x[r / g, :] (each unique image row expanded to the g = seq_per_img replicas the loader feeds,
+ * dataloader.py:251-252) and its backward out[r,:] = sum_{i<g} x[r*g + i, :] */
+int rfn_expand_rows_f32(const float* x, int g, float* out, int rows_out, int R, rfn_stream_t stream);
+int rfn_group_sum_f32(const float* x, int g, float* out, int rows_out, int R, rfn_stream_t stream);
 /* gradients of the criteria w.r.t. their log-prob inputs (gout: device scalar, upstream gradient) */
 int rfn_xe_loss_bwd_f32(const int64_t* target, const float* mask, int ld_t, int rows, int T, int V, float eps,
                         const float* gout, float* dlp, rfn_stream_t stream);

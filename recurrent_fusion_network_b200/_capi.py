@@ -89,6 +89,8 @@ _SIGNATURES = {
     "rfn_select_token_f32": (_i, [_vp, _sz, _i, _i, _vp, _f, _vp, _vp, _vp]),
     "rfn_gather_cols_f32": (_i, [_vp, _sz, _vp, _vp, _i, _vp]),
     "rfn_scatter_cols_f32": (_i, [_vp, _vp, _vp, _sz, _i, _i, _vp]),
+    "rfn_expand_rows_f32": (_i, [_vp, _i, _vp, _i, _i, _vp]),
+    "rfn_group_sum_f32": (_i, [_vp, _i, _vp, _i, _i, _vp]),
     "rfn_xe_loss_bwd_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     "rfn_rl_loss_bwd_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
     "rfn_multilabel_margin_bwd_f32": (_i, [_vp, _vp, _i, _i, _f, _vp, _vp, _vp]),

@@ -290,6 +290,32 @@ def dropout(x, p, training, mask=None):
     return DropoutFn.apply(x, mask, 1.0 / (1.0 - p))
 
 
+class ExpandRowsFn(Function):
+    """Each unique image row -> g identical rows (the seq_per_img replicas, dataloader.py:251-252);
+    backward sums the replicas' gradients, so stages 1-2 run once per image."""
+
+    @staticmethod
+    def forward(ctx, x, g):
+        x = _c(x)
+        n = x.shape[0]
+        R = x[0].numel()
+        out = torch.empty((n * g,) + tuple(x.shape[1:]), dtype=torch.float32, device=x.device)
+        check(lib().rfn_expand_rows_f32(ptr(x), g, ptr(out), n * g, R, stream()), "rfn_expand_rows_f32")
+        ctx.g = g
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        dout = _c(dout)
+        g = ctx.g
+        n = dout.shape[0] // g
+        R = dout[0].numel()
+        dx = torch.empty((n,) + tuple(dout.shape[1:]), dtype=torch.float32, device=dout.device)
+        check(lib().rfn_group_sum_f32(ptr(dout), g, ptr(dx), n, R, stream()), "rfn_group_sum_f32")
+        return dx, None
+
+
 class GatherColsFn(Function):
     """logprobs.gather(1, it) (misc/RecurrentFusionModel.py:632)."""
 

@@ -465,6 +465,19 @@ __global__ void scatter_cols_kernel(const float* __restrict__ dout, const int64_
   for (int v = threadIdx.x; v < V; v += blockDim.x) dx[(size_t)r * ld + v] = (v == t) ? d : 0.f;
 }
 
+
+// ---- row replication (dataloader.py:251-252 repeats every image seq_per_img times) ---------------------
+// out[r, :] = sum_{i < g} x[r*g + i, :]   -- backward of expanding each unique row to g identical rows
+__global__ void group_sum_kernel(const float* __restrict__ x, float* __restrict__ out, int rows, int g, int R) {
+  const size_t total = (size_t)rows * R;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / R, k = i % R;
+    float s = 0.f;
+    for (int j = 0; j < g; ++j) s += x[(r * g + j) * R + k];
+    out[i] = s;
+  }
+}
+
 // ---- criteria gradients ------------------------------------------------------------------------------------
 // XE (misc/utils.py:161-184): dL/dlp[b,t,v] = -gout * mask[b,t]/rows * ((1-eps) 1[v == y] + eps/V)
 __global__ void __launch_bounds__(256)
@@ -648,6 +661,19 @@ int rfn_scatter_cols_f32(const float* dout, const int64_t* idx, float* dx, size_
   RFN_CHECK_ARG(dout && idx && dx, "rfn_scatter_cols_f32: null pointer");
   if (rows == 0) return RFN_OK;
   scatter_cols_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(dout, idx, dx, ld, V);
+  RFN_LAUNCH_CHECK();
+  return RFN_OK;
+}
+
+int rfn_expand_rows_f32(const float* x, int g, float* out, int rows_out, int R, rfn_stream_t stream) {
+  RFN_CHECK_ARG(x && out && g >= 1, "rfn_expand_rows_f32: bad arguments");
+  return gather_rows(x, nullptr, g, out, rows_out, R, (cudaStream_t)stream);
+}
+int rfn_group_sum_f32(const float* x, int g, float* out, int rows_out, int R, rfn_stream_t stream) {
+  RFN_CHECK_ARG(x && out && g >= 1, "rfn_group_sum_f32: bad arguments");
+  if (rows_out == 0) return RFN_OK;
+  const size_t total = (size_t)rows_out * R;
+  group_sum_kernel<<<(int)min((size_t)148 * 8, (total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, out, rows_out, g, R);
   RFN_LAUNCH_CHECK();
   return RFN_OK;
 }

@@ -330,6 +330,9 @@ class RecurrentFusionModel(nn.Module):
 
     #: images decoded per device call (bounds the workspace: logits are rows x 9488 floats)
     chunk_images = 1024
+    #: training only: set to seq_per_img (5) when the batch holds that many consecutive replicas of every image
+    #: (dataloader.py:251-252) and stage-1/2 dropout is 0; stages 1-2 then run once per image
+    dedup_rows = 1
 
     def __init__(self, opt):
         super().__init__()

@@ -32,6 +32,21 @@ def thought_vectors(model, att, state_list):
     return TVc, reason_pred, state
 
 
+def _stages(model, fc, att):
+    """get_init_state + thought vectors; with model.dedup_rows = g > 1 (rows are g consecutive replicas of each
+    image and no stage-1/2 dropout) the stages run on the unique rows only and their outputs are expanded."""
+    g = int(getattr(model, "dedup_rows", 1) or 1)
+    rows = fc[0].shape[0]
+    if g > 1 and rows % g == 0 and not (model._dropout_active(model.drop_prob_fusion) or
+                                        model._dropout_active(model.drop_prob_reason)):
+        fcu = [f[::g].contiguous() for f in fc]
+        attu = [a[::g].contiguous() for a in att]
+        TVc, reason_pred, (h, c) = thought_vectors(model, attu, model.get_init_state(fcu))
+        ex = lambda t: AG.ExpandRowsFn.apply(t, g)
+        return ex(TVc), [ex(r) for r in reason_pred], (ex(h[0]).unsqueeze(0), ex(c[0]).unsqueeze(0))
+    return thought_vectors(model, att, model.get_init_state(fc))
+
+
 def _step(model, it, TVc, state):
     xt = AG.EmbedFn.apply(it, model.embed.weight)
     output, state = model.decoder(xt, TVc, state)
@@ -43,8 +58,7 @@ def forward_xe(model, fc_feats, att_feats, seq):
     """RecurrentFusionModel.forward with gradients (misc/RecurrentFusionModel.py:198-281)."""
     fc, att, rows = model._check_feats(fc_feats, att_feats)
     seq = seq.to(device=fc[0].device, dtype=torch.int64)
-    state_list = model.get_init_state(fc)
-    TVc, reason_pred, state = thought_vectors(model, att, state_list)
+    TVc, reason_pred, state = _stages(model, fc, att)
     outputs = []
     col_any = (seq != 0).any(dim=0).cpu().tolist()
     for i in range(seq.size(1)):
@@ -76,8 +90,7 @@ def sample_with_grad(model, fc_feats, att_feats, opt):
         if uniforms is None:
             uniforms = torch.rand(rows, L, device=dev)
         uniforms = uniforms.to(dev).float()
-    state_list = model.get_init_state(fc)
-    TVc, reason_pred, state = thought_vectors(model, att, state_list)
+    TVc, reason_pred, state = _stages(model, fc, att)
     seq, slps, lp_all = [], [], []
     lp = None
     unfinished = None

@@ -121,3 +121,28 @@ def test_train_mode_dropout_runs_and_eval_matches_inference_path():
     m.eval()
     b, _ = m(cuda_list(fc), cuda_list(att), labels.cuda())         # eval + grad: tape without dropout
     assert maxdiff(a, b) <= 2e-5
+
+
+def test_row_deduplication_gives_the_same_gradients():
+    """seq_per_img replicas (dataloader.py:251-252): stages 1-2 once per image == as-written."""
+    cfg = O.tiny_config(2)
+    sd = O.make_state_dict(cfg, seed=77, init_range=0.5, logit_scale=3.0)
+    g, imgs = 5, 3
+    fc, att = O.make_inputs(cfg, imgs, seed=4)
+    fc = [f.repeat_interleave(g, 0) for f in fc]
+    att = [a.repeat_interleave(g, 0) for a in att]
+    labels, masks, top = O.make_labels(cfg, imgs * g, seed=6)
+    from recurrent_fusion_network_b200.criteria import ReviewNetEnsembleCriterion
+    crit = ReviewNetEnsembleCriterion(SimpleNamespace(use_label_smoothing=1, label_smoothing_epsilon=0.1, use_cuda=1))
+    grads = {}
+    for dedup in (1, g):
+        m = build_model(cfg, sd).train()
+        m.dedup_rows = dedup
+        lp, rp = m(cuda_list(fc), cuda_list(att), labels.cuda())
+        loss = crit(lp, labels[:, 1:].cuda(), masks[:, 1:].cuda(), rp, top.cuda(), 10.0)
+        loss.backward()
+        grads[dedup] = ({k: p.grad.clone() for k, p in m.named_parameters()}, float(loss))
+    assert abs(grads[1][1] - grads[g][1]) <= 1e-5 * max(1.0, abs(grads[1][1]))
+    for k in grads[1][0]:
+        a, b = grads[1][0][k], grads[g][0][k]
+        assert maxdiff(a, b) <= 2e-5 * (float(a.abs().max()) + 1e-6) + 1e-7, k
