@@ -74,6 +74,9 @@ int rfn_get_gemm_mode(void);
  * 256 x 256 tiles, operands split across the pair); 0: one CTA per 128 x 256 tile. */
 int rfn_set_tc_cluster(int on);
 int rfn_get_tc_cluster(void);
+/* Debugging aid: device buffer receiving 8 clock64() stamps per CTA of the 2-CTA GEMM kernel
+ * (start, init done, first MMA, last MMA, last drain, epilogue done, exit); NULL switches it off. */
+int rfn_debug_set_timeline(long long* d_buf);
 
 /* 1 (default): the J independent encoder cells of a fusion step run on internal side streams forked
  * from / joined into the caller's stream; 0: everything is serialised on the caller's stream. */

@@ -21,6 +21,7 @@
 
 #include "rfn_internal.cuh"
 #include "rfn_tc_ptx.cuh"
+#include "rfn_tc_epilogue.cuh"
 #include "rfn_tc_args.cuh"
 
 namespace rfn {
@@ -56,6 +57,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   uint64_t* cfull = bars + 3 * STAGES;   // [2] accumulator chunk complete
   uint64_t* drained = cfull + 2;         // [2] accumulator buffer drained into registers
   uint32_t* tmem_slot = (uint32_t*)(drained + 2);
+  float* s_bias = (float*)((uint8_t*)bars + 512);   // [BN] bias summed over the sources (16-byte aligned)
+  float* s_wv = s_bias + 256;                // [BN] att_h_2_out weights (score epilogue)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * TC_BM;
@@ -156,6 +159,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     float acc[COLS];
 #pragma unroll
     for (int i = 0; i < COLS; ++i) acc[i] = 0.f;
+    tc_stage_bias<BN>(a, n0, wt, s_bias, EPI == 1 ? s_wv : nullptr);
 
     auto drain = [&](int d) {
       const int b = d & 1;
@@ -204,39 +208,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     const int m = m0 + wq * 32 + lane;
     const int nb = n0 + half * COLS;
     if (EPI == 0) {
-      if (m < a.M) {
-        float* yr = a.y + (size_t)m * a.ldy;
-#pragma unroll
-        for (int q = 0; q < COLS / 4; ++q) {
-          const int n = nb + q * 4;
-          if (n + 3 < a.N) {
-            float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int s = 0; s < a.nsrc; ++s)
-              if (a.bias[s]) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(a.bias[s] + n));
-                bsum.x += t.x; bsum.y += t.y; bsum.z += t.z; bsum.w += t.w;
-              }
-            float4 o = make_float4(acc[q * 4] + bsum.x, acc[q * 4 + 1] + bsum.y, acc[q * 4 + 2] + bsum.z, acc[q * 4 + 3] + bsum.w);
-            if (a.accumulate) {
-              const float4 t = *reinterpret_cast<const float4*>(yr + n);
-              o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
-            }
-            *reinterpret_cast<float4*>(yr + n) = o;
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (n + e < a.N) {
-                float bs = 0.f;
-                for (int s = 0; s < a.nsrc; ++s)
-                  if (a.bias[s]) bs += __ldg(a.bias[s] + n + e);
-                float o = acc[q * 4 + e] + bs;
-                if (a.accumulate) o += yr[n + e];
-                yr[n + e] = o;
-              }
-            }
-          }
-        }
-      }
+      // all MMAs have retired (last chunk drained), so the operand ring is free: stage the tile through it
+      float* stage = reinterpret_cast<float*>(smem) + (size_t)(warp - 2) * 32 * (COLS + 4);
+      tc_epilogue_store<COLS>(acc, stage, a, m0 + wq * 32, nb, lane, s_bias + half * COLS);
     } else if (EPI == 1) {
       // fused additive-attention score (misc/AttentionModelCore.py:37-42):
       //   score[tile][m] = sum_{n in this thread's columns} w[n] * tanh(acc[m,n] + U_b[n] + g[m / natt, n])
@@ -248,9 +222,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       for (int q = 0; q < COLS / 4; ++q) {
         const int n = nb + q * 4;
         if (n + 3 < a.N) {
-          const float4 b4 = a.bias[0] ? __ldg(reinterpret_cast<const float4*>(a.bias[0] + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + half * COLS + q * 4);
           const float4 gg = *reinterpret_cast<const float4*>(gr + n);
-          const float4 ww = __ldg(reinterpret_cast<const float4*>(a.wv + n));
+          const float4 ww = *reinterpret_cast<const float4*>(s_wv + half * COLS + q * 4);
           part = fmaf(ww.x, tanhf(acc[q * 4 + 0] + b4.x + gg.x), part);
           part = fmaf(ww.y, tanhf(acc[q * 4 + 1] + b4.y + gg.y), part);
           part = fmaf(ww.z, tanhf(acc[q * 4 + 2] + b4.z + gg.z), part);
@@ -267,7 +241,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       for (int i = 0; i < COLS; ++i) {
         const int n = nb + i;
         if (n < a.N) {
-          acc[i] += a.bias[0] ? __ldg(a.bias[0] + n) : 0.f;
+          acc[i] += s_bias[half * COLS + i];
           mx = fmaxf(mx, acc[i]);
         } else {
           acc[i] = -INFINITY;
@@ -352,7 +326,7 @@ int tc_make_map(CUtensorMap* tm, const float* base, int rows, int K, int ld, int
 template <int BN, int STAGES, int PASSES, int CH, int EPI>
 static int launch_tc_epi(const TcArgs& t, cudaStream_t st) {
   using S = TcSmem<BN, PASSES>;
-  const size_t smem = (size_t)STAGES * S::STAGE_BYTES + 1024 + 256;
+  const size_t smem = (size_t)STAGES * S::STAGE_BYTES + 1024 + 4096;
   static bool configured = false;
   if (!configured) {
     RFN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, PASSES, CH, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -373,6 +347,7 @@ static int launch_tc(const TcArgs& t, cudaStream_t st) {
   return RFN_ERR_INVALID;
 }
 
+static std::atomic<long long*> g_tc_dbg{nullptr};
 static std::atomic<int> g_tc_cluster{1};   // default: 2-CTA clusters for large tensor-engine GEMMs
 int launch_tc2(const TcArgs& t, int passes, cudaStream_t st);   // rfn_gemm_tc2.cu
 static bool use_cluster(const GemmArgs& a) { return g_tc_cluster.load() != 0 && a.N >= 256 && a.M >= 256; }
@@ -412,6 +387,7 @@ int gemm_tc(const GemmArgs& a, int passes, const float* g, int ldg, const float*
   t.y = a.y; t.ldy = a.ldy; t.M = a.M; t.N = a.N; t.accumulate = a.accumulate;
   t.epi = score ? 1 : 0;
   t.g = g; t.ldg = ldg; t.wv = wv; t.score = score; t.natt = natt > 0 ? natt : 1;
+  t.dbg = g_tc_dbg.load();
   if (cluster) return launch_tc2(t, passes, st);
   if (passes == 3) return bn == 256 ? launch_tc<256, 2, 3, 4>(t, st) : launch_tc<128, 3, 3, 4>(t, st);
   return bn == 256 ? launch_tc<256, 4, 1, 1>(t, st) : launch_tc<128, 6, 1, 1>(t, st);
@@ -444,3 +420,8 @@ extern "C" int rfn_set_tc_cluster(int on) {
   return RFN_OK;
 }
 extern "C" int rfn_get_tc_cluster(void) { return rfn::g_tc_cluster.load(); }
+// debugging aid: device buffer of 8 clock64 stamps per CTA filled by the 2-CTA kernel (NULL = off)
+extern "C" int rfn_debug_set_timeline(long long* d_buf) {
+  rfn::g_tc_dbg.store(d_buf);
+  return RFN_OK;
+}

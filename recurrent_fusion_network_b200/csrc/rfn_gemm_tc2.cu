@@ -18,6 +18,7 @@
 #include "rfn_internal.cuh"
 #include "rfn_tc_args.cuh"
 #include "rfn_tc_ptx.cuh"
+#include "rfn_tc_epilogue.cuh"
 
 namespace rfn {
 
@@ -43,8 +44,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc2_kernel(const __grid_co
   uint64_t* cfull = bars + 3 * STAGES;   // [2] both: accumulator chunk complete
   uint64_t* drained = cfull + 2;         // [2] leader: both halves drained
   uint32_t* tmem_slot = (uint32_t*)(drained + 2);
+  float* s_bias = (float*)((uint8_t*)bars + 512);   // [BN] bias summed over the sources (16-byte aligned)
+  float* s_wv = s_bias + 256;                // [BN] att_h_2_out weights (score epilogue)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long* dbg = a.dbg ? a.dbg + (size_t)blockIdx.x * 8 : nullptr;
+  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
   const uint32_t rank = cluster_ctarank();
   const bool leader = (rank == 0);
   const int cid = blockIdx.x >> 1;
@@ -74,6 +79,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc2_kernel(const __grid_co
   cluster_sync_all();   // both CTAs' barriers are initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
   if (warp == 0) {
     // ===================== TMA producer (each CTA loads its own half) =====================
@@ -106,6 +112,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc2_kernel(const __grid_co
         if (DRAIN && chunk_start && c >= 2) mbar_wait(smem_u32(&drained[b]), (uint32_t)((c >> 1) - 1) & 1u);
         mbar_wait(smem_u32(&ready[st]), ph);
         tc_fence_after();
+        if (dbg && lane == 0) { if (it == 0) dbg[2] = clock64(); if (it == total_kb - 1) dbg[3] = clock64(); }
         if (lane == 0) {
           const uint32_t td = tmem_base + (uint32_t)(b * T2_BN);
           const uint32_t sa = smem_u32(smem + st * STAGE_BYTES);
@@ -138,6 +145,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc2_kernel(const __grid_co
     float acc[COLS];
 #pragma unroll
     for (int i = 0; i < COLS; ++i) acc[i] = 0.f;
+    tc_stage_bias<T2_BN>(a, n0, wt, s_bias, EPI == 1 ? s_wv : nullptr);
 
     auto signal = [&](uint64_t* bar) {   // arrive on the LEADER's barrier
       if (leader) mbar_arrive(smem_u32(bar)); else mbar_arrive_remote(smem_u32(bar), 0);
@@ -187,44 +195,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc2_kernel(const __grid_co
         while (next_drain < nchunk && min((next_drain + 1) * CH, total_kb) - 1 <= it - STAGES) drain(next_drain++);
     }
     while (next_drain < nchunk) drain(next_drain++);
+    if (dbg && threadIdx.x == 64) dbg[4] = clock64();
 
     // ----- epilogue (identical to the 1-CTA kernel; this CTA owns rows m0 .. m0+127) -----
     const int m = m0 + wq * 32 + lane;
     const int nb = n0 + half * COLS;
     if (EPI == 0) {
-      if (m < a.M) {
-        float* yr = a.y + (size_t)m * a.ldy;
-#pragma unroll
-        for (int q = 0; q < COLS / 4; ++q) {
-          const int n = nb + q * 4;
-          if (n + 3 < a.N) {
-            float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int s = 0; s < a.nsrc; ++s)
-              if (a.bias[s]) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(a.bias[s] + n));
-                bsum.x += t.x; bsum.y += t.y; bsum.z += t.z; bsum.w += t.w;
-              }
-            float4 o = make_float4(acc[q * 4] + bsum.x, acc[q * 4 + 1] + bsum.y, acc[q * 4 + 2] + bsum.z, acc[q * 4 + 3] + bsum.w);
-            if (a.accumulate) {
-              const float4 t = *reinterpret_cast<const float4*>(yr + n);
-              o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
-            }
-            *reinterpret_cast<float4*>(yr + n) = o;
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (n + e < a.N) {
-                float bs = 0.f;
-                for (int s = 0; s < a.nsrc; ++s)
-                  if (a.bias[s]) bs += __ldg(a.bias[s] + n + e);
-                float o = acc[q * 4 + e] + bs;
-                if (a.accumulate) o += yr[n + e];
-                yr[n + e] = o;
-              }
-            }
-          }
-        }
-      }
+      // all MMAs have retired (last chunk drained), so the operand ring is free: stage the tile through it
+      float* stage = reinterpret_cast<float*>(smem) + (size_t)(warp - 2) * 32 * (COLS + 4);
+      tc_epilogue_store<COLS>(acc, stage, a, m0 + wq * 32, nb, lane, s_bias + half * COLS);
     } else if (EPI == 1) {
       const int mg = (m < a.M ? m : a.M - 1) / a.natt;
       const float* gr = a.g + (size_t)mg * a.ldg;
@@ -233,9 +212,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc2_kernel(const __grid_co
       for (int q = 0; q < COLS / 4; ++q) {
         const int n = nb + q * 4;
         if (n + 3 < a.N) {
-          const float4 b4 = a.bias[0] ? __ldg(reinterpret_cast<const float4*>(a.bias[0] + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + half * COLS + q * 4);
           const float4 gg = *reinterpret_cast<const float4*>(gr + n);
-          const float4 ww = __ldg(reinterpret_cast<const float4*>(a.wv + n));
+          const float4 ww = *reinterpret_cast<const float4*>(s_wv + half * COLS + q * 4);
           part = fmaf(ww.x, tanhf(acc[q * 4 + 0] + b4.x + gg.x), part);
           part = fmaf(ww.y, tanhf(acc[q * 4 + 1] + b4.y + gg.y), part);
           part = fmaf(ww.z, tanhf(acc[q * 4 + 2] + b4.z + gg.z), part);
@@ -250,7 +229,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc2_kernel(const __grid_co
       for (int i = 0; i < COLS; ++i) {
         const int n = nb + i;
         if (n < a.N) {
-          acc[i] += a.bias[0] ? __ldg(a.bias[0] + n) : 0.f;
+          acc[i] += s_bias[half * COLS + i];
           mx = fmaxf(mx, acc[i]);
         } else {
           acc[i] = -INFINITY;
@@ -285,6 +264,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc2_kernel(const __grid_co
       }
     }
     tc_fence_before();
+    if (dbg && threadIdx.x == 64) dbg[5] = clock64();
   }
   __syncthreads();
   cluster_sync_all();   // the peer may still be signalling our barriers / the leader reading our smem until here
@@ -292,12 +272,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc2_kernel(const __grid_co
     tc_fence_after();
     tmem_dealloc2(tmem_base, TMEM_COLS);
   }
+  if (dbg && threadIdx.x == 32) dbg[6] = clock64();
 }
 
 template <int STAGES, int PASSES, int CH, int EPI>
 static int launch_tc2_epi(const TcArgs& t, cudaStream_t st) {
   constexpr int STAGE_BYTES = T2_TILE_BYTES * (PASSES == 3 ? 2 : 1);
-  const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
+  const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024 + 4096;
   static bool configured = false;
   if (!configured) {
     RFN_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<STAGES, PASSES, CH, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

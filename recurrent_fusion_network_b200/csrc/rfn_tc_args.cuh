@@ -30,6 +30,9 @@ struct TcArgs {
   float* st_val;    // (slices, M, ktop)
   int32_t* st_idx;  // (slices, M, ktop)
   int ktop;
+  // optional per-CTA timeline stamps (clock64): [cta][8] = start, init done, first MMA issue, last MMA issue,
+  // last chunk drained, epilogue done, exit
+  long long* dbg;
 };
 
 // host helpers (rfn_gemm_tc.cu)
