@@ -215,20 +215,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       // fused additive-attention score (misc/AttentionModelCore.py:37-42):
       //   score[tile][m] = sum_{n in this thread's columns} w[n] * tanh(acc[m,n] + U_b[n] + g[m / natt, n])
       // partials are stored per column slice and summed in a fixed order by the attention kernel
+      // g rows (one per image) are staged through the dead operand ring: a warp's 32 consecutive rows span
+      // mg_first .. mg_last; reading g straight from global memory cost one L2 round trip per float4
+      // (registers are full of accumulators, so the loads cannot be hoisted) -- ~10k cycles per tile.
       const int mg = (m < a.M ? m : a.M - 1) / a.natt;
-      const float* gr = a.g + (size_t)mg * a.ldg;
+      const int mg_first = __shfl_sync(0xffffffffu, mg, 0);
+      const int nslots = __shfl_sync(0xffffffffu, mg, 31) - mg_first + 1;
+      float* gst = reinterpret_cast<float*>(smem) + (size_t)(warp - 2) * 32 * COLS;
+      for (int sl = 0; sl < nslots; ++sl) {
+#pragma unroll
+        for (int c = lane * 4; c < COLS; c += 128) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (nb + c + 3 < a.N) v = *reinterpret_cast<const float4*>(a.g + (size_t)(mg_first + sl) * a.ldg + nb + c);
+          *reinterpret_cast<float4*>(gst + sl * COLS + c) = v;
+        }
+      }
+      __syncwarp();
+      const float* gr = gst + (mg - mg_first) * COLS;
       float part = 0.f;
 #pragma unroll
       for (int q = 0; q < COLS / 4; ++q) {
         const int n = nb + q * 4;
         if (n + 3 < a.N) {
           const float4 b4 = *reinterpret_cast<const float4*>(s_bias + half * COLS + q * 4);
-          const float4 gg = *reinterpret_cast<const float4*>(gr + n);
+          const float4 gg = *reinterpret_cast<const float4*>(gr + q * 4);
           const float4 ww = *reinterpret_cast<const float4*>(s_wv + half * COLS + q * 4);
-          part = fmaf(ww.x, tanhf(acc[q * 4 + 0] + b4.x + gg.x), part);
-          part = fmaf(ww.y, tanhf(acc[q * 4 + 1] + b4.y + gg.y), part);
-          part = fmaf(ww.z, tanhf(acc[q * 4 + 2] + b4.z + gg.z), part);
-          part = fmaf(ww.w, tanhf(acc[q * 4 + 3] + b4.w + gg.w), part);
+          part = fmaf(ww.x, tc_tanh(acc[q * 4 + 0] + b4.x + gg.x), part);
+          part = fmaf(ww.y, tc_tanh(acc[q * 4 + 1] + b4.y + gg.y), part);
+          part = fmaf(ww.z, tc_tanh(acc[q * 4 + 2] + b4.z + gg.z), part);
+          part = fmaf(ww.w, tc_tanh(acc[q * 4 + 3] + b4.w + gg.w), part);
         }
       }
       const int slice = blockIdx.x * 2 + half;   // N / COLS slices in total
@@ -409,6 +424,7 @@ int gemm_tc_vocab(const GemmArgs& a, int passes, float* st_max, float* st_sum, f
   t.M = a.M; t.N = a.N;
   t.epi = 2;
   t.st_max = st_max; t.st_sum = st_sum; t.st_val = st_val; t.st_idx = st_idx; t.ktop = ktop;
+  t.dbg = g_tc_dbg.load();
   if (cluster) return launch_tc2(t, passes, st);
   return passes == 3 ? launch_tc<256, 2, 3, 4>(t, st) : launch_tc<256, 4, 1, 1>(t, st);
 }

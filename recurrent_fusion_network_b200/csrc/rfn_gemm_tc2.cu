@@ -205,20 +205,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc2_kernel(const __grid_co
       float* stage = reinterpret_cast<float*>(smem) + (size_t)(warp - 2) * 32 * (COLS + 4);
       tc_epilogue_store<COLS>(acc, stage, a, m0 + wq * 32, nb, lane, s_bias + half * COLS);
     } else if (EPI == 1) {
+      // g rows (one per image) are staged through the dead operand ring: a warp's 32 consecutive rows span
+      // mg_first .. mg_last; reading g straight from global memory cost one L2 round trip per float4
+      // (registers are full of accumulators, so the loads cannot be hoisted) -- ~10k cycles per tile.
       const int mg = (m < a.M ? m : a.M - 1) / a.natt;
-      const float* gr = a.g + (size_t)mg * a.ldg;
+      const int mg_first = __shfl_sync(0xffffffffu, mg, 0);
+      const int nslots = __shfl_sync(0xffffffffu, mg, 31) - mg_first + 1;
+      float* gst = reinterpret_cast<float*>(smem) + (size_t)(warp - 2) * 32 * COLS;
+      for (int sl = 0; sl < nslots; ++sl) {
+#pragma unroll
+        for (int c = lane * 4; c < COLS; c += 128) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (nb + c + 3 < a.N) v = *reinterpret_cast<const float4*>(a.g + (size_t)(mg_first + sl) * a.ldg + nb + c);
+          *reinterpret_cast<float4*>(gst + sl * COLS + c) = v;
+        }
+      }
+      __syncwarp();
+      const float* gr = gst + (mg - mg_first) * COLS;
       float part = 0.f;
 #pragma unroll
       for (int q = 0; q < COLS / 4; ++q) {
         const int n = nb + q * 4;
         if (n + 3 < a.N) {
           const float4 b4 = *reinterpret_cast<const float4*>(s_bias + half * COLS + q * 4);
-          const float4 gg = *reinterpret_cast<const float4*>(gr + n);
+          const float4 gg = *reinterpret_cast<const float4*>(gr + q * 4);
           const float4 ww = *reinterpret_cast<const float4*>(s_wv + half * COLS + q * 4);
-          part = fmaf(ww.x, tanhf(acc[q * 4 + 0] + b4.x + gg.x), part);
-          part = fmaf(ww.y, tanhf(acc[q * 4 + 1] + b4.y + gg.y), part);
-          part = fmaf(ww.z, tanhf(acc[q * 4 + 2] + b4.z + gg.z), part);
-          part = fmaf(ww.w, tanhf(acc[q * 4 + 3] + b4.w + gg.w), part);
+          part = fmaf(ww.x, tc_tanh(acc[q * 4 + 0] + b4.x + gg.x), part);
+          part = fmaf(ww.y, tc_tanh(acc[q * 4 + 1] + b4.y + gg.y), part);
+          part = fmaf(ww.z, tc_tanh(acc[q * 4 + 2] + b4.z + gg.z), part);
+          part = fmaf(ww.w, tc_tanh(acc[q * 4 + 3] + b4.w + gg.w), part);
         }
       }
       const int slice = (n0 / T2_BN) * 2 + half;

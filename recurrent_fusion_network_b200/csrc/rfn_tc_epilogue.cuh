@@ -26,6 +26,14 @@ __device__ __forceinline__ void tc_stage_bias(const TcArgs& a, int n0, int t /* 
   asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight worker warps only
 }
 
+// tanh for the fused score epilogue: 1 - 2 / (exp(2x) + 1) on the SFU (ex2.approx + rcp.approx), absolute error
+// <= ~2e-7 over the whole range (|tanh| <= 1), against ~35 instructions for tanhf: the epilogue evaluates 128 of
+// them per thread and was compute-bound on tanhf (14k of 120k cycles per tile).
+__device__ __forceinline__ float tc_tanh(float x) {
+  const float e = exp2f(x * 2.8853900817779268f);       // exp(2x); saturates cleanly to 0 / inf
+  return 1.f - __fdividef(2.f, e + 1.f);
+}
+
 template <int COLS>
 __device__ __forceinline__ void tc_epilogue_store(float (&acc)[COLS], float* stage /* this warp's 32 x (COLS+4) floats */,
                                                   const TcArgs& a, int m_base, int nb, int lane, const float* s_bias_half) {

@@ -284,7 +284,7 @@ def test_full_size_properties():
         m.chunk_images = 7
         seq_c, slp_c, *_ = m.sample_beam(fcg, attg, {"beam_size": 3})
         m.chunk_images = 1024
-        assert torch.equal(seq_c, seq) and maxdiff(slp_c, slp) <= 1e-5
+        assert torch.equal(seq_c, seq) and maxdiff(slp_c, slp) <= 5e-5   # different chunking -> different GEMM engines/tiles
         s, sl, la, _ = m.sample(fcg, attg, {"sample_max": 1})
         assert maxdiff(la.exp().sum(-1), torch.ones(la.shape[:2])) <= 1e-4
         # finished rows stay zero, and seqLogprobs is the log-prob of the chosen token
