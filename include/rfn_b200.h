@@ -76,7 +76,7 @@ int rfn_set_tc_cluster(int on);
 int rfn_get_tc_cluster(void);
 /* Debugging aid: device buffer receiving 8 clock64() stamps per CTA of the 2-CTA GEMM kernel
  * (start, init done, first MMA, last MMA, last drain, epilogue done, exit); NULL switches it off. */
-int rfn_debug_set_timeline(long long* d_buf);
+int rfn_debug_set_timeline(long long* d_buf, int epilogue_kind /* -1 all, 0 store, 1 score, 2 vocab */);
 
 /* 1 (default): the J independent encoder cells of a fusion step run on internal side streams forked
  * from / joined into the caller's stream; 0: everything is serialised on the caller's stream. */

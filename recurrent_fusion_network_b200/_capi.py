@@ -52,7 +52,7 @@ _SIGNATURES = {
     "rfn_get_gemm_mode": (_i, []),
     "rfn_set_tc_cluster": (_i, [_i]),
     "rfn_get_tc_cluster": (_i, []),
-    "rfn_debug_set_timeline": (_i, [_vp]),
+    "rfn_debug_set_timeline": (_i, [_vp, _i]),
     "rfn_set_concurrency": (_i, [_i]),
     "rfn_profile_enable": (_i, [_i]),
     "rfn_profile_num_tags": (_i, []),

@@ -234,38 +234,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       const float* gr = gst + (mg - mg_first) * COLS;
       float part = 0.f;
 #pragma unroll
-      for (int q = 0; q < COLS / 4; ++q) {
-        const int n = nb + q * 4;
-        if (n + 3 < a.N) {
-          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + half * COLS + q * 4);
-          const float4 gg = *reinterpret_cast<const float4*>(gr + q * 4);
-          const float4 ww = *reinterpret_cast<const float4*>(s_wv + half * COLS + q * 4);
-          part = fmaf(ww.x, tc_tanh(acc[q * 4 + 0] + b4.x + gg.x), part);
-          part = fmaf(ww.y, tc_tanh(acc[q * 4 + 1] + b4.y + gg.y), part);
-          part = fmaf(ww.z, tc_tanh(acc[q * 4 + 2] + b4.z + gg.z), part);
-          part = fmaf(ww.w, tc_tanh(acc[q * 4 + 3] + b4.w + gg.w), part);
-        }
+      for (int q = 0; q < COLS / 4; ++q) {   // branch-free: columns beyond N carry zero weight (s_wv) and zero inputs
+        const float4 b4 = *reinterpret_cast<const float4*>(s_bias + half * COLS + q * 4);
+        const float4 gg = *reinterpret_cast<const float4*>(gr + q * 4);
+        const float4 ww = *reinterpret_cast<const float4*>(s_wv + half * COLS + q * 4);
+        part = fmaf(ww.x, tc_tanh(acc[q * 4 + 0] + b4.x + gg.x), part);
+        part = fmaf(ww.y, tc_tanh(acc[q * 4 + 1] + b4.y + gg.y), part);
+        part = fmaf(ww.z, tc_tanh(acc[q * 4 + 2] + b4.z + gg.z), part);
+        part = fmaf(ww.w, tc_tanh(acc[q * 4 + 3] + b4.w + gg.w), part);
       }
       const int slice = blockIdx.x * 2 + half;   // N / COLS slices in total
       if (m < a.M) a.score[(size_t)slice * a.M + m] = part;
     } else {
       // fused vocabulary epilogue: logits never reach HBM.  Per thread (row m, COLS columns): running max,
       // sum exp(x - max) and the top-k logits with ties -> lower index; vocab_merge_kernel combines the slices.
+      // branch-free on purpose: per-column `if`s compile to BSSY/BRA/BSYNC triplets (61k cycles per tile measured)
       float mx = -INFINITY;
 #pragma unroll
       for (int i = 0; i < COLS; ++i) {
-        const int n = nb + i;
-        if (n < a.N) {
-          acc[i] += s_bias[half * COLS + i];
-          mx = fmaxf(mx, acc[i]);
-        } else {
-          acc[i] = -INFINITY;
-        }
+        const float v = acc[i] + s_bias[half * COLS + i];
+        acc[i] = (nb + i < a.N) ? v : -INFINITY;      // columns beyond N never win and contribute exp(-inf) = 0
+        mx = fmaxf(mx, acc[i]);
       }
+      const float mref = (mx == -INFINITY) ? 0.f : mx;  // a slice entirely beyond N
       float se = 0.f;
 #pragma unroll
-      for (int i = 0; i < COLS; ++i)
-        if (nb + i < a.N) se += expf(acc[i] - mx);
+      for (int i = 0; i < COLS; ++i) se += expf(acc[i] - mref);
       const int slice = blockIdx.x * 2 + half;
       if (m < a.M) {
         a.st_max[(size_t)slice * a.M + m] = mx;
@@ -273,15 +267,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       }
       float pv = INFINITY;
       int pi = -1;
-      for (int r = 0; r < a.ktop; ++r) {   // k selection passes over the register tile
+      for (int r = 0; r < a.ktop; ++r) {   // k selection passes over the register tile (ties -> lower index)
         float bv = -INFINITY;
         int bi = 0x7fffffff;
 #pragma unroll
         for (int i = 0; i < COLS; ++i) {
           const float v = acc[i];
           const int n = nb + i;
-          const bool after = (v < pv) || (v == pv && n > pi);
-          if (after && (v > bv || (v == bv && n < bi))) { bv = v; bi = n; }
+          const bool after = (v < pv) | ((v == pv) & (n > pi));
+          const bool take = after & ((v > bv) | ((v == bv) & (n < bi)));
+          bv = take ? v : bv;
+          bi = take ? n : bi;
         }
         if (m < a.M) {
           a.st_val[((size_t)slice * a.M + m) * a.ktop + r] = bv;
@@ -363,6 +359,7 @@ static int launch_tc(const TcArgs& t, cudaStream_t st) {
 }
 
 static std::atomic<long long*> g_tc_dbg{nullptr};
+static std::atomic<int> g_tc_dbg_epi{-1};   // -1: every epilogue kind
 static std::atomic<int> g_tc_cluster{1};   // default: 2-CTA clusters for large tensor-engine GEMMs
 int launch_tc2(const TcArgs& t, int passes, cudaStream_t st);   // rfn_gemm_tc2.cu
 static bool use_cluster(const GemmArgs& a) { return g_tc_cluster.load() != 0 && a.N >= 256 && a.M >= 256; }
@@ -402,7 +399,7 @@ int gemm_tc(const GemmArgs& a, int passes, const float* g, int ldg, const float*
   t.y = a.y; t.ldy = a.ldy; t.M = a.M; t.N = a.N; t.accumulate = a.accumulate;
   t.epi = score ? 1 : 0;
   t.g = g; t.ldg = ldg; t.wv = wv; t.score = score; t.natt = natt > 0 ? natt : 1;
-  t.dbg = g_tc_dbg.load();
+  t.dbg = (g_tc_dbg_epi.load() < 0 || g_tc_dbg_epi.load() == t.epi) ? g_tc_dbg.load() : nullptr;
   if (cluster) return launch_tc2(t, passes, st);
   if (passes == 3) return bn == 256 ? launch_tc<256, 2, 3, 4>(t, st) : launch_tc<128, 3, 3, 4>(t, st);
   return bn == 256 ? launch_tc<256, 4, 1, 1>(t, st) : launch_tc<128, 6, 1, 1>(t, st);
@@ -424,7 +421,7 @@ int gemm_tc_vocab(const GemmArgs& a, int passes, float* st_max, float* st_sum, f
   t.M = a.M; t.N = a.N;
   t.epi = 2;
   t.st_max = st_max; t.st_sum = st_sum; t.st_val = st_val; t.st_idx = st_idx; t.ktop = ktop;
-  t.dbg = g_tc_dbg.load();
+  t.dbg = (g_tc_dbg_epi.load() < 0 || g_tc_dbg_epi.load() == 2) ? g_tc_dbg.load() : nullptr;
   if (cluster) return launch_tc2(t, passes, st);
   return passes == 3 ? launch_tc<256, 2, 3, 4>(t, st) : launch_tc<256, 4, 1, 1>(t, st);
 }
@@ -437,7 +434,8 @@ extern "C" int rfn_set_tc_cluster(int on) {
 }
 extern "C" int rfn_get_tc_cluster(void) { return rfn::g_tc_cluster.load(); }
 // debugging aid: device buffer of 8 clock64 stamps per CTA filled by the 2-CTA kernel (NULL = off)
-extern "C" int rfn_debug_set_timeline(long long* d_buf) {
+extern "C" int rfn_debug_set_timeline(long long* d_buf, int epilogue_kind) {
+  rfn::g_tc_dbg_epi.store(epilogue_kind);
   rfn::g_tc_dbg.store(d_buf);
   return RFN_OK;
 }

@@ -224,36 +224,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc2_kernel(const __grid_co
       const float* gr = gst + (mg - mg_first) * COLS;
       float part = 0.f;
 #pragma unroll
-      for (int q = 0; q < COLS / 4; ++q) {
-        const int n = nb + q * 4;
-        if (n + 3 < a.N) {
-          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + half * COLS + q * 4);
-          const float4 gg = *reinterpret_cast<const float4*>(gr + q * 4);
-          const float4 ww = *reinterpret_cast<const float4*>(s_wv + half * COLS + q * 4);
-          part = fmaf(ww.x, tc_tanh(acc[q * 4 + 0] + b4.x + gg.x), part);
-          part = fmaf(ww.y, tc_tanh(acc[q * 4 + 1] + b4.y + gg.y), part);
-          part = fmaf(ww.z, tc_tanh(acc[q * 4 + 2] + b4.z + gg.z), part);
-          part = fmaf(ww.w, tc_tanh(acc[q * 4 + 3] + b4.w + gg.w), part);
-        }
+      for (int q = 0; q < COLS / 4; ++q) {   // branch-free: columns beyond N carry zero weight (s_wv) and zero inputs
+        const float4 b4 = *reinterpret_cast<const float4*>(s_bias + half * COLS + q * 4);
+        const float4 gg = *reinterpret_cast<const float4*>(gr + q * 4);
+        const float4 ww = *reinterpret_cast<const float4*>(s_wv + half * COLS + q * 4);
+        part = fmaf(ww.x, tc_tanh(acc[q * 4 + 0] + b4.x + gg.x), part);
+        part = fmaf(ww.y, tc_tanh(acc[q * 4 + 1] + b4.y + gg.y), part);
+        part = fmaf(ww.z, tc_tanh(acc[q * 4 + 2] + b4.z + gg.z), part);
+        part = fmaf(ww.w, tc_tanh(acc[q * 4 + 3] + b4.w + gg.w), part);
       }
       const int slice = (n0 / T2_BN) * 2 + half;
       if (m < a.M) a.score[(size_t)slice * a.M + m] = part;
     } else {
+      // branch-free on purpose: per-column `if`s compile to BSSY/BRA/BSYNC triplets (61k cycles per tile measured)
       float mx = -INFINITY;
 #pragma unroll
       for (int i = 0; i < COLS; ++i) {
-        const int n = nb + i;
-        if (n < a.N) {
-          acc[i] += s_bias[half * COLS + i];
-          mx = fmaxf(mx, acc[i]);
-        } else {
-          acc[i] = -INFINITY;
-        }
+        const float v = acc[i] + s_bias[half * COLS + i];
+        acc[i] = (nb + i < a.N) ? v : -INFINITY;      // columns beyond N never win and contribute exp(-inf) = 0
+        mx = fmaxf(mx, acc[i]);
       }
+      const float mref = (mx == -INFINITY) ? 0.f : mx;  // a slice entirely beyond N
       float se = 0.f;
 #pragma unroll
-      for (int i = 0; i < COLS; ++i)
-        if (nb + i < a.N) se += expf(acc[i] - mx);
+      for (int i = 0; i < COLS; ++i) se += expf(acc[i] - mref);
       const int slice = (n0 / T2_BN) * 2 + half;
       if (m < a.M) {
         a.st_max[(size_t)slice * a.M + m] = mx;
@@ -261,15 +255,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc2_kernel(const __grid_co
       }
       float pv = INFINITY;
       int pi = -1;
-      for (int r = 0; r < a.ktop; ++r) {
+      for (int r = 0; r < a.ktop; ++r) {   // k selection passes over the register tile (ties -> lower index)
         float bv = -INFINITY;
         int bi = 0x7fffffff;
 #pragma unroll
         for (int i = 0; i < COLS; ++i) {
           const float v = acc[i];
           const int n = nb + i;
-          const bool after = (v < pv) || (v == pv && n > pi);
-          if (after && (v > bv || (v == bv && n < bi))) { bv = v; bi = n; }
+          const bool after = (v < pv) | ((v == pv) & (n > pi));
+          const bool take = after & ((v > bv) | ((v == bv) & (n < bi)));
+          bv = take ? v : bv;
+          bi = take ? n : bi;
         }
         if (m < a.M) {
           a.st_val[((size_t)slice * a.M + m) * a.ktop + r] = bv;

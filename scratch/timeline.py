@@ -1,4 +1,5 @@
 import sys, torch
+EPI = int(sys.argv[1]) if len(sys.argv) > 1 else -1
 sys.path.insert(0, '.')
 from tests.test_gpu_engines import _linear_engine
 from recurrent_fusion_network_b200 import _capi
@@ -9,9 +10,9 @@ for K in (32, 512, 2048):
     nct = 2 * ((N + 255) // 256) * ((M + 255) // 256)
     buf = torch.zeros(nct, 8, dtype=torch.int64, device='cuda')
     _linear_engine(1, [x], [w], [b], M, N); torch.cuda.synchronize()
-    _capi.lib().rfn_debug_set_timeline(buf.data_ptr())
+    _capi.lib().rfn_debug_set_timeline(buf.data_ptr(), EPI)
     _linear_engine(1, [x], [w], [b], M, N); torch.cuda.synchronize()
-    _capi.lib().rfn_debug_set_timeline(None)
+    _capi.lib().rfn_debug_set_timeline(None, -1)
     t = buf.cpu().double()
     lead = t[0::2]
     d = lambda a, b_: float((lead[:, b_] - lead[:, a]).median())

@@ -1,4 +1,5 @@
 import sys, torch
+EPI = int(sys.argv[1]) if len(sys.argv) > 1 else -1
 sys.path.insert(0, '.')
 import bench
 from recurrent_fusion_network_b200 import _capi
@@ -10,10 +11,10 @@ buf = torch.zeros(40000, 8, dtype=torch.int64, device='cuda')
 with torch.no_grad():
     model.beam_search(fc, att, 3, want_reason=False)
     torch.cuda.synchronize()
-    _capi.lib().rfn_debug_set_timeline(buf.data_ptr())
+    _capi.lib().rfn_debug_set_timeline(buf.data_ptr(), EPI)
     model.beam_search(fc, att, 3, want_reason=False)
     torch.cuda.synchronize()
-    _capi.lib().rfn_debug_set_timeline(None)
+    _capi.lib().rfn_debug_set_timeline(None, -1)
 t = buf.cpu().double()
 nct = 2 * 38 * ((n * 3 + 255) // 256)
 lead = t[0:nct:2]
