@@ -1,20 +1,23 @@
 // tcgen05 tensor-core GEMM engine for sm_100a:  y[M,N] = sum_i x_i[M,K_i] . W_i[N,K_i]^T + bias.
 //
-// Design (one CTA = one 128 x BN output tile, accumulator in TMEM):
+// One CTA = one 128 x BN output tile (this file) or a 2-CTA cluster = one 256 x 256 tile (rfn_gemm_tc2.cu).
 //   warp 0        TMA producer: cp.async.bulk.tensor loads of raw fp32 tiles (K-major, 128-byte rows,
 //                 SWIZZLE_128B) of x and W into a multi-stage shared-memory ring, mbarrier complete_tx.
-//   warps 4..7    3xTF32 splitter: rewrite every landed tile in place as hi = tf32(x) and write
-//                 lo = x - hi beside it (element-wise, so the hardware swizzle is preserved), then
-//                 fence.proxy.async and hand the stage to the MMA warp.  Afterwards the same warps run
-//                 the epilogue: tcgen05.ld the accumulator out of TMEM, add bias, store -- or the fused
-//                 additive-attention epilogue score[m] += sum_n w[n] tanh(acc + b[n] + g[m/Natt, n])
-//                 so that U_a A never reaches HBM.
-//   warp 1        MMA issuer: one elected lane issues tcgen05.mma.kind::tf32 from shared-memory
-//                 descriptors; per 8-wide K step three MMAs (lo.hi, hi.lo, hi.hi) accumulate the
-//                 fp32-equivalent product; tcgen05.commit releases the stage / publishes the tile.
-//   PASSES == 1   single-pass TF32 (no splitter): the reduced-precision mode.
-// Both operands are K-major so activations (row-major) and nn.Linear weights (out,in) are consumed
-// exactly as torch stores them; ragged M / N / K edges are zero-filled by TMA.
+//   warp 1        MMA issuer: one elected lane issues tcgen05.mma.kind::tf32 from shared-memory descriptors.
+//                 The tensor core truncates its TF32 inputs, so the raw fp32 tile is the `hi` operand as is:
+//                 hi.hi is issued as soon as TMA lands, lo.hi and hi.lo once the splitter has written `lo`.
+//                 tcgen05.commit releases the stage / publishes an accumulator chunk.
+//   warps 2..9    workers, 256 threads: (a) 3xTF32 splitter: lo = x - trunc_tf32(x) written beside the raw
+//                 tile (element-wise, so the TMA swizzle is preserved), fence.proxy.async; (b) chunked drain:
+//                 every CH k-blocks the MMA warp switches to the other of two TMEM accumulators and the workers
+//                 tcgen05.ld the finished one into round-to-nearest fp32 registers (the tensor core itself
+//                 accumulates with truncation, -0.5 ulp per MMA); (c) epilogue: bias + coalesced store staged
+//                 through the dead operand ring, or the fused additive-attention score
+//                 score[m] = sum_n w[n] tanh(acc + b[n] + g[m/Natt, n]) (U_a A never reaches HBM), or the fused
+//                 vocabulary epilogue (row max, sum-exp and top-k of the logits; logits never reach HBM).
+//   PASSES == 1   single-pass TF32 (no splitter, one accumulator): the reduced-precision mode.
+// Both operands are K-major so activations (row-major) and nn.Linear weights (out,in) are consumed exactly as
+// torch stores them; ragged M / N / K edges are zero-filled by TMA.
 #include <cuda.h>
 
 #include <atomic>
