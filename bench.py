@@ -286,6 +286,7 @@ def run_ours(args):
 
 
 def xe_train_bench(model, device, world, rank, steps, timed):
+    from recurrent_fusion_network_b200 import _capi
     """BASELINE.json configs[1]: XE teacher-forced training of the full model, rows 80 per GPU (16 images x
     seq_per_img 5, features replicated as dataloader.py:251-252 does), label smoothing, drop_prob_lm 0.3,
     fwd + bwd + gradient all-reduce (mean) + clamp 1 + Adam(5e-4, wd 1e-5)  (train.py:154-163)."""
@@ -331,13 +332,21 @@ def xe_train_bench(model, device, world, rank, steps, timed):
     model.dedup_rows = spi      # stages 1-2 once per image (legal: fusion / reason dropout are 0 in the shipped script)
     ms_dd, launches_dd, _ = timed(step, steps, 1)
     model.dedup_rows = 1
+    # where the step's device time goes (kernels timed with CUDA events, serialised)
+    _capi.profile_enable(True)
+    step()
+    torch.cuda.synchronize()
+    prof = _capi.profile_read()
+    _capi.profile_enable(False)
+    tot = sum(v[0] for v in prof.values()) or 1.0
+    train_shares = {k: [round(v[0], 2), v[1]] for k, v in prof.items() if v[1]}
     model.eval()
     model.drop_prob_lm = model.decoder.drop_prob_lm = 0.0
     for p in params:
         p.grad = None
     return dict(metric="xe_train_tokens_per_sec", value=round(tokens / (ms / 1e3), 1), unit="target tokens/s",
                 ms_per_step=round(ms, 2), deduplicated=dict(value=round(tokens / (ms_dd / 1e3), 1), ms_per_step=round(ms_dd, 2)),
-                rows_per_gpu=rows, tokens_per_step=int(tokens), loss=round(float(loss_box[0]), 4),
+                kernel_ms_and_launches=train_shares, rows_per_gpu=rows, tokens_per_step=int(tokens), loss=round(float(loss_box[0]), 4),
                 note="as written (80 replicated rows; no row de-duplication); per-op autograd over our kernels, "
                      "backward GEMMs on the fp32 SIMT engine", gpu_launches_per_step=launches // max(1, steps))
 

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) gemm_gen_kernel(GemmGenArgs a) {
 
 int gemm_general(bool a_kmajor, bool b_kmajor, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M,
                  int N, int K, int accumulate, cudaStream_t st) {
-  ProfScope prof__(TAG_GEMM_OTHER, st);
+  ProfScope prof__(TAG_GEMM_BWD, st);
   RFN_CHECK_ARG(A && B && C && M >= 0 && N >= 0 && K >= 0, "gemm_general: bad arguments");
   if (M == 0 || N == 0) return RFN_OK;
   GemmGenArgs a{A, B, C, lda, ldb, ldc, M, N, K, accumulate};
@@ -227,7 +227,7 @@ attention_bwd_kernel(const float* __restrict__ A, const float* __restrict__ P, c
 int attention_bwd(const float* A, const float* P, const float* g, const float* w, const float* alpha, const float* dz,
                   int lddz, float* dP, float* dg, float* dw, float* dwb, float* dA, int rows, int N, int D, int Ah, int div,
                   cudaStream_t st) {
-  ProfScope prof__(TAG_ATTN_SMALL, st);
+  ProfScope prof__(TAG_ATTN_BWD, st);
   RFN_CHECK_ARG(A && P && g && w && alpha && dz && dP && dg && dw && dwb, "attention_bwd: null pointer");
   RFN_CHECK_ARG(D % 4 == 0 && lddz % 4 == 0, "attention_bwd: D and lddz must be multiples of 4");
   if (rows == 0) return RFN_OK;

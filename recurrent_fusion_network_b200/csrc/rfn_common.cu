@@ -89,7 +89,7 @@ int rfn_profile_num_tags(void) { return rfn::TAG_COUNT; }
 const char* rfn_profile_tag_name(int tag) {
   static const char* names[rfn::TAG_COUNT] = {"misc", "gemm_att2att_stage1", "attention_step_stage1", "gemm_gates",
                                               "gemm_logit", "gemm_other", "attention_step_small", "lstm_cell",
-                                              "vocab_stats_select", "beam_merge"};
+                                              "vocab_stats_select", "beam_merge", "gemm_backward", "attention_backward"};
   return (tag >= 0 && tag < rfn::TAG_COUNT) ? names[tag] : "?";
 }
 int rfn_profile_read(float* ms, uint64_t* launches, int n) {

@@ -15,7 +15,7 @@ int gemm_mode();
 // kernel classes for the optional CUDA-event profile (rfn_profile_*)
 enum Tag {
   TAG_MISC = 0, TAG_GEMM_ATT2ATT = 1, TAG_ATTN_S1 = 2, TAG_GEMM_GATES = 3, TAG_GEMM_LOGIT = 4, TAG_GEMM_OTHER = 5,
-  TAG_ATTN_SMALL = 6, TAG_CELL = 7, TAG_VOCAB = 8, TAG_BEAM = 9, TAG_COUNT = 10
+  TAG_ATTN_SMALL = 6, TAG_CELL = 7, TAG_VOCAB = 8, TAG_BEAM = 9, TAG_GEMM_BWD = 10, TAG_ATTN_BWD = 11, TAG_COUNT = 12
 };
 bool prof_enabled();
 struct TagScope {  // call-site override of a launcher's default class

@@ -54,13 +54,16 @@ def _step(model, it, TVc, state):
     return lp, state
 
 
-def forward_xe(model, fc_feats, att_feats, seq):
-    """RecurrentFusionModel.forward with gradients (misc/RecurrentFusionModel.py:198-281)."""
+def forward_xe(model, fc_feats, att_feats, seq, col_any=None):
+    """RecurrentFusionModel.forward with gradients (misc/RecurrentFusionModel.py:198-281).  `col_any` (which label
+    columns hold a non-zero token) may be supplied by a caller that already knows it on the host, so that the
+    call contains no device->host synchronisation (CUDA-graph capture)."""
     fc, att, rows = model._check_feats(fc_feats, att_feats)
     seq = seq.to(device=fc[0].device, dtype=torch.int64)
     TVc, reason_pred, state = _stages(model, fc, att)
     outputs = []
-    col_any = (seq != 0).any(dim=0).cpu().tolist()
+    if col_any is None:
+        col_any = (seq != 0).any(dim=0).cpu().tolist()
     for i in range(seq.size(1)):
         it = seq[:, i].clone()
         if i >= 1 and model.ss_prob > 0.0:                              # scheduled sampling (:260-270)
@@ -129,3 +132,4 @@ def rl_criterion(crit, input, seq, reward, logprobs_all, entropy_reg, top_pred, 
     for p in top_pred:
         terms.append(AG.MarginFn.apply(p, top_true, reason_weight / len(top_pred)))
     return AG.AddScalarsFn.apply(*terms)[0]
+

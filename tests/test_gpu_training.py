@@ -146,3 +146,4 @@ def test_row_deduplication_gives_the_same_gradients():
     for k in grads[1][0]:
         a, b = grads[1][0][k], grads[g][0][k]
         assert maxdiff(a, b) <= 2e-5 * (float(a.abs().max()) + 1e-6) + 1e-7, k
+
