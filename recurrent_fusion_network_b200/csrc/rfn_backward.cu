@@ -16,6 +16,7 @@ struct GemmGenArgs {
   int lda, ldb, ldc;
   int M, N, K;
   int accumulate;
+  int ksplit;   // > 1: blockIdx.z owns a K slice and adds its partial sums with atomics (C pre-zeroed / accumulated)
 };
 
 template <bool A_KMAJOR, bool B_KMAJOR>
@@ -32,7 +33,9 @@ __global__ void __launch_bounds__(256) gemm_gen_kernel(GemmGenArgs a) {
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-  for (int k0 = 0; k0 < a.K; k0 += BK) {
+  const int kper = ((a.K + a.ksplit - 1) / a.ksplit + BK - 1) / BK * BK;
+  const int kbeg = blockIdx.z * kper, kend = min(a.K, kbeg + kper);
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
     // each thread stages 4 elements of A and 4 of B (64x16 tiles, 256 threads)
     {
       if (A_KMAJOR) {
@@ -41,7 +44,7 @@ __global__ void __launch_bounds__(256) gemm_gen_kernel(GemmGenArgs a) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int k = k0 + kq + e;
-          As[kq + e][row] = (m < a.M && k < a.K) ? a.A[(size_t)m * a.lda + k] : 0.f;
+          As[kq + e][row] = (m < a.M && k < kend) ? a.A[(size_t)m * a.lda + k] : 0.f;
         }
       } else {
         const int kk = tid >> 4, mq = (tid & 15) * 4;
@@ -49,7 +52,7 @@ __global__ void __launch_bounds__(256) gemm_gen_kernel(GemmGenArgs a) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int m = m0 + mq + e;
-          As[kk][mq + e] = (m < a.M && k < a.K) ? a.A[(size_t)k * a.lda + m] : 0.f;
+          As[kk][mq + e] = (m < a.M && k < kend) ? a.A[(size_t)k * a.lda + m] : 0.f;
         }
       }
       if (B_KMAJOR) {
@@ -58,7 +61,7 @@ __global__ void __launch_bounds__(256) gemm_gen_kernel(GemmGenArgs a) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int k = k0 + kq + e;
-          Bs[kq + e][row] = (n < a.N && k < a.K) ? __ldg(a.B + (size_t)n * a.ldb + k) : 0.f;
+          Bs[kq + e][row] = (n < a.N && k < kend) ? __ldg(a.B + (size_t)n * a.ldb + k) : 0.f;
         }
       } else {
         const int kk = tid >> 4, nq = (tid & 15) * 4;
@@ -66,7 +69,7 @@ __global__ void __launch_bounds__(256) gemm_gen_kernel(GemmGenArgs a) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int n = n0 + nq + e;
-          Bs[kk][nq + e] = (n < a.N && k < a.K) ? __ldg(a.B + (size_t)k * a.ldb + n) : 0.f;
+          Bs[kk][nq + e] = (n < a.N && k < kend) ? __ldg(a.B + (size_t)k * a.ldb + n) : 0.f;
         }
       }
     }
@@ -94,7 +97,8 @@ __global__ void __launch_bounds__(256) gemm_gen_kernel(GemmGenArgs a) {
       const int n = n0 + tx * TN + j;
       if (n >= a.N) continue;
       float* cp = a.C + (size_t)m * a.ldc + n;
-      *cp = a.accumulate ? (*cp + acc[i][j]) : acc[i][j];
+      if (a.ksplit > 1) atomicAdd(cp, acc[i][j]);
+      else *cp = a.accumulate ? (*cp + acc[i][j]) : acc[i][j];
     }
   }
 }
@@ -104,8 +108,13 @@ int gemm_general(bool a_kmajor, bool b_kmajor, const float* A, int lda, const fl
   ProfScope prof__(TAG_GEMM_BWD, st);
   RFN_CHECK_ARG(A && B && C && M >= 0 && N >= 0 && K >= 0, "gemm_general: bad arguments");
   if (M == 0 || N == 0) return RFN_OK;
-  GemmGenArgs a{A, B, C, lda, ldb, ldc, M, N, K, accumulate};
-  dim3 grid((N + 63) / 64, (M + 63) / 64);
+  // few output tiles and a long contraction (dX = dY . W at small batch): split K over blockIdx.z
+  const int tiles = ((N + 63) / 64) * ((M + 63) / 64);
+  int ksplit = 1;
+  while (tiles * ksplit < 296 && K / (ksplit * 2) >= 64 && ksplit < 32) ksplit *= 2;
+  if (ksplit > 1 && !accumulate) RFN_CUDA(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, st));
+  GemmGenArgs a{A, B, C, lda, ldb, ldc, M, N, K, accumulate, ksplit};
+  dim3 grid((N + 63) / 64, (M + 63) / 64, ksplit);
   if (a_kmajor && b_kmajor) gemm_gen_kernel<true, true><<<grid, 256, 0, st>>>(a);
   else if (a_kmajor && !b_kmajor) gemm_gen_kernel<true, false><<<grid, 256, 0, st>>>(a);
   else if (!a_kmajor && b_kmajor) gemm_gen_kernel<false, true><<<grid, 256, 0, st>>>(a);

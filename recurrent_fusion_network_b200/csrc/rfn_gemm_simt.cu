@@ -122,6 +122,85 @@ gemm_tn_simt_kernel(GemmArgs a) {
   }
 }
 
+
+// ---- skinny GEMM: M <= 32 rows ("warp-level FMA when batch x beam is small") --------------------------------
+// The problem is a weight stream: every W element is used M times.  One warp per output column, lanes stride
+// K with 128-bit coalesced loads of the W row, x staged in shared memory in K chunks, M accumulators per lane,
+// deterministic shuffle reduction.  grid = N / 8 CTAs so that even N = 512 launches 64 CTAs, and K is consumed
+// at several hundred GB/s per SM instead of one 16-wide tile per __syncthreads.
+constexpr int SK_WARPS = 8;
+constexpr int SK_KCHUNK = 512;   // floats of K staged per round: M * 512 * 4 bytes <= 64 KB
+
+template <int MMAX>
+__global__ void __launch_bounds__(SK_WARPS * 32) gemm_skinny_kernel(GemmArgs a) {
+  extern __shared__ __align__(16) float s_x[];   // [MMAX][SK_KCHUNK]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * SK_WARPS + warp;
+  const int M = a.M;
+  float acc[MMAX];
+#pragma unroll
+  for (int m = 0; m < MMAX; ++m) acc[m] = 0.f;
+  for (int s = 0; s < a.nsrc; ++s) {
+    const float* __restrict__ x = a.src[s].x;
+    const float* __restrict__ w = a.src[s].w + (size_t)min(n, a.N - 1) * a.src[s].ldw;
+    const int K = a.src[s].K, ldx = a.src[s].ldx;
+    for (int k0 = 0; k0 < K; k0 += SK_KCHUNK) {
+      const int kc = min(SK_KCHUNK, K - k0);
+      __syncthreads();
+      for (int i = threadIdx.x * 4; i < MMAX * kc; i += SK_WARPS * 32 * 4) {
+        const int m = i / kc, k = i % kc;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < M) v = *reinterpret_cast<const float4*>(x + (size_t)m * ldx + k0 + k);
+        *reinterpret_cast<float4*>(s_x + m * SK_KCHUNK + k) = v;
+      }
+      __syncthreads();
+      for (int k = lane * 4; k < kc; k += 128) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(w + k0 + k));
+#pragma unroll
+        for (int m = 0; m < MMAX; ++m) {
+          const float4 xv = *reinterpret_cast<const float4*>(s_x + m * SK_KCHUNK + k);
+          acc[m] = fmaf(wv.x, xv.x, acc[m]);
+          acc[m] = fmaf(wv.y, xv.y, acc[m]);
+          acc[m] = fmaf(wv.z, xv.z, acc[m]);
+          acc[m] = fmaf(wv.w, xv.w, acc[m]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < MMAX; ++m) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], o);
+  }
+  if (n < a.N && lane == 0) {
+    float b = 0.f;
+    for (int s = 0; s < a.nsrc; ++s)
+      if (a.src[s].bias) b += __ldg(a.src[s].bias + n);
+#pragma unroll
+    for (int m = 0; m < MMAX; ++m) {
+      if (m < M) {
+        float* yp = a.y + (size_t)m * a.ldy + n;
+        float v = acc[m] + b;
+        if (a.accumulate) v += *yp;
+        *yp = v;
+      }
+    }
+  }
+}
+
+template <int MMAX>
+static int launch_skinny(const GemmArgs& a, cudaStream_t st) {
+  const size_t smem = (size_t)MMAX * SK_KCHUNK * sizeof(float);
+  static bool configured = false;
+  if (!configured && smem > 48 * 1024) {
+    RFN_CUDA(cudaFuncSetAttribute(gemm_skinny_kernel<MMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  gemm_skinny_kernel<MMAX><<<(a.N + SK_WARPS - 1) / SK_WARPS, SK_WARPS * 32, smem, st>>>(a);
+  RFN_LAUNCH_CHECK();
+  return RFN_OK;
+}
+
 int gemm_simt(const GemmArgs& a, cudaStream_t st) {
   ProfScope prof__(TAG_GEMM_OTHER, st);
   RFN_CHECK_ARG(a.nsrc >= 1 && a.nsrc <= 3, "gemm: n_src %d not in 1..3", a.nsrc);
@@ -134,10 +213,10 @@ int gemm_simt(const GemmArgs& a, cudaStream_t st) {
                   "gemm: K=%d ldx=%d ldw=%d must be multiples of 4", g.K, g.ldx, g.ldw);
     RFN_CHECK_ARG(((uintptr_t)g.x % 16 == 0) && ((uintptr_t)g.w % 16 == 0), "gemm: operands must be 16-byte aligned");
   }
-  if (a.M <= 32) {
-    dim3 grid((a.N + 31) / 32, (a.M + 31) / 32);
-    gemm_tn_simt_kernel<32, 32, 2, 2><<<grid, 256, 0, st>>>(a);
-  } else if (a.M <= 64) {
+  if (a.M <= 8) return launch_skinny<8>(a, st);
+  if (a.M <= 16) return launch_skinny<16>(a, st);
+  if (a.M <= 32) return launch_skinny<32>(a, st);
+  if (a.M <= 64) {
     dim3 grid((a.N + 63) / 64, (a.M + 63) / 64);
     gemm_tn_simt_kernel<64, 64, 4, 4><<<grid, 256, 0, st>>>(a);
   } else {

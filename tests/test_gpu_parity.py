@@ -209,7 +209,7 @@ def test_beam_batching_is_chunk_invariant():
         b = m.sample_beam(cuda_list(fc), cuda_list(att), {"beam_size": 3})
         m.chunk_images = 1024
         o = O.sample_beam(sd, cfg, fc, att, beam_size=3)
-    assert torch.equal(a[0], b[0]) and maxdiff(a[1], b[1]) <= 1e-6
+    assert torch.equal(a[0], b[0]) and maxdiff(a[1], b[1]) <= 2e-5   # chunk size selects different GEMM kernels
     assert torch.equal(a[0].cpu(), o[0]) and maxdiff(a[1], o[1]) <= LP_TOL
     assert [t.shape for t in a[2]] == [t.shape for t in o[2]]
     for x, y in zip(a[2], o[2]):
