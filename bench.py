@@ -347,8 +347,9 @@ def xe_train_bench(model, device, world, rank, steps, timed):
     return dict(metric="xe_train_tokens_per_sec", value=round(tokens / (ms / 1e3), 1), unit="target tokens/s",
                 ms_per_step=round(ms, 2), deduplicated=dict(value=round(tokens / (ms_dd / 1e3), 1), ms_per_step=round(ms_dd, 2)),
                 kernel_ms_and_launches=train_shares, rows_per_gpu=rows, tokens_per_step=int(tokens), loss=round(float(loss_box[0]), 4),
-                note="as written (80 replicated rows; no row de-duplication); per-op autograd over our kernels, "
-                     "backward GEMMs on the fp32 SIMT engine", gpu_launches_per_step=launches // max(1, steps))
+                note="value: as written (80 replicated rows); deduplicated: stages 1-2 once per image (SURVEY D9); per-op autograd "
+                     "over our kernels, small-row GEMMs on the skinny weight-streaming kernel, backward GEMMs fp32 SIMT with "
+                     "split-K; torch.optim.Adam as in train.py:56", gpu_launches_per_step=launches // max(1, steps))
 
 
 def args_dtype(args):

@@ -1,5 +1,5 @@
 import sys, torch
-sys.path.insert(0, '.')
+sys.path.insert(0, '.')  # run from the repo root
 from tests.test_gpu_engines import _linear_engine
 torch.manual_seed(0)
 M, N, K = 128, 256, 32

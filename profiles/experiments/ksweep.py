@@ -1,5 +1,5 @@
 import sys, torch
-sys.path.insert(0, '.')
+sys.path.insert(0, '.')  # run from the repo root
 from tests.test_gpu_engines import _linear_engine
 from recurrent_fusion_network_b200 import _capi
 def t(fn, n=5):

@@ -2,7 +2,7 @@
 on the 5000-image bench workload, and both against the oracle on a subset, classifying every divergence by
 the decision margin."""
 import sys, json, torch
-sys.path.insert(0, '.')
+sys.path.insert(0, '.')  # run from the repo root
 import bench
 from recurrent_fusion_network_b200 import _capi
 from oracle import rfnet_oracle as O

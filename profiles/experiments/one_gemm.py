@@ -1,5 +1,5 @@
 import sys, torch
-sys.path.insert(0, '.')
+sys.path.insert(0, '.')  # run from the repo root
 from tests.test_gpu_engines import _linear_engine
 M, N, K = 15000, 9488, int(sys.argv[1]) if len(sys.argv) > 1 else 32
 b = torch.zeros(N, device='cuda')

@@ -1,6 +1,6 @@
 import sys, torch
 EPI = int(sys.argv[1]) if len(sys.argv) > 1 else -1
-sys.path.insert(0, '.')
+sys.path.insert(0, '.')  # run from the repo root
 from tests.test_gpu_engines import _linear_engine
 from recurrent_fusion_network_b200 import _capi
 M, N = 15000, 9488

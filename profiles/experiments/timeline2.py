@@ -1,6 +1,6 @@
 import sys, torch
 EPI = int(sys.argv[1]) if len(sys.argv) > 1 else -1
-sys.path.insert(0, '.')
+sys.path.insert(0, '.')  # run from the repo root
 import bench
 from recurrent_fusion_network_b200 import _capi
 dev = torch.device('cuda', 0)

@@ -123,18 +123,31 @@ int gemm_general(bool a_kmajor, bool b_kmajor, const float* A, int lda, const fl
   return RFN_OK;
 }
 
-// db[n] (+)= sum_m dY[m,n]
-__global__ void colsum_kernel(const float* __restrict__ dY, int ld, int M, int N, float* __restrict__ db, int accumulate) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+// db[n] (+)= sum_m dY[m,n]: 32 columns x 8 row-lanes per block, each block reduces a 256-row slab and adds
+// its partial with one atomic per column
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ dY, int ld, int M, int N, float* __restrict__ db) {
+  __shared__ float s_p[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + tx;
+  const int m0 = blockIdx.y * 256;
   float s = 0.f;
-  for (int m = 0; m < M; ++m) s += dY[(size_t)m * ld + n];
-  db[n] = accumulate ? db[n] + s : s;
+  if (n < N)
+    for (int m = m0 + ty; m < min(M, m0 + 256); m += 8) s += dY[(size_t)m * ld + n];
+  s_p[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += s_p[i][tx];
+    atomicAdd(db + n, t);
+  }
 }
 int colsum(const float* dY, int ld, int M, int N, float* db, int accumulate, cudaStream_t st) {
   ProfScope prof__(TAG_MISC, st);
   if (N == 0) return RFN_OK;
-  colsum_kernel<<<(N + 127) / 128, 128, 0, st>>>(dY, ld, M, N, db, accumulate);
+  if (!accumulate) RFN_CUDA(cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), st));
+  if (M == 0) return RFN_OK;
+  colsum_kernel<<<dim3((N + 31) / 32, (M + 255) / 256), 256, 0, st>>>(dY, ld, M, N, db);
   RFN_LAUNCH_CHECK();
   return RFN_OK;
 }

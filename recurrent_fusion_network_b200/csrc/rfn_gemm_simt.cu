@@ -216,6 +216,17 @@ int gemm_simt(const GemmArgs& a, cudaStream_t st) {
   if (a.M <= 8) return launch_skinny<8>(a, st);
   if (a.M <= 16) return launch_skinny<16>(a, st);
   if (a.M <= 32) return launch_skinny<32>(a, st);
+  if (a.M < 128) {
+    // still a weight stream: 32 rows at a time (W comes from L2 after the first group)
+    for (int m0 = 0; m0 < a.M; m0 += 32) {
+      GemmArgs g = a;
+      g.M = (a.M - m0 < 32) ? a.M - m0 : 32;
+      g.y = a.y + (size_t)m0 * a.ldy;
+      for (int s = 0; s < a.nsrc; ++s) g.src[s].x = a.src[s].x + (size_t)m0 * a.src[s].ldx;
+      RFN_TRY(g.M <= 8 ? launch_skinny<8>(g, st) : (g.M <= 16 ? launch_skinny<16>(g, st) : launch_skinny<32>(g, st)));
+    }
+    return RFN_OK;
+  }
   if (a.M <= 64) {
     dim3 grid((a.N + 63) / 64, (a.M + 63) / 64);
     gemm_tn_simt_kernel<64, 64, 4, 4><<<grid, 256, 0, st>>>(a);
