@@ -340,3 +340,32 @@ def test_max_beam_width_and_bad_arguments():
             m.sample(cuda_list(fc)[:1], cuda_list(att), {})                      # wrong encoder count
         with pytest.raises(_capi.RfnError):
             m.sample(cuda_list(fc), [a[:, :-1] for a in cuda_list(att)], {})     # wrong att_num
+
+
+def test_full_size_ensemble_two_models():
+    """BASELINE.json configs[4] at reference sizes (two five-encoder models, logit-mean ensemble, beam 3)."""
+    from recurrent_fusion_network_b200.ensemble import ensemble_sample_beam, model_ensemble_feat_array_one_step
+    cfg = O.RFNConfig()
+    sds = [O.make_state_dict(cfg, seed=1235 + i, sharpen=True) for i in range(2)]
+    fc, att = O.make_inputs(cfg, 3, seed=12)
+    models = [build_model(cfg, sd) for sd in sds]
+    torch.set_num_threads(16)
+    with torch.no_grad():
+        seq, slp, ts, tp = ensemble_sample_beam(models, cuda_list(fc), cuda_list(att), {"beam_size": 3})
+        o = O.ensemble_sample_beam(sds, cfg, fc, att, beam_size=3)
+        assert torch.equal(seq.cpu(), o[0]) and maxdiff(slp, o[1]) <= LP_TOL
+        assert [t.shape for t in ts] == [t.shape for t in o[2]]
+        # one ensemble step through the model-level API (eval_utils.py:268-290)
+        states, tvs, xts = [], [], []
+        for m in models:
+            TVc, _, st = m.get_thought_vectors(cuda_list(fc), cuda_list(att), m.get_init_state(cuda_list(fc)))
+            tvs.append(TVc); states.append(st)
+            xts.append(m.embed.weight[torch.zeros(3, dtype=torch.int64, device="cuda")])
+        _, _, lp = model_ensemble_feat_array_one_step(models, xts, states, tvs)
+        lg = []
+        for sd in sds:
+            TVc_o, _, st_o = O.get_thought_vectors(sd, cfg, att, O.get_init_state(sd, cfg, fc))
+            l, _ = O.one_time_step(sd, sd["embed.weight"][torch.zeros(3, dtype=torch.int64)], TVc_o, st_o)
+            lg.append(l)
+        want = torch.log_softmax(sum(lg) / 2, dim=1)
+        assert maxdiff(lp, want) <= LP_TOL
