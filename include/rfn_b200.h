@@ -70,8 +70,9 @@ uint64_t rfn_launch_count(void);
  * (reduced precision).  Problems with fewer rows always use the SIMT kernel. */
 int rfn_set_gemm_mode(int mode);
 int rfn_get_gemm_mode(void);
-/* 1: tensor-engine GEMMs with >= 256 rows and columns run as 2-CTA clusters (tcgen05 cta_group::2,
- * 256 x 256 tiles, operands split across the pair); 0: one CTA per 128 x 256 tile. */
+/* Tensor-engine GEMMs with >= 256 rows and columns: 0 = one CTA per 128 x 256 tile; 1 = 2-CTA clusters
+ * (tcgen05 cta_group::2, 256 x 256 tiles, operands split across the pair), one tile per cluster;
+ * 2 = persistent 2-CTA clusters looping over tiles with the epilogue overlapped (3xTF32 mode). */
 int rfn_set_tc_cluster(int on);
 int rfn_get_tc_cluster(void);
 /* Debugging aid: device buffer receiving 8 clock64() stamps per CTA of the 2-CTA GEMM kernel

@@ -365,6 +365,7 @@ static std::atomic<long long*> g_tc_dbg{nullptr};
 static std::atomic<int> g_tc_dbg_epi{-1};   // -1: every epilogue kind
 static std::atomic<int> g_tc_cluster{1};   // default: 2-CTA clusters for large tensor-engine GEMMs
 int launch_tc2(const TcArgs& t, int passes, cudaStream_t st);   // rfn_gemm_tc2.cu
+int launch_tc2p(const TcArgs& t, cudaStream_t st);               // rfn_gemm_tc2p.cu (persistent, 3xTF32)
 static bool use_cluster(const GemmArgs& a) { return g_tc_cluster.load() != 0 && a.N >= 256 && a.M >= 256; }
 
 bool gemm_tc_supported(const GemmArgs& a) {
@@ -403,7 +404,7 @@ int gemm_tc(const GemmArgs& a, int passes, const float* g, int ldg, const float*
   t.epi = score ? 1 : 0;
   t.g = g; t.ldg = ldg; t.wv = wv; t.score = score; t.natt = natt > 0 ? natt : 1;
   t.dbg = (g_tc_dbg_epi.load() < 0 || g_tc_dbg_epi.load() == t.epi) ? g_tc_dbg.load() : nullptr;
-  if (cluster) return launch_tc2(t, passes, st);
+  if (cluster) return (g_tc_cluster.load() >= 2 && passes == 3) ? launch_tc2p(t, st) : launch_tc2(t, passes, st);
   if (passes == 3) return bn == 256 ? launch_tc<256, 2, 3, 4>(t, st) : launch_tc<128, 3, 3, 4>(t, st);
   return bn == 256 ? launch_tc<256, 4, 1, 1>(t, st) : launch_tc<128, 6, 1, 1>(t, st);
 }
@@ -425,14 +426,14 @@ int gemm_tc_vocab(const GemmArgs& a, int passes, float* st_max, float* st_sum, f
   t.epi = 2;
   t.st_max = st_max; t.st_sum = st_sum; t.st_val = st_val; t.st_idx = st_idx; t.ktop = ktop;
   t.dbg = (g_tc_dbg_epi.load() < 0 || g_tc_dbg_epi.load() == 2) ? g_tc_dbg.load() : nullptr;
-  if (cluster) return launch_tc2(t, passes, st);
+  if (cluster) return (g_tc_cluster.load() >= 2 && passes == 3) ? launch_tc2p(t, st) : launch_tc2(t, passes, st);
   return passes == 3 ? launch_tc<256, 2, 3, 4>(t, st) : launch_tc<256, 4, 1, 1>(t, st);
 }
 
 }  // namespace rfn
 
 extern "C" int rfn_set_tc_cluster(int on) {
-  rfn::g_tc_cluster.store(on ? 1 : 0);
+  rfn::g_tc_cluster.store(on < 0 ? 0 : (on > 2 ? 2 : on));
   return RFN_OK;
 }
 extern "C" int rfn_get_tc_cluster(void) { return rfn::g_tc_cluster.load(); }

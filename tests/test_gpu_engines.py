@@ -111,16 +111,17 @@ def test_fused_vocab_epilogue_beam_matches_oracle_and_simt():
     assert maxdiff(res[0][1][same], res[1][1][same]) <= 1e-4
 
 
-@pytest.fixture
-def tc_cluster():
+@pytest.fixture(params=[1, 2], ids=["cluster", "persistent"])
+def tc_cluster(request):
     from recurrent_fusion_network_b200 import _capi
-    _capi.check(_capi.lib().rfn_set_tc_cluster(1))
+    prev = _capi.lib().rfn_get_tc_cluster()
+    _capi.check(_capi.lib().rfn_set_tc_cluster(request.param))
     yield
-    _capi.check(_capi.lib().rfn_set_tc_cluster(0))
+    _capi.check(_capi.lib().rfn_set_tc_cluster(prev))
 
 
 @pytest.mark.parametrize("M,N,Ks", [(256, 256, [32]), (256, 512, [2048]), (1000, 2048, [2560, 1280]), (300, 9488, [512]),
-                                    (777, 260, [36, 64, 128])])
+                                    (777, 260, [36, 64, 128]), (20000, 768, [96])])
 @pytest.mark.parametrize("engine,tol", [(1, 3e-6), (2, 3e-3)])
 def test_two_cta_cluster_engine(tc_cluster, engine, tol, M, N, Ks):
     """cta_group::2 pairs (256 x 256 tiles, operands split across the two CTAs)."""
