@@ -363,7 +363,7 @@ static int launch_tc(const TcArgs& t, cudaStream_t st) {
 
 static std::atomic<long long*> g_tc_dbg{nullptr};
 static std::atomic<int> g_tc_dbg_epi{-1};   // -1: every epilogue kind
-static std::atomic<int> g_tc_cluster{1};   // default: 2-CTA clusters for large tensor-engine GEMMs
+static std::atomic<int> g_tc_cluster{2};   // default: persistent 2-CTA clusters for large tensor-engine GEMMs
 int launch_tc2(const TcArgs& t, int passes, cudaStream_t st);   // rfn_gemm_tc2.cu
 int launch_tc2p(const TcArgs& t, cudaStream_t st);               // rfn_gemm_tc2p.cu (persistent, 3xTF32)
 static bool use_cluster(const GemmArgs& a) { return g_tc_cluster.load() != 0 && a.N >= 256 && a.M >= 256; }
@@ -404,7 +404,9 @@ int gemm_tc(const GemmArgs& a, int passes, const float* g, int ldg, const float*
   t.epi = score ? 1 : 0;
   t.g = g; t.ldg = ldg; t.wv = wv; t.score = score; t.natt = natt > 0 ? natt : 1;
   t.dbg = (g_tc_dbg_epi.load() < 0 || g_tc_dbg_epi.load() == t.epi) ? g_tc_dbg.load() : nullptr;
-  if (cluster) return (g_tc_cluster.load() >= 2 && passes == 3) ? launch_tc2p(t, st) : launch_tc2(t, passes, st);
+  // persistent clusters for the fused-epilogue GEMMs; the plain-store GEMMs keep the 3-stage one-tile kernel
+  // (the persistent store epilogue needs staging memory that costs a pipeline stage: measured slower)
+  if (cluster) return (g_tc_cluster.load() >= 2 && passes == 3 && t.epi != 0) ? launch_tc2p(t, st) : launch_tc2(t, passes, st);
   if (passes == 3) return bn == 256 ? launch_tc<256, 2, 3, 4>(t, st) : launch_tc<128, 3, 3, 4>(t, st);
   return bn == 256 ? launch_tc<256, 4, 1, 1>(t, st) : launch_tc<128, 6, 1, 1>(t, st);
 }
