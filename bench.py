@@ -209,14 +209,14 @@ def run_ours(args):
     tf = flops_att / (g_ms / 1e3) / 1e12 if g_ms else 0.0
     gbs = bytes_attn / (a_ms / 1e3) / 1e9 if a_ms else 0.0
     # traffic: dram__bytes_read+write of ONE launch from the committed ncu --set full captures (resnet encoder,
-    # 1024 images per launch; profiles/r1_gemm_tc2_score_ncu.txt, profiles/r1_attention_step_ncu.txt); the
+    # 1024 images per launch; profiles/r1_gemm_tc2p_score_ncu.txt, profiles/r1_attention_step_ncu.txt); the
     # algorithmic bytes of that same launch are given beside it.
     passes = {0: 1, 1: 3, 2: 1}[args.gemm_mode]
     roof_gemm = dict(kernel="gemm_att2att_stage1", bound="tensor", achieved=round(tf, 2), peak=peaks["bf16_sustained"],
                      unit="TFLOP/s", frac=round(tf / peaks["bf16_sustained"], 4),
-                     traffic=1.720e9 if args.gemm_mode == 1 else None,
-                     traffic_note="ncu capture of one launch (resnet encoder, 1024 images): 1.665 GB read + 0.056 GB written "
-                                  "vs 1.648 GB algorithmic (A once + W once); tensor pipe 87.0 % active",
+                     traffic=1.718e9 if args.gemm_mode == 1 else None,
+                     traffic_note="ncu capture of one launch (resnet encoder, 1024 images, persistent 2-CTA kernel): 1.711 GB read "
+                                  "+ 0.007 GB written vs 1.648 GB algorithmic (A once + W once); tensor pipe 97.7 % active",
                      mma_tflops_executed=round(tf * passes, 1),
                      frac_of_3xtf32_ceiling=(round(tf * passes / (peaks["bf16_burst"] / 2), 4) if args.gemm_mode >= 1 else None),
                      ceiling_note="fp32-equivalent = 3 TF32 MMAs per product; TF32 peak taken as half the measured bf16 burst peak",
