@@ -392,8 +392,10 @@ int gemm_tc(const GemmArgs& a, int passes, const float* g, int ldg, const float*
   t.nsrc = a.nsrc;
   // 128 x 256 tiles unless that leaves most of the 148 SMs idle (few rows): then 128 x 128 doubles the CTA count
   const long tiles256 = (long)((a.M + TC_BM - 1) / TC_BM) * ((a.N + 255) / 256);
-  const int bn = score ? 256 : ((a.N > 128 && tiles256 >= 148) ? 256 : 128);
-  const bool cluster = use_cluster(a) && bn == 256;   // 2-CTA pairs: each CTA lands 128 rows of W
+  // 2-CTA pairs (each CTA lands 128 rows of W) whenever the problem has >= 256 rows and columns: even when one
+  // launch does not fill the SMs, the encoder side streams run several such GEMMs concurrently
+  const bool cluster = use_cluster(a);
+  const int bn = (score || cluster) ? 256 : ((a.N > 128 && tiles256 >= 148) ? 256 : 128);
   for (int s = 0; s < a.nsrc; ++s) {
     RFN_TRY(tc_make_map(&t.tm_x[s], a.src[s].x, a.M, a.src[s].K, a.src[s].ldx, TC_BM));
     RFN_TRY(tc_make_map(&t.tm_w[s], a.src[s].w, a.N, a.src[s].K, a.src[s].ldw, cluster ? 128 : bn));
