@@ -134,3 +134,35 @@ def test_two_cta_cluster_engine(tc_cluster, engine, tol, M, N, Ks):
     torch.cuda.synchronize()
     scale = float(want.abs().max())
     assert maxdiff(got, want) <= tol * scale
+
+
+def test_library_services_profile_concurrency_and_errors():
+    """rfn_profile_*, rfn_set_concurrency, rfn_launch_count and the error path of a too-small workspace."""
+    import ctypes as C
+    from recurrent_fusion_network_b200 import _capi
+    from recurrent_fusion_network_b200._capi import lib, ptr, ptr_array, stream
+    cfg = O.tiny_config(2)
+    sd = O.make_state_dict(cfg, seed=3, init_range=0.5)
+    fc, att = O.make_inputs(cfg, 5, seed=1)
+    m = build_model(cfg, sd)
+    outs = {}
+    for conc in (0, 1):
+        _capi.check(lib().rfn_set_concurrency(conc))
+        n0 = lib().rfn_launch_count()
+        _capi.profile_enable(True)
+        with torch.no_grad():
+            outs[conc] = m.sample_beam(cuda_list(fc), cuda_list(att), {"beam_size": 3})
+        torch.cuda.synchronize()
+        prof = _capi.profile_read()
+        _capi.profile_enable(False)
+        assert lib().rfn_launch_count() - n0 == sum(v[1] for v in prof.values()) > 50
+        assert prof["beam_merge"][1] == cfg.seq_length + 1 and prof["lstm_cell"][0] > 0
+    _capi.check(lib().rfn_set_concurrency(1))
+    assert torch.equal(outs[0][0], outs[1][0]) and maxdiff(outs[0][1], outs[1][1]) == 0.0   # same kernels, same bits
+    # workspace too small -> RFN_ERR_WORKSPACE with a message, nothing launched
+    TVc = torch.empty(5, cfg.num_review_steps, cfg.rnn_size, device="cuda")
+    h = torch.empty(5, cfg.rnn_size, device="cuda")
+    ws = torch.empty(64, dtype=torch.uint8, device="cuda")
+    rc = lib().rfn_thought_vectors(C.byref(m._dims), m._params(), ptr_array(cuda_list(fc)), None, None, ptr_array(cuda_list(att)), 5,
+                                   ptr(TVc), ptr(h), ptr(h.clone()), None, None, ptr(ws), ws.numel(), stream())
+    assert rc == -3 and b"workspace" in lib().rfn_last_error()
