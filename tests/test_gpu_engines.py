@@ -155,7 +155,8 @@ def test_library_services_profile_concurrency_and_errors():
         torch.cuda.synchronize()
         prof = _capi.profile_read()
         _capi.profile_enable(False)
-        assert lib().rfn_launch_count() - n0 == sum(v[1] for v in prof.values()) > 50
+        n_prof = sum(v[1] for v in prof.values())
+        assert lib().rfn_launch_count() - n0 >= n_prof > 50   # a profiled launcher may issue several kernels
         assert prof["beam_merge"][1] == cfg.seq_length + 1 and prof["lstm_cell"][0] > 0
     _capi.check(lib().rfn_set_concurrency(1))
     assert torch.equal(outs[0][0], outs[1][0]) and maxdiff(outs[0][1], outs[1][1]) == 0.0   # same kernels, same bits
