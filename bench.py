@@ -274,6 +274,11 @@ def run_ours(args):
         torch.cuda.empty_cache()
         xe = xe_train_bench(model, device, world, rank, args.train_steps, timed)
 
+    # ---- next-row component: CIDEr-D self-critical reward, device vs the oracle port on the host ----
+    ciderd = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ciderd = ciderd_bench(device)
+
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on a bounded sample --------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -293,7 +298,7 @@ def run_ours(args):
                                 parity="fp32 mode; tests/test_gpu_parity.py vs the reference fixtures"),
                     clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=dominant,
                     roofline_attention=roof_attn, roofline_gemm=roof_gemm, kernel_time_shares=shares,
-                    cpu_baseline=cpu, xe_train=xe, seq_checksum=seq_checksum)
+                    cpu_baseline=cpu, xe_train=xe, ciderd_reward=ciderd, seq_checksum=seq_checksum)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -364,6 +369,48 @@ def xe_train_bench(model, device, world, rank, steps, timed):
                 note="value: as written (80 replicated rows); deduplicated: stages 1-2 once per image (SURVEY D9); per-op autograd "
                      "over our kernels, small-row GEMMs on the skinny weight-streaming kernel, backward GEMMs fp32 SIMT with "
                      "split-K; torch.optim.Adam as in train.py:56", gpu_launches_per_step=launches // max(1, steps))
+
+
+def ciderd_bench(device):
+    """Self-critical reward of one RL step at config-4 size (250 rows = 50 images x 5, sample + greedy hypotheses, 5
+    references per image, corpus document frequencies): device kernel vs the oracle port (= the reference scorer)."""
+    import numpy as np
+    from types import SimpleNamespace
+    from oracle import ciderd_oracle as CD
+    from recurrent_fusion_network_b200 import reward as RW
+    rng = np.random.RandomState(0)
+    imgs, spi, T = 50, 5, 16
+    rows = imgs * spi
+
+    def cap(n):
+        a = np.zeros(n, dtype=np.int64)
+        k = rng.randint(5, n)
+        a[:k] = rng.randint(1, 9488, size=k)
+        return a
+
+    gen = np.stack([cap(T) for _ in range(rows)]); greedy = np.stack([cap(T) for _ in range(rows)])
+    gts = [[cap(T + 1) for _ in range(5)] for _ in range(imgs)]
+    hyps = [CD.caption_tokens(x) for x in list(gen) + list(greedy)]
+    gt_tok = [[CD.caption_tokens(g) for g in gts[i]] for i in range(imgs)]
+    refs = [gt_tok[(i % rows) // spi] for i in range(2 * rows)]
+    df = CD.corpus_document_frequency(refs)
+    t0 = time.perf_counter()
+    want = CD.ciderd_scores(hyps, refs, df, np.log(float(len(refs))))
+    cpu_ms = (time.perf_counter() - t0) * 1e3
+    table = RW.DocumentFrequency(df, len(refs), device)
+    g, gr = torch.from_numpy(gen).to(device), torch.from_numpy(greedy).to(device)
+    opt = SimpleNamespace(cider_weight=1.0, bleu4_weight=0, spice_weight=0, use_baseline=1)
+    RW.compute_reward(g, gr, gts, table, opt, seq_per_img=spi)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        rew, sc = RW.compute_reward(g, gr, gts, table, opt, seq_per_img=spi)
+    e1.record(); torch.cuda.synchronize()
+    gpu_ms = e0.elapsed_time(e1) / 10
+    err = float(np.abs(sc.cpu().numpy() - want).max())
+    return dict(hypotheses=2 * rows, refs_per_image=5, device_ms=round(gpu_ms, 3), cpu_port_ms=round(cpu_ms, 1),
+                max_abs_diff_vs_port=err, note="device time includes packing the references on the host each call")
 
 
 def args_dtype(args):

@@ -281,6 +281,23 @@ int rfn_rl_loss_bwd_f32(const int64_t* seq, const float* reward, const float* lp
 int rfn_multilabel_margin_bwd_f32(const float* pred, const int64_t* target, int rows, int K, float weight,
                                   const float* gout, float* dx, rfn_stream_t stream);
 
+/* ---- CIDEr-D reward scorer (cider/pyciderevalcap/ciderD/ciderD_scorer.py:114-199 as driven by
+ * get_rewards.py:39-112).  Captions are int32 token rows (the tokens up to and including the first 0 form the
+ * caption, get_rewards.py:20-27; at most 32 tokens).  hyp (n_hyp, ld_h); hyp_img[n_hyp] = image of each hypothesis;
+ * refs (n_img, R, Lr) with n_refs[n_img] valid references per image.  Document frequencies: open-addressing table
+ * df_keys (cap, 4) int32 (n-gram tokens, unused = -1, empty slot = INT32_MIN in column 0), df_vals (cap) double, cap
+ * a power of two (0 = empty table), slot = rfn_ciderd_hash(key) & (cap-1) with linear probing.  ref_len = log(#docs).
+ * sims_scratch: n_hyp*R*4 doubles.  scores (n_hyp) double = CIDEr-D x 10 per hypothesis, fp64 throughout. */
+int rfn_ciderd_scores_f64(const int32_t* hyp, int ld_h, int n_hyp, const int32_t* hyp_img, const int32_t* refs,
+                          const int32_t* n_refs, int R, int Lr, const int32_t* df_keys, const double* df_vals,
+                          int df_cap, double ref_len, double sigma, double* sims_scratch, double* scores,
+                          rfn_stream_t stream);
+/* reward[b, t] = weight * (scores[b] - scores[rows + b]) (use_baseline) or weight * scores[b], broadcast over T
+ * (get_rewards.py:96-110) */
+int rfn_ciderd_reward_f32(const double* scores, int rows, int T, double weight, int use_baseline, float* reward,
+                          rfn_stream_t stream);
+uint64_t rfn_ciderd_hash(const int32_t* key4);
+
 #ifdef __cplusplus
 }
 #endif

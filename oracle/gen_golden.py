@@ -194,6 +194,64 @@ def run_case(mod, opts, ref_utils, name, cfg, rows, wseed, iseed, wkw, stride, b
     return out
 
 
+def ciderd_case(log):
+    """CIDEr-D: reference scorer (cider/pyciderevalcap/ciderD/ciderD_scorer.py) vs oracle/ciderd_oracle.py on random
+    token captions, 'corpus' document frequencies and an injected 'coco-train'-style table."""
+    sys.path.insert(0, os.path.join(REF, "cider"))
+    from pyciderevalcap.ciderD.ciderD_scorer import CiderScorer
+    from oracle import ciderd_oracle as CD
+    from collections import defaultdict
+    rng = np.random.RandomState(0)
+    L, V, n_img, spi = 16, 30, 6, 5
+
+    def cap(maxlen):
+        n = rng.randint(1, maxlen)
+        a = np.zeros(maxlen, dtype=np.int64)
+        a[:n] = rng.randint(1, V, size=n)
+        return a
+
+    rows = n_img * spi
+    gen = np.stack([cap(L) for _ in range(rows)]); gen[3] = rng.randint(1, V, size=L)   # one caption without any 0
+    greedy = np.stack([cap(L) for _ in range(rows)]); greedy[7, 0] = 0                   # one empty caption
+    gts = [[cap(L + 1) for _ in range(rng.randint(1, 6))] for _ in range(n_img)]
+    hyps = [CD.caption_tokens(x) for x in list(gen) + list(greedy)]
+    gt_tok = [[CD.caption_tokens(g) for g in gts[i]] for i in range(n_img)]
+    refs = [gt_tok[(i % rows) // spi] for i in range(2 * rows)]
+    tostr = lambda t: " ".join(str(x) for x in t)
+    out = dict(gen=gen, greedy=greedy, n_img=n_img, spi=spi,
+               gts=np.stack([np.stack([np.pad(g, (0, 0)) for g in (gts[i] + [np.zeros(L + 1, dtype=np.int64)] * (5 - len(gts[i])))]) for i in range(n_img)]),
+               n_refs=np.array([len(g) for g in gts]))
+    # corpus mode
+    sc = CiderScorer(df_mode="corpus")
+    for h, r in zip(hyps, refs):
+        sc += (tostr(h), [tostr(x) for x in r])
+    _, ref_scores = sc.compute_score()
+    mine = CD.ciderd_scores(hyps, refs, CD.corpus_document_frequency(refs), np.log(float(len(refs))))
+    d1 = float(np.abs(mine - ref_scores).max())
+    out["scores_corpus"] = ref_scores
+    # injected document frequencies, 'coco-train' reference length
+    dfi = {}
+    for ng in list(CD.corpus_document_frequency(refs).keys())[::3]:
+        dfi[ng] = float(rng.randint(1, 5000))
+    sc2 = CiderScorer(df_mode="corpus")
+    sc2.df_mode = "coco-train-synthetic"
+    d = defaultdict(float)
+    for ng, v in dfi.items():
+        d[tuple(str(t) for t in ng)] = v
+    sc2.document_frequency = d
+    for h, r in zip(hyps, refs):
+        sc2 += (tostr(h), [tostr(x) for x in r])
+    _, ref_scores2 = sc2.compute_score()
+    mine2 = CD.ciderd_scores(hyps, refs, dfi, np.log(float(113287)))
+    d2 = float(np.abs(mine2 - ref_scores2).max())
+    out["scores_table"] = ref_scores2
+    out["df_keys"] = np.array([list(k) + [-1] * (4 - len(k)) for k in dfi.keys()], dtype=np.int64)
+    out["df_vals"] = np.array(list(dfi.values()))
+    log(f"[ciderd] oracle-vs-reference: corpus={d1:.3g}, table={d2:.3g}")
+    assert d1 < 1e-12 and d2 < 1e-12
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden"))
@@ -228,6 +286,7 @@ def main():
     for name, cfg, rows, wseed, iseed, wkw, stride in cases:
         out = run_case(mod, opts, ref_utils, name, cfg, rows, wseed, iseed, wkw, stride, log=log)
         np.savez_compressed(os.path.join(args.out, name + ".npz"), **out)
+    np.savez_compressed(os.path.join(args.out, "ciderd.npz"), **ciderd_case(log))
     with open(os.path.join(args.out, "PIN_LOG.txt"), "w") as f:
         f.write("oracle/gen_golden.py -- oracle restatement vs the imported reference modules "
                 f"(torch {torch.__version__}, CPU fp32)\n")
