@@ -334,7 +334,8 @@ def xe_train_bench(model, device, world, rank, steps, timed):
     model.drop_prob_lm = model.decoder.drop_prob_lm = 0.3
     crit = ReviewNetEnsembleCriterion(SimpleNamespace(use_label_smoothing=1, label_smoothing_epsilon=0.1, use_cuda=1))
     params = [p for p in model.parameters()]
-    opt = torch.optim.Adam(params, lr=5e-4, weight_decay=1e-5)
+    from recurrent_fusion_network_b200.optim import FusedAdam
+    opt = FusedAdam(params, lr=5e-4, weight_decay=1e-5, grad_clip=1.0)   # clamp + Adam in one HBM pass
     loss_box = [None]
 
     def step():
@@ -342,7 +343,7 @@ def xe_train_bench(model, device, world, rank, steps, timed):
         lp, rp = model(fc, att, labels)
         loss = crit(lp, labels[:, 1:], masks[:, 1:], rp, top, 10.0)
         loss.backward()
-        D.average_gradients(params, grad_clip=1.0)   # NCCL all-reduce (mean) then the reference's clamp
+        D.average_gradients(params)   # NCCL all-reduce (mean); the reference's clamp rides in the optimizer kernel
         opt.step()
         loss_box[0] = loss.detach()
         return loss_box[0], loss_box[0]
@@ -368,7 +369,7 @@ def xe_train_bench(model, device, world, rank, steps, timed):
                 kernel_ms_and_launches=train_shares, rows_per_gpu=rows, tokens_per_step=int(tokens), loss=round(float(loss_box[0]), 4),
                 note="value: as written (80 replicated rows); deduplicated: stages 1-2 once per image (SURVEY D9); per-op autograd "
                      "over our kernels, small-row GEMMs on the skinny weight-streaming kernel, backward GEMMs fp32 SIMT with "
-                     "split-K; torch.optim.Adam as in train.py:56", gpu_launches_per_step=launches // max(1, steps))
+                     "split-K; clip_gradient + Adam (train.py:56,160-163) fused in rfn_adam_step_f32", gpu_launches_per_step=launches // max(1, steps))
 
 
 def ciderd_bench(device):

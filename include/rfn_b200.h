@@ -281,6 +281,13 @@ int rfn_rl_loss_bwd_f32(const int64_t* seq, const float* reward, const float* lp
 int rfn_multilabel_margin_bwd_f32(const float* pred, const int64_t* target, int rows, int K, float weight,
                                   const float* gout, float* dx, rfn_stream_t stream);
 
+/* Fused clip_gradient (element-wise clamp to +-grad_clip, misc/utils.py:292-296; <= 0 disables) + Adam step with
+ * L2 weight decay (torch.optim.Adam semantics, train.py:56,160-163) over n_tensors parameter tensors; `step` is the
+ * 1-based update count (bias correction).  HOST arrays of device pointers / element counts. */
+int rfn_adam_step_f32(int n_tensors, float* const* p, const float* const* g, float* const* m, float* const* v,
+                      const int64_t* numel, float lr, float beta1, float beta2, float eps, float weight_decay,
+                      float grad_clip, int step, rfn_stream_t stream);
+
 /* ---- CIDEr-D reward scorer (cider/pyciderevalcap/ciderD/ciderD_scorer.py:114-199 as driven by
  * get_rewards.py:39-112).  Captions are int32 token rows (the tokens up to and including the first 0 form the
  * caption, get_rewards.py:20-27; at most 32 tokens).  hyp (n_hyp, ld_h); hyp_img[n_hyp] = image of each hypothesis;

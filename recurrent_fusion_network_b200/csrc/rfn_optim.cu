@@ -1,0 +1,78 @@
+// Fused gradient clamp + Adam step over many tensors (train.py:160-163 = clip_gradient
+// (misc/utils.py:292-296) followed by torch.optim.Adam.step with L2 weight decay).  One pass over p, g, m, v:
+// 7 floats of HBM traffic per parameter (489 M parameters -> 13.7 GB -> ~2 ms at the measured HBM rate), instead of a
+// clamp pass plus the optimizer's multi-tensor passes.
+#include "rfn_internal.cuh"
+
+namespace rfn {
+
+constexpr int AD_MAXT = 48;      // tensors per launch (pointer table travels in the kernel arguments)
+constexpr int AD_BLOCK_ELEMS = 4096;
+
+struct AdamChunk {
+  float* p[AD_MAXT];
+  const float* g[AD_MAXT];
+  float* m[AD_MAXT];
+  float* v[AD_MAXT];
+  long long n[AD_MAXT];
+  int block_start[AD_MAXT + 1];   // prefix sum of blocks per tensor
+  int nt;
+};
+
+__global__ void __launch_bounds__(256)
+adam_kernel(AdamChunk c, float lr, float beta1, float beta2, float eps, float wd, float clip, float bc1, float bc2_sqrt) {
+  int t = 0;
+  while (t + 1 < c.nt && (int)blockIdx.x >= c.block_start[t + 1]) ++t;
+  const long long base = (long long)(blockIdx.x - c.block_start[t]) * AD_BLOCK_ELEMS;
+  const long long n = c.n[t];
+  float* __restrict__ p = c.p[t];
+  const float* __restrict__ g = c.g[t];
+  float* __restrict__ m = c.m[t];
+  float* __restrict__ v = c.v[t];
+  const float step_size = lr / bc1;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < AD_BLOCK_ELEMS; i += 256) {
+    const long long k = base + i;
+    if (k >= n) break;
+    float gk = g[k];
+    if (clip > 0.f) gk = fminf(fmaxf(gk, -clip), clip);      // clip_gradient: element-wise clamp
+    const float pk = p[k];
+    gk = fmaf(wd, pk, gk);                                     // L2 weight decay added to the gradient
+    const float mk = beta1 * m[k] + (1.f - beta1) * gk;
+    const float vk = beta2 * v[k] + (1.f - beta2) * gk * gk;
+    m[k] = mk;
+    v[k] = vk;
+    const float denom = sqrtf(vk) / bc2_sqrt + eps;
+    p[k] = pk - step_size * (mk / denom);
+  }
+}
+
+}  // namespace rfn
+
+using namespace rfn;
+extern "C" int rfn_adam_step_f32(int n_tensors, float* const* p, const float* const* g, float* const* m, float* const* v,
+                                 const int64_t* numel, float lr, float beta1, float beta2, float eps, float weight_decay,
+                                 float grad_clip, int step, rfn_stream_t stream) {
+  RFN_CHECK_ARG(n_tensors >= 0 && p && g && m && v && numel && step >= 1, "rfn_adam_step_f32: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+  for (int t0 = 0; t0 < n_tensors; t0 += AD_MAXT) {
+    AdamChunk c{};
+    c.nt = 0;
+    int blocks = 0;
+    for (int t = t0; t < n_tensors && c.nt < AD_MAXT; ++t) {
+      if (numel[t] <= 0 || !g[t]) continue;
+      c.p[c.nt] = p[t]; c.g[c.nt] = g[t]; c.m[c.nt] = m[t]; c.v[c.nt] = v[t]; c.n[c.nt] = numel[t];
+      c.block_start[c.nt] = blocks;
+      blocks += (int)((numel[t] + AD_BLOCK_ELEMS - 1) / AD_BLOCK_ELEMS);
+      ++c.nt;
+    }
+    c.block_start[c.nt] = blocks;
+    if (blocks == 0) continue;
+    ProfScope prof__(TAG_MISC, st);
+    adam_kernel<<<blocks, 256, 0, st>>>(c, lr, beta1, beta2, eps, weight_decay, grad_clip, bc1, bc2_sqrt);
+    RFN_LAUNCH_CHECK();
+  }
+  return RFN_OK;
+}

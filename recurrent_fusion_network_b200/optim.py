@@ -1,0 +1,45 @@
+"""FusedAdam: torch.optim.Adam's update (train.py:56: Adam(lr, weight_decay), no amsgrad) with the reference's
+clip_gradient (misc/utils.py:292-296) folded in, as one HBM pass per step through rfn_adam_step_f32.
+Same constructor arguments / param_groups / state_dict layout conventions as torch.optim.Adam, so
+misc/utils.set_lr and the reference's checkpoint code keep working."""
+import ctypes as C
+
+import torch
+
+from ._capi import check, lib, ptr_array, stream
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_clip=0.0):
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, grad_clip=grad_clip)
+        super().__init__(params, defaults)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for group in self.param_groups:
+            ps = [p for p in group["params"] if p.grad is not None]
+            if not ps:
+                continue
+            for p in ps:
+                st = self.state[p]
+                if not st:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["step"] += 1
+                if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.grad.is_contiguous()):
+                    raise RuntimeError("FusedAdam needs contiguous fp32 CUDA parameters and gradients")
+            step = self.state[ps[0]]["step"]
+            n = len(ps)
+            numel = (C.c_int64 * n)(*[p.numel() for p in ps])
+            b1, b2 = group["betas"]
+            check(lib().rfn_adam_step_f32(n, ptr_array(ps), ptr_array([p.grad for p in ps]),
+                                          ptr_array([self.state[p]["exp_avg"] for p in ps]),
+                                          ptr_array([self.state[p]["exp_avg_sq"] for p in ps]), numel, float(group["lr"]),
+                                          float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
+                                          float(group.get("grad_clip", 0.0)), int(step), stream()), "rfn_adam_step_f32")
+        return loss

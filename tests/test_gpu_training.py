@@ -147,3 +147,25 @@ def test_row_deduplication_gives_the_same_gradients():
         a, b = grads[1][0][k], grads[g][0][k]
         assert maxdiff(a, b) <= 2e-5 * (float(a.abs().max()) + 1e-6) + 1e-7, k
 
+
+
+def test_fused_adam_matches_clip_gradient_plus_torch_adam():
+    """FusedAdam == clip_gradient (element-wise clamp) followed by torch.optim.Adam(lr, weight_decay) (train.py:56,160-163)."""
+    from recurrent_fusion_network_b200.criteria import clip_gradient
+    from recurrent_fusion_network_b200.optim import FusedAdam
+    g = torch.Generator().manual_seed(0)
+    shapes = [(3,), (17, 5), (4096,), (300, 33), (1,)] * 11          # > 48 tensors: several kernel chunks
+    a = [torch.nn.Parameter(torch.randn(s, generator=g).cuda()) for s in shapes]
+    b = [torch.nn.Parameter(p.detach().clone()) for p in a]
+    oa = torch.optim.Adam(a, lr=5e-4, weight_decay=1e-5)
+    ob = FusedAdam(b, lr=5e-4, weight_decay=1e-5, grad_clip=1.0)
+    for it in range(4):
+        for pa, pb in zip(a, b):
+            gr = torch.randn(pa.shape, generator=g).cuda() * 3
+            pa.grad = gr.clone(); pb.grad = gr.clone()
+        clip_gradient(oa, 1.0)
+        oa.step(); ob.step()
+    for pa, pb in zip(a, b):
+        assert maxdiff(pa, pb) <= 2e-6
+    ob.param_groups[0]["lr"] = 1e-4   # set_lr works through param_groups
+    ob.step()
