@@ -96,7 +96,11 @@ int rfn_profile_read(float* ms, uint64_t* launches, int n);
 /* y[M,N] = (accumulate ? y : 0) + sum_i x_i[M,K_i] . W_i[N,K_i]^T + sum_i bias_i[N]
  * replaces nn.Linear at every call site of the path, e.g. H2h(H) + z2h(z)
  * (misc/RecurrentFusionModel.py:53), i2h + h2h + z2h (misc/LSTMSoftAttentionCore.py:81).
- * n_src in 1..3; bias_i may be NULL; K_i % 4 == 0 and 16-byte aligned rows required. */
+ * n_src in 1..3; bias_i may be NULL; K_i % 4 == 0 and 16-byte aligned rows required.
+ * accumulate is a flag word: bit 0 = add into y; RFN_GEMM_SPLITK = the tensor engine may split a long contraction
+ * over clusters and add the partial tiles atomically (summation order then varies from run to run: used for the
+ * weight gradients dU = dP^T . A only, never on the decode path). */
+#define RFN_GEMM_SPLITK 2
 int rfn_linear_f32(int n_src, const float* const* x, const int* ldx, const float* const* W,
                    const int* K, const float* const* bias, float* y, int ldy, int M, int N,
                    int accumulate, rfn_stream_t stream);
@@ -232,6 +236,10 @@ int rfn_mean_log_softmax_f32(int n, const float* const* logits, int rows, int V,
  * (N,K) row-major else (K,N).  dX = dY . W is (1,0); dW += dY^T . X is (0,0). */
 int rfn_gemm_general_f32(int a_kmajor, int b_kmajor, const float* A, int lda, const float* B, int ldb,
                          float* C, int ldc, int M, int N, int K, int accumulate, rfn_stream_t stream);
+/* dst[c, r] = src[r, c] for r < rows, c < cols; dst rows are ld_dst long and columns rows..ld_dst-1 are zero-filled
+ * (ld_dst = rows rounded up to a multiple of 4).  Brings dP and A of dU = dP^T . A into the K-major layout
+ * of the tensor engine: dU = rfn_linear_f32(x = dP^T, W = A^T). */
+int rfn_transpose_f32(const float* src, int ld_src, int rows, int cols, float* dst, int ld_dst, rfn_stream_t stream);
 /* db[n] (+)= sum_m dY[m,n]  (bias gradient) */
 int rfn_colsum_f32(const float* dY, int ld, int M, int N, float* db, int accumulate, rfn_stream_t stream);
 /* backward of rfn_attention_step_f32: from dz and the saved alpha -> dP (rows,N,Ah), dg (rows,Ah),
@@ -283,10 +291,12 @@ int rfn_multilabel_margin_bwd_f32(const float* pred, const int64_t* target, int 
 
 /* Fused clip_gradient (element-wise clamp to +-grad_clip, misc/utils.py:292-296; <= 0 disables) + Adam step with
  * L2 weight decay (torch.optim.Adam semantics, train.py:56,160-163) over n_tensors parameter tensors; `step` is the
- * 1-based update count (bias correction).  HOST arrays of device pointers / element counts. */
+ * 1-based update count (bias correction).  HOST arrays of device pointers / element counts.  d_hyper (nullable):
+ * device float[2] = {step, lr} read by the kernel instead of the two host arguments, so that a captured CUDA graph
+ * of the training step follows the update count and the learning-rate schedule. */
 int rfn_adam_step_f32(int n_tensors, float* const* p, const float* const* g, float* const* m, float* const* v,
                       const int64_t* numel, float lr, float beta1, float beta2, float eps, float weight_decay,
-                      float grad_clip, int step, rfn_stream_t stream);
+                      float grad_clip, int step, const float* d_hyper, rfn_stream_t stream);
 
 /* ---- CIDEr-D reward scorer (cider/pyciderevalcap/ciderD/ciderD_scorer.py:114-199 as driven by
  * get_rewards.py:39-112).  Captions are int32 token rows (the tokens up to and including the first 0 form the

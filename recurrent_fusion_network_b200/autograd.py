@@ -82,6 +82,45 @@ def linear(srcs):
     return LinearFn.apply(n, *[x for x, _ in srcs], *[m.weight for _, m in srcs], *[m.bias for _, m in srcs])
 
 
+_TRANSPOSED = {}   # data_ptr -> (version, shape, A^T): features transposed once per training step (cleared by _stages)
+
+
+def clear_transposed_cache():
+    _TRANSPOSED.clear()
+
+
+def _transpose(x2d):
+    rows, cols = x2d.shape
+    ld = (rows + 3) // 4 * 4
+    out = torch.empty(cols, ld, dtype=torch.float32, device=x2d.device)
+    check(lib().rfn_transpose_f32(ptr(x2d), x2d.stride(0), rows, cols, ptr(out), ld, stream()), "rfn_transpose_f32")
+    return out
+
+
+def _transposed_features(A2):
+    key = A2.data_ptr()
+    hit = _TRANSPOSED.get(key)
+    if hit is None or hit[0] != A2._version or hit[1] != tuple(A2.shape):
+        hit = (A2._version, tuple(A2.shape), _transpose(A2))
+        _TRANSPOSED[key] = hit
+    return hit[2]
+
+
+def _dw_long(dY, X2, out_features, in_features):
+    """dW = dY^T . X for a long contraction (rows x attention locations) on the tensor engine: both operands are
+    brought into its K-major layout (X^T cached across the steps that share the features) and the contraction is
+    split over clusters (RFN_GEMM_SPLITK)."""
+    dYt = _transpose(dY)
+    Xt = _transposed_features(X2)
+    K = dYt.shape[1]
+    dW = torch.empty(out_features, in_features, dtype=torch.float32, device=dY.device)
+    ld = (C.c_int * 1)(K)
+    ks = (C.c_int * 1)(K)
+    check(lib().rfn_linear_f32(1, ptr_array([dYt]), ld, ptr_array([Xt]), ks, ptr_array([None]), ptr(dW), in_features,
+                               out_features, in_features, 2, stream()), "rfn_linear_f32")
+    return dW
+
+
 class AttentionFn(Function):
     """AttentionModelCore.forward (misc/AttentionModelCore.py:31-48) with its full backward."""
 
@@ -118,8 +157,11 @@ class AttentionFn(Function):
                                                ptr(dw), ptr(dwb), ptr(dA), rows, N, D, Ah, 1, stream()),
               "rfn_attention_step_bwd_f32")
         A2 = A.view(rows * N, D)
-        dU_w = torch.empty(Ah, D, dtype=torch.float32, device=dev)
-        _gemm_general(0, 0, dP, Ah, A2, D, dU_w, D, Ah, D, rows * N)          # dU = dP^T . A
+        if rows * N >= 1024 and Ah >= 256 and D >= 256 and D % 4 == 0 and not need_dA and lib().rfn_get_gemm_mode() >= 1:
+            dU_w = _dw_long(dP, A2, Ah, D)                                     # dU = dP^T . A on the tensor engine
+        else:
+            dU_w = torch.empty(Ah, D, dtype=torch.float32, device=dev)
+            _gemm_general(0, 0, dP, Ah, A2, D, dU_w, D, Ah, D, rows * N)      # dU = dP^T . A
         dU_b = torch.empty(Ah, dtype=torch.float32, device=dev)
         check(lib().rfn_colsum_f32(ptr(dP), Ah, rows * N, Ah, ptr(dU_b), 0, stream()), "rfn_colsum_f32")
         if need_dA:                                                            # dA += dP . U

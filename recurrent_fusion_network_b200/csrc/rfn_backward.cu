@@ -103,6 +103,25 @@ __global__ void __launch_bounds__(256) gemm_gen_kernel(GemmGenArgs a) {
   }
 }
 
+// dst[c][r] = src[r][c], zero padding up to ld_dst
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ src, int ld_src, int rows, int cols,
+                                                        float* __restrict__ dst, int ld_dst) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < rows && c < cols) ? src[(size_t)r * ld_src + c] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (c < cols && r < ld_dst) dst[(size_t)c * ld_dst + r] = tile[tx][i];
+  }
+}
+
 int gemm_general(bool a_kmajor, bool b_kmajor, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M,
                  int N, int K, int accumulate, cudaStream_t st) {
   ProfScope prof__(TAG_GEMM_BWD, st);
@@ -605,6 +624,16 @@ int multilabel_margin_bwd(const float* pred, const int64_t* target, int rows, in
 using namespace rfn;
 extern "C" {
 
+int rfn_transpose_f32(const float* src, int ld_src, int rows, int cols, float* dst, int ld_dst, rfn_stream_t stream) {
+  RFN_CHECK_ARG(src && dst && rows >= 0 && cols >= 0 && ld_src >= cols && ld_dst >= rows, "rfn_transpose_f32: bad arguments");
+  if (rows == 0 || cols == 0) return RFN_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof__(TAG_GEMM_BWD, st);
+  dim3 grid((ld_dst + 31) / 32, (cols + 31) / 32);
+  transpose_kernel<<<grid, 256, 0, st>>>(src, ld_src, rows, cols, dst, ld_dst);
+  RFN_LAUNCH_CHECK();
+  return RFN_OK;
+}
 int rfn_gemm_general_f32(int a_kmajor, int b_kmajor, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                          int M, int N, int K, int accumulate, rfn_stream_t stream) {
   return gemm_general(a_kmajor != 0, b_kmajor != 0, A, lda, B, ldb, C, ldc, M, N, K, accumulate, (cudaStream_t)stream);

@@ -27,6 +27,6 @@ extern "C" int rfn_linear_f32_engine(int engine, int n_src, const float* const* 
   rfn::GemmArgs a{};
   a.nsrc = n_src;
   for (int s = 0; s < n_src; ++s) a.src[s] = rfn::GemmSrc{x[s], W[s], bias ? bias[s] : nullptr, ldx[s], K[s], K[s]};
-  a.y = y; a.ldy = ldy; a.M = M; a.N = N; a.accumulate = accumulate;
+  a.y = y; a.ldy = ldy; a.M = M; a.N = N; a.accumulate = accumulate & 1; a.splitk_ok = (accumulate & RFN_GEMM_SPLITK) ? 1 : 0;
   return rfn::gemm_engine(a, engine, (cudaStream_t)stream);
 }

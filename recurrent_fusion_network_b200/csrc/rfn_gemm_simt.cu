@@ -251,6 +251,6 @@ extern "C" int rfn_linear_f32(int n_src, const float* const* x, const int* ldx, 
   a.ldy = ldy;
   a.M = M;
   a.N = N;
-  a.accumulate = accumulate;
+  a.accumulate = accumulate & 1; a.splitk_ok = (accumulate & RFN_GEMM_SPLITK) ? 1 : 0;
   return rfn::gemm(a, (cudaStream_t)stream);
 }

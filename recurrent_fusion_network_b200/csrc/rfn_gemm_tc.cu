@@ -20,6 +20,8 @@
 // torch stores them; ragged M / N / K edges are zero-filled by TMA.
 #include <cuda.h>
 
+#include <algorithm>
+
 #include <atomic>
 
 #include "rfn_internal.cuh"
@@ -406,6 +408,22 @@ int gemm_tc(const GemmArgs& a, int passes, const float* g, int ldg, const float*
   t.epi = score ? 1 : 0;
   t.g = g; t.ldg = ldg; t.wv = wv; t.score = score; t.natt = natt > 0 ? natt : 1;
   t.dbg = (g_tc_dbg_epi.load() < 0 || g_tc_dbg_epi.load() == t.epi) ? g_tc_dbg.load() : nullptr;
+  // few output tiles and a long contraction (weight gradients dU = dP^T . A over rows x locations): split K over
+  // clusters so that one wave of 74 cluster slots is filled; partial tiles are added with red.global.add
+  if (cluster && t.epi == 0 && a.nsrc == 1 && a.splitk_ok) {
+    const int tiles = ((a.N + 255) / 256) * ((a.M + 255) / 256);
+    const int nkb = (a.src[0].K + TC_BK - 1) / TC_BK;
+    int ks = std::min(74 / std::max(tiles, 1), nkb / 16);
+    if (ks > 1) {
+      const int kper = (nkb + ks - 1) / ks;
+      ks = (nkb + kper - 1) / kper;             // every slice non-empty
+      if (ks > 1) {
+        t.ksplit = ks;
+        if (!a.accumulate)
+          RFN_CUDA(cudaMemset2DAsync(a.y, (size_t)a.ldy * sizeof(float), 0, (size_t)a.N * sizeof(float), (size_t)a.M, st));
+      }
+    }
+  }
   // persistent clusters for the fused-epilogue GEMMs; the plain-store GEMMs keep the 3-stage one-tile kernel
   // (the persistent store epilogue needs staging memory that costs a pipeline stage: measured slower)
   if (cluster) return (g_tc_cluster.load() >= 2 && passes == 3 && t.epi != 0) ? launch_tc2p(t, st) : launch_tc2(t, passes, st);

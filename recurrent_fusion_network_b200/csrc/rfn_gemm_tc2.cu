@@ -52,12 +52,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc2_kernel(const __grid_co
   if (dbg && threadIdx.x == 0) dbg[0] = clock64();
   const uint32_t rank = cluster_ctarank();
   const bool leader = (rank == 0);
-  const int cid = blockIdx.x >> 1;
+  const int tiles_all = n_tiles * ((a.M + 2 * TC_BM - 1) / (2 * TC_BM));
+  const int cid = (int)(blockIdx.x >> 1) % tiles_all;
+  const int kz = (int)(blockIdx.x >> 1) / tiles_all;                  // split-K slice (0 when ksplit == 1)
   const int n0 = (cid % n_tiles) * T2_BN;
   const int m0 = (cid / n_tiles) * (2 * TC_BM) + (int)rank * TC_BM;   // this CTA's 128 rows
 
   int total_kb = 0;
   for (int s = 0; s < a.nsrc; ++s) total_kb += (a.K[s] + TC_BK - 1) / TC_BK;
+  int kb_first = 0;                                                   // split-K: one source, k-blocks [kb_first, +total_kb)
+  if (EPI == 0 && a.ksplit > 1) {
+    const int kper = (total_kb + a.ksplit - 1) / a.ksplit;
+    kb_first = kz * kper;
+    total_kb = min(total_kb, kb_first + kper) - kb_first;
+  }
   const int nchunk = DRAIN ? (total_kb + CH - 1) / CH : 1;
 
   if (warp == 0 && lane == 0) {
@@ -86,8 +94,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc2_kernel(const __grid_co
     if (lane == 0) {
       int it = 0;
       for (int s = 0; s < a.nsrc; ++s) {
-        const int nkb = (a.K[s] + TC_BK - 1) / TC_BK;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int nkb = (EPI == 0 && a.ksplit > 1) ? kb_first + total_kb : (a.K[s] + TC_BK - 1) / TC_BK;
+        for (int kb = kb_first; kb < nkb; ++kb, ++it) {
           const int st = it % STAGES;
           const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
           mbar_wait(smem_u32(&empty[st]), ph ^ 1u);
@@ -145,7 +153,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc2_kernel(const __grid_co
     float acc[COLS];
 #pragma unroll
     for (int i = 0; i < COLS; ++i) acc[i] = 0.f;
-    tc_stage_bias<T2_BN>(a, n0, wt, s_bias, EPI == 1 ? s_wv : nullptr);
+    tc_stage_bias<T2_BN>(a, n0, wt, s_bias, EPI == 1 ? s_wv : nullptr, kz == 0);
 
     auto signal = [&](uint64_t* bar) {   // arrive on the LEADER's barrier
       if (leader) mbar_arrive(smem_u32(bar)); else mbar_arrive_remote(smem_u32(bar), 0);
@@ -203,7 +211,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc2_kernel(const __grid_co
     if (EPI == 0) {
       // all MMAs have retired (last chunk drained), so the operand ring is free: stage the tile through it
       float* stage = reinterpret_cast<float*>(smem) + (size_t)(warp - 2) * 32 * (COLS + 4);
-      tc_epilogue_store<COLS>(acc, stage, a, m0 + wq * 32, nb, lane, s_bias + half * COLS);
+      tc_epilogue_store<COLS>(acc, stage, a, m0 + wq * 32, nb, lane, s_bias + half * COLS, a.ksplit > 1);
     } else if (EPI == 1) {
       // g rows (one per image) are staged through the dead operand ring: a warp's 32 consecutive rows span
       // mg_first .. mg_last; reading g straight from global memory cost one L2 round trip per float4
@@ -298,7 +306,8 @@ static int launch_tc2_epi(const TcArgs& t, cudaStream_t st) {
   const int n_tiles = (t.N + T2_BN - 1) / T2_BN;
   const int n_pairs = (t.M + 2 * TC_BM - 1) / (2 * TC_BM);
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(2 * n_tiles * n_pairs), 1, 1);
+  const int ksplit = (EPI == 0 && t.ksplit > 1) ? t.ksplit : 1;
+  cfg.gridDim = dim3((unsigned)(2 * n_tiles * n_pairs * ksplit), 1, 1);
   cfg.blockDim = dim3(TC_THREADS, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;

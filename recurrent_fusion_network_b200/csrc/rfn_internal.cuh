@@ -80,6 +80,7 @@ struct GemmArgs {
   int M;
   int N;
   int accumulate;
+  int splitk_ok;   // the caller accepts a split-K sum (atomic adds: summation order not reproducible); weight gradients only
 };
 int gemm_simt(const GemmArgs& a, cudaStream_t st);
 // tcgen05 engine: passes 3 = 3xTF32 (fp32-equivalent), 1 = single-pass TF32; score != nullptr selects

@@ -20,7 +20,14 @@ struct AdamChunk {
 };
 
 __global__ void __launch_bounds__(256)
-adam_kernel(AdamChunk c, float lr, float beta1, float beta2, float eps, float wd, float clip, float bc1, float bc2_sqrt) {
+adam_kernel(AdamChunk c, float lr, float beta1, float beta2, float eps, float wd, float clip, float bc1, float bc2_sqrt,
+            const float* __restrict__ d_hyper) {
+  if (d_hyper) {   // capturable mode: {step, lr} live in device memory so that a CUDA graph replay sees new values
+    const float step = d_hyper[0];
+    lr = d_hyper[1];
+    bc1 = 1.f - powf(beta1, step);
+    bc2_sqrt = sqrtf(1.f - powf(beta2, step));
+  }
   int t = 0;
   while (t + 1 < c.nt && (int)blockIdx.x >= c.block_start[t + 1]) ++t;
   const long long base = (long long)(blockIdx.x - c.block_start[t]) * AD_BLOCK_ELEMS;
@@ -52,8 +59,8 @@ adam_kernel(AdamChunk c, float lr, float beta1, float beta2, float eps, float wd
 using namespace rfn;
 extern "C" int rfn_adam_step_f32(int n_tensors, float* const* p, const float* const* g, float* const* m, float* const* v,
                                  const int64_t* numel, float lr, float beta1, float beta2, float eps, float weight_decay,
-                                 float grad_clip, int step, rfn_stream_t stream) {
-  RFN_CHECK_ARG(n_tensors >= 0 && p && g && m && v && numel && step >= 1, "rfn_adam_step_f32: bad arguments");
+                                 float grad_clip, int step, const float* d_hyper, rfn_stream_t stream) {
+  RFN_CHECK_ARG(n_tensors >= 0 && p && g && m && v && numel && (step >= 1 || d_hyper), "rfn_adam_step_f32: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
@@ -71,7 +78,7 @@ extern "C" int rfn_adam_step_f32(int n_tensors, float* const* p, const float* co
     c.block_start[c.nt] = blocks;
     if (blocks == 0) continue;
     ProfScope prof__(TAG_MISC, st);
-    adam_kernel<<<blocks, 256, 0, st>>>(c, lr, beta1, beta2, eps, weight_decay, grad_clip, bc1, bc2_sqrt);
+    adam_kernel<<<blocks, 256, 0, st>>>(c, lr, beta1, beta2, eps, weight_decay, grad_clip, bc1, bc2_sqrt, d_hyper);
     RFN_LAUNCH_CHECK();
   }
   return RFN_OK;

@@ -17,6 +17,10 @@ struct TcArgs {
   int ldy;
   int M, N;
   int accumulate;
+  // split-K (2-CTA store kernel only, one source): cluster z of ksplit owns a contiguous range of k-blocks and adds its
+  // partial tile with red.global.add (y pre-zeroed or accumulated into); used by the weight-gradient GEMMs whose output
+  // has few tiles and whose contraction runs over rows x attention locations
+  int ksplit;
   // fused attention-score epilogue (epi == 1)
   int epi;
   const float* g;   // (rows, ldg)   h_2_att_h(h)

@@ -13,11 +13,12 @@ namespace rfn {
 // att_h_2_out weights into shared memory during the prologue: per-thread global loads in the epilogue formed a
 // serialized long-scoreboard chain (~10k cycles per tile, profiles/r1_epi0 source view).
 template <int BN>
-__device__ __forceinline__ void tc_stage_bias(const TcArgs& a, int n0, int t /* 0..255 */, float* s_bias, float* s_wv) {
+__device__ __forceinline__ void tc_stage_bias(const TcArgs& a, int n0, int t /* 0..255 */, float* s_bias, float* s_wv,
+                                              bool with_bias = true) {
   if (t < BN) {
     const int n = n0 + t;
     float b = 0.f;
-    if (n < a.N)
+    if (n < a.N && with_bias)
       for (int s = 0; s < a.nsrc; ++s)
         if (a.bias[s]) b += __ldg(a.bias[s] + n);
     s_bias[t] = b;
@@ -36,7 +37,8 @@ __device__ __forceinline__ float tc_tanh(float x) {
 
 template <int COLS>
 __device__ __forceinline__ void tc_epilogue_store(float (&acc)[COLS], float* stage /* this warp's 32 x (COLS+4) floats */,
-                                                  const TcArgs& a, int m_base, int nb, int lane, const float* s_bias_half) {
+                                                  const TcArgs& a, int m_base, int nb, int lane, const float* s_bias_half,
+                                                  bool atomic = false) {
   constexpr int LD = COLS + 4;
   // bias is the same for every row: add it on the way into shared memory
 #pragma unroll
@@ -57,6 +59,10 @@ __device__ __forceinline__ void tc_epilogue_store(float (&acc)[COLS], float* sta
       const int n = nb + c;
       if (n + 3 < a.N) {
         float4 o = *reinterpret_cast<const float4*>(stage + r * LD + c);
+        if (atomic) {   // split-K partial tile
+          atomicAdd(yr + n, o.x); atomicAdd(yr + n + 1, o.y); atomicAdd(yr + n + 2, o.z); atomicAdd(yr + n + 3, o.w);
+          continue;
+        }
         if (a.accumulate) {
           const float4 t = *reinterpret_cast<const float4*>(yr + n);
           o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;

@@ -1,18 +1,49 @@
 """FusedAdam: torch.optim.Adam's update (train.py:56: Adam(lr, weight_decay), no amsgrad) with the reference's
 clip_gradient (misc/utils.py:292-296) folded in, as one HBM pass per step through rfn_adam_step_f32.
-Same constructor arguments / param_groups / state_dict layout conventions as torch.optim.Adam, so
-misc/utils.set_lr and the reference's checkpoint code keep working."""
+Same constructor arguments / param_groups / state conventions as torch.optim.Adam, so misc/utils.set_lr and the
+reference's checkpoint code keep working.
+
+capturable=True keeps {step, lr} of each group in a device tensor that the kernel reads, so that step() can be
+captured in a CUDA graph (training.GraphedXEStep): the update count advances on the device and `sync_lr()` pushes a
+changed param_group['lr'] before the next replay."""
 import ctypes as C
 
 import torch
 
-from ._capi import check, lib, ptr_array, stream
+from ._capi import check, lib, ptr, ptr_array, stream
 
 
 class FusedAdam(torch.optim.Optimizer):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_clip=0.0):
-        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, grad_clip=grad_clip)
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_clip=0.0, capturable=False):
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, grad_clip=grad_clip, capturable=capturable)
         super().__init__(params, defaults)
+        self._hyper_t = {}     # group index -> (device {step, lr}, device {1, 0}); kept out of param_groups / state_dict
+
+    def _hyper(self, gi, group):
+        if gi not in self._hyper_t:
+            dev = group["params"][0].device
+            self._hyper_t[gi] = (torch.tensor([0.0, float(group["lr"])], dtype=torch.float32, device=dev),
+                                 torch.tensor([1.0, 0.0], dtype=torch.float32, device=dev))
+        return self._hyper_t[gi]
+
+    def init_state(self):
+        """Allocates exp_avg / exp_avg_sq (and the device {step, lr}) now instead of at the first step(): a CUDA-graph
+        capture of step() must not contain the zero-fills."""
+        for gi, group in enumerate(self.param_groups):
+            for p in group["params"]:
+                st = self.state[p]
+                if p.requires_grad and not st:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            if group.get("capturable"):
+                self._hyper(gi, group)
+
+    def sync_lr(self):
+        """capturable mode: copy each group's lr to the device (call after misc/utils.set_lr)."""
+        for gi, group in enumerate(self.param_groups):
+            if group.get("capturable"):
+                self._hyper(gi, group)[0][1] = float(group["lr"])
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -20,7 +51,7 @@ class FusedAdam(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        for group in self.param_groups:
+        for gi, group in enumerate(self.param_groups):
             ps = [p for p in group["params"] if p.grad is not None]
             if not ps:
                 continue
@@ -30,9 +61,13 @@ class FusedAdam(torch.optim.Optimizer):
                     st["step"] = 0
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                st["step"] += 1
+                st["step"] += 1     # host mirror; not advanced by graph replays
                 if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.grad.is_contiguous()):
                     raise RuntimeError("FusedAdam needs contiguous fp32 CUDA parameters and gradients")
+            hyper = None
+            if group.get("capturable"):
+                hyper, one = self._hyper(gi, group)
+                hyper.add_(one)                    # step += 1 on the device (captured with the graph)
             step = self.state[ps[0]]["step"]
             n = len(ps)
             numel = (C.c_int64 * n)(*[p.numel() for p in ps])
@@ -41,5 +76,6 @@ class FusedAdam(torch.optim.Optimizer):
                                           ptr_array([self.state[p]["exp_avg"] for p in ps]),
                                           ptr_array([self.state[p]["exp_avg_sq"] for p in ps]), numel, float(group["lr"]),
                                           float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
-                                          float(group.get("grad_clip", 0.0)), int(step), stream()), "rfn_adam_step_f32")
+                                          float(group.get("grad_clip", 0.0)), int(step), ptr(hyper), stream()),
+                  "rfn_adam_step_f32")
         return loss

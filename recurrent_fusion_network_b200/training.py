@@ -37,6 +37,7 @@ def _stages(model, fc, att):
     image and no stage-1/2 dropout) the stages run on the unique rows only and their outputs are expanded."""
     g = int(getattr(model, "dedup_rows", 1) or 1)
     rows = fc[0].shape[0]
+    AG.clear_transposed_cache()
     if g > 1 and rows % g == 0 and not (model._dropout_active(model.drop_prob_fusion) or
                                         model._dropout_active(model.drop_prob_reason)):
         fcu = [f[::g].contiguous() for f in fc]
@@ -133,3 +134,65 @@ def rl_criterion(crit, input, seq, reward, logprobs_all, entropy_reg, top_pred, 
         terms.append(AG.MarginFn.apply(p, top_true, reason_weight / len(top_pred)))
     return AG.AddScalarsFn.apply(*terms)[0]
 
+
+
+class GraphedXEStep:
+    """One XE training step (train.py:154-163: zero_grad, forward, criterion, backward, clip_gradient, Adam) captured as
+    CUDA graphs and replayed: the eager step issues ~2,600 kernels from Python and is bound by the host, not the device.
+
+    Two graphs -- forward+backward, and the optimizer -- so that the data-parallel gradient all-reduce
+    (dist.average_gradients) runs between them.  Inputs are copied into static buffers before each replay.  The decode
+    loop is captured over seq_length + 1 label columns (the reference stops at the first all-zero column, :274-275,
+    which is at most that many; columns it would have skipped carry mask 0 and contribute nothing to the loss or the
+    gradients).  Needs ss_prob == 0 (scheduled sampling
+    reads a mask back to the host) and a FusedAdam(capturable=True)."""
+
+    def __init__(self, model, crit, optimizer, fc, att, labels, masks, top_true, reason_weight, warmup=3, between=None):
+        if model.ss_prob > 0.0:
+            raise RuntimeError("GraphedXEStep: scheduled sampling is not capturable (ss_prob must be 0)")
+        if not all(g.get("capturable") for g in optimizer.param_groups):
+            raise RuntimeError("GraphedXEStep needs FusedAdam(capturable=True)")
+        self.model, self.crit, self.opt, self.between = model, crit, optimizer, between
+        self.reason_weight = float(reason_weight)
+        self.fc = [f.clone() for f in fc]
+        self.att = [a.clone() for a in att]
+        self.labels, self.masks, self.top = labels.clone(), masks.clone(), top_true.clone()
+        self.col_any = [True] * (labels.size(1) - 1) + [False]   # the last label column is always <pad>: stop there as :274-275 does
+        self.loss = None
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        optimizer.init_state()
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):     # allocator and lazy kernel attributes; parameters are not touched
+                self._fwd_bwd()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.g_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_fb):
+            self.loss = self._fwd_bwd()
+        self.g_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_opt, pool=self.g_fb.pool()):
+            optimizer.step()
+
+    def _fwd_bwd(self):
+        self.opt.zero_grad(set_to_none=True)
+        lp, rp = forward_xe(self.model, self.fc, self.att, self.labels, col_any=self.col_any)
+        loss = self.crit(lp, self.labels[:, 1:], self.masks[:, 1:], rp, self.top, self.reason_weight)
+        loss.backward()
+        return loss.detach()
+
+    def __call__(self, fc=None, att=None, labels=None, masks=None, top_true=None):
+        """Replays the step on new data (same shapes); returns the loss tensor (device, overwritten by the next call)."""
+        if fc is not None:
+            for d, s in zip(self.fc, fc):
+                d.copy_(s, non_blocking=True)
+            for d, s in zip(self.att, att):
+                d.copy_(s, non_blocking=True)
+            self.labels.copy_(labels, non_blocking=True)
+            self.masks.copy_(masks, non_blocking=True)
+            self.top.copy_(top_true, non_blocking=True)
+        self.g_fb.replay()
+        if self.between is not None:
+            self.between()
+        self.g_opt.replay()
+        return self.loss

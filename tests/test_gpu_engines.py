@@ -167,3 +167,61 @@ def test_library_services_profile_concurrency_and_errors():
     rc = lib().rfn_thought_vectors(C.byref(m._dims), m._params(), ptr_array(cuda_list(fc)), None, None, ptr_array(cuda_list(att)), 5,
                                    ptr(TVc), ptr(h), ptr(h.clone()), None, None, ptr(ws), ws.numel(), stream())
     assert rc == -3 and b"workspace" in lib().rfn_last_error()
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 2048, 15680), (512, 1536, 3136), (256, 260, 1028), (512, 2208, 784)])
+def test_split_k_weight_gradient_gemm(M, N, K):
+    """RFN_GEMM_SPLITK: long contraction, few output tiles (dU = dP^T . A) split over clusters, partial tiles added
+    atomically; with and without accumulation into y."""
+    g = torch.Generator().manual_seed(K)
+    x = torch.randn(M, K, generator=g).cuda()
+    w = ((torch.rand(N, K, generator=g) * 2 - 1) * 0.1).cuda()
+    want = x.double() @ w.double().t()
+    scale = float(want.abs().max())
+    y = _linear_engine_flags(1, x, w, M, N, 2)
+    assert maxdiff(y, want) <= 3e-6 * scale
+    y0 = torch.randn(M, N, generator=g).cuda()
+    y = _linear_engine_flags(1, x, w, M, N, 3, y0.clone())
+    assert maxdiff(y, want + y0.double()) <= 3e-6 * scale
+
+
+def _linear_engine_flags(engine, x, w, M, N, flags, y=None):
+    from recurrent_fusion_network_b200._capi import check, lib, ptr, ptr_array, stream
+    y = torch.empty(M, N, device="cuda") if y is None else y
+    ld = (C.c_int * 1)(x.stride(0))
+    ks = (C.c_int * 1)(x.shape[1])
+    check(lib().rfn_linear_f32_engine(engine, 1, ptr_array([x]), ld, ptr_array([w]), ks, ptr_array([None]), ptr(y), N, M, N,
+                                      flags, stream()), "rfn_linear_f32_engine")
+    return y
+
+
+def test_transpose_with_zero_padding():
+    from recurrent_fusion_network_b200.autograd import _transpose
+    g = torch.Generator().manual_seed(3)
+    for rows, cols in [(5, 7), (1000, 130), (33, 64), (3137, 512)]:
+        big = torch.randn(rows, cols + 3, generator=g).cuda()
+        x = big[:, :cols]
+        t = _transpose(x)
+        assert t.shape == (cols, (rows + 3) // 4 * 4)
+        assert torch.equal(t[:, :rows], x.t()) and float(t[:, rows:].abs().sum()) == 0.0
+
+
+def test_attention_backward_tensor_engine_weight_gradient():
+    """AttentionFn.backward: dU = dP^T . A through transposes + the split-K tensor GEMM == the fp32 SIMT general GEMM."""
+    from recurrent_fusion_network_b200 import _capi, autograd as AG
+    g = torch.Generator().manual_seed(9)
+    rows, N, D, R, Ah = 12, 196, 512, 256, 256
+    mk = lambda *s: (torch.randn(*s, generator=g) * 0.1).cuda().requires_grad_(True)
+    h, U_w, U_b, Wh_w, Wh_b, v_w, v_b = mk(rows, R), mk(Ah, D), mk(Ah), mk(Ah, R), mk(Ah), mk(1, Ah), mk(1)
+    A = torch.randn(rows, N, D, generator=g).cuda()
+    dz = torch.randn(rows, D, generator=g).cuda()
+    grads = {}
+    for mode in (1, 0):
+        _capi.check(_capi.lib().rfn_set_gemm_mode(mode))
+        AG.clear_transposed_cache()
+        z = AG.AttentionFn.apply(h, A, U_w, U_b, Wh_w, Wh_b, v_w, v_b)
+        grads[mode] = torch.autograd.grad(z, [h, U_w, U_b, Wh_w], dz)
+    _capi.check(_capi.lib().rfn_set_gemm_mode(1))
+    for a, b in zip(grads[1], grads[0]):
+        assert maxdiff(a, b) <= 2e-5 * max(1.0, float(b.abs().max()))
+    assert float(grads[1][1].abs().max()) > 0

@@ -169,3 +169,52 @@ def test_fused_adam_matches_clip_gradient_plus_torch_adam():
         assert maxdiff(pa, pb) <= 2e-6
     ob.param_groups[0]["lr"] = 1e-4   # set_lr works through param_groups
     ob.step()
+
+
+def test_graphed_xe_step_matches_eager_steps():
+    """training.GraphedXEStep (CUDA graphs of forward+backward and of clip+Adam) == the eager step, three steps with
+    fresh data each, dropout off (a captured dropout draws from the graph-safe Philox stream, not the eager one)."""
+    from types import SimpleNamespace
+    from recurrent_fusion_network_b200 import training as T
+    from recurrent_fusion_network_b200.criteria import ReviewNetEnsembleCriterion
+    from recurrent_fusion_network_b200.optim import FusedAdam
+    cfg = O.tiny_config(2)
+    sd = O.make_state_dict(cfg, seed=11, init_range=0.5)
+    rows = 6
+    crit = ReviewNetEnsembleCriterion(SimpleNamespace(use_label_smoothing=1, label_smoothing_epsilon=0.1, use_cuda=1))
+
+    def batch(seed):
+        fc, att = O.make_inputs(cfg, rows, seed=seed)
+        labels, masks, top = O.make_labels(cfg, rows, seed=seed)
+        return cuda_list(fc), cuda_list(att), labels.cuda(), masks.cuda().float(), top.cuda()
+
+    def make():
+        m = build_model(cfg, sd)
+        m.train()
+        m.drop_prob_lm = m.decoder.drop_prob_lm = 0.0
+        return m, FusedAdam(m.parameters(), lr=1e-3, weight_decay=1e-5, grad_clip=1.0, capturable=True)
+
+    ma, oa = make()
+    losses_a = []
+    for s in (1, 2, 3, 4, 5, 6):
+        fc, att, labels, masks, top = batch(s)
+        oa.zero_grad(set_to_none=True)
+        lp, rp = ma(fc, att, labels)
+        loss = crit(lp, labels[:, 1:], masks[:, 1:], rp, top, 10.0)
+        loss.backward()
+        oa.step()
+        losses_a.append(float(loss))
+    mb, ob = make()
+    step = T.GraphedXEStep(mb, crit, ob, *batch(1), 10.0, warmup=1)
+    # capture does not execute: replay the six batches
+    losses_b = [float(step(*batch(s))) for s in (1, 2, 3, 4, 5, 6)]
+    assert max(abs(a - b) for a, b in zip(losses_a, losses_b)) <= 1e-4 * max(1.0, abs(losses_a[0]))
+    worst = {}
+    for (k, pa), (_, pb) in zip(ma.state_dict().items(), mb.state_dict().items()):
+        if k.endswith("att_h_2_out.bias"):
+            # softmax is shift-invariant: this gradient is analytically 0, what arrives is atomic-add rounding noise, and
+            # Adam turns noise of either sign into +-lr steps (the reference's parameter random-walks the same way)
+            continue
+        worst[k] = maxdiff(pa, pb)
+    bad = {k: v for k, v in worst.items() if v > 2e-5}
+    assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:5]
