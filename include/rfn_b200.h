@@ -236,6 +236,10 @@ int rfn_mean_log_softmax_f32(int n, const float* const* logits, int rows, int V,
  * (N,K) row-major else (K,N).  dX = dY . W is (1,0); dW += dY^T . X is (0,0). */
 int rfn_gemm_general_f32(int a_kmajor, int b_kmajor, const float* A, int lda, const float* B, int ldb,
                          float* C, int ldc, int M, int N, int K, int accumulate, rfn_stream_t stream);
+/* Same contraction on an explicitly chosen engine (0 = fp32 SIMT; 1 / 2 = tcgen05 3xTF32 / TF32, layout (1,0) only: the B
+ * operand is read MN-major, no transposed copy of the weights); used by the engine parity tests. */
+int rfn_gemm_general_f32_engine(int engine, int a_kmajor, int b_kmajor, const float* A, int lda, const float* B, int ldb,
+                                float* C, int ldc, int M, int N, int K, int accumulate, rfn_stream_t stream);
 /* dst[c, r] = src[r, c] for r < rows, c < cols; dst rows are ld_dst long and columns rows..ld_dst-1 are zero-filled
  * (ld_dst = rows rounded up to a multiple of 4).  Brings dP and A of dU = dP^T . A into the K-major layout
  * of the tensor engine: dU = rfn_linear_f32(x = dP^T, W = A^T). */

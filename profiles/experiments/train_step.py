@@ -20,7 +20,8 @@ for b in range(rows):
 labels, masks, top = labels.to(dev), masks.to(dev), top.to(dev)
 model.train(); model.dedup_rows = int(sys.argv[1]) if len(sys.argv) > 1 else 5
 crit = ReviewNetEnsembleCriterion(SimpleNamespace(use_label_smoothing=1, label_smoothing_epsilon=0.1, use_cuda=1))
-opt = torch.optim.Adam(model.parameters(), lr=5e-4, weight_decay=1e-5)
+from recurrent_fusion_network_b200.optim import FusedAdam
+opt = FusedAdam(model.parameters(), lr=5e-4, weight_decay=1e-5, grad_clip=1.0)
 for it in range(2):
     opt.zero_grad(set_to_none=True)
     lp, rp = model(fc, att, labels)

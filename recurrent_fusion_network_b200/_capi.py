@@ -77,6 +77,7 @@ _SIGNATURES = {
     "rfn_multilabel_margin_f32": (_i, [_vp, _vp, _i, _i, _f, _i, _vp, _vp]),
     "rfn_mean_log_softmax_f32": (_i, [_i, _pp, _i, _i, _vp, _vp, _vp]),
     "rfn_gemm_general_f32": (_i, [_i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
+    "rfn_gemm_general_f32_engine": (_i, [_i, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
     "rfn_colsum_f32": (_i, [_vp, _i, _i, _i, _vp, _i, _vp]),
     "rfn_attention_step_bwd_f32": (_i, [_vp] * 6 + [_i] + [_vp] * 5 + [_i] * 5 + [_vp]),
     "rfn_lstm_cell_bwd_f32": (_i, [_vp] * 6 + [_i, _i, _vp]),

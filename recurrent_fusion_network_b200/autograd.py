@@ -33,7 +33,7 @@ def _linear_fwd(xs, Ws, bs, rows, out_features):
         ks = (C.c_int * len(grp))(*[xs[i].shape[1] for i in grp])
         check(lib().rfn_linear_f32(len(grp), ptr_array([xs[i] for i in grp]), ld, ptr_array([Ws[i] for i in grp]), ks,
                                    ptr_array([bs[i] for i in grp]), ptr(y), y.stride(0), rows, out_features,
-                                   1 if done > 0 else 0, stream()), "rfn_linear_f32")
+                                   (1 if done > 0 else 0) | 2, stream()), "rfn_linear_f32")   # 2 = RFN_GEMM_SPLITK
         done += len(grp)
     return y
 

@@ -122,10 +122,35 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
   }
 }
 
+static bool tc_general_ok(const float* A, int lda, const float* B, int ldb, const float* C, int ldc, int N, int K) {
+  return N % 4 == 0 && K % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0 && ((uintptr_t)A % 16) == 0 &&
+         ((uintptr_t)B % 16) == 0 && ((uintptr_t)C % 16) == 0;
+}
+static int gemm_general_tc(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K,
+                           int accumulate, int passes, cudaStream_t st) {
+  GemmArgs g{};
+  g.src[0] = GemmSrc{A, B, nullptr, lda, ldb, K};
+  g.nsrc = 1;
+  g.y = C; g.ldy = ldc; g.M = M; g.N = N; g.accumulate = accumulate ? 1 : 0; g.splitk_ok = 1;
+  return gemm_tc_splitk(g, true, passes, st);
+}
+
+static int gemm_general_simt(bool a_kmajor, bool b_kmajor, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                             int M, int N, int K, int accumulate, cudaStream_t st);
+
 int gemm_general(bool a_kmajor, bool b_kmajor, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M,
                  int N, int K, int accumulate, cudaStream_t st) {
   ProfScope prof__(TAG_GEMM_BWD, st);
   RFN_CHECK_ARG(A && B && C && M >= 0 && N >= 0 && K >= 0, "gemm_general: bad arguments");
+  // dX = dY . W with W = nn.Linear weights (out, in) = (K, N) row-major: tensor engine, B operand MN-major
+  if (a_kmajor && !b_kmajor && gemm_mode() >= 1 && (long)M * N * K >= (1L << 25) && N >= 128 &&
+      tc_general_ok(A, lda, B, ldb, C, ldc, N, K))
+    return gemm_general_tc(A, lda, B, ldb, C, ldc, M, N, K, accumulate, gemm_mode() == 1 ? 3 : 1, st);
+  return gemm_general_simt(a_kmajor, b_kmajor, A, lda, B, ldb, C, ldc, M, N, K, accumulate, st);
+}
+
+static int gemm_general_simt(bool a_kmajor, bool b_kmajor, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                             int M, int N, int K, int accumulate, cudaStream_t st) {
   if (M == 0 || N == 0) return RFN_OK;
   // few output tiles and a long contraction (dX = dY . W at small batch): split K over blockIdx.z
   const int tiles = ((N + 63) / 64) * ((M + 63) / 64);
@@ -633,6 +658,17 @@ int rfn_transpose_f32(const float* src, int ld_src, int rows, int cols, float* d
   transpose_kernel<<<grid, 256, 0, st>>>(src, ld_src, rows, cols, dst, ld_dst);
   RFN_LAUNCH_CHECK();
   return RFN_OK;
+}
+int rfn_gemm_general_f32_engine(int engine, int a_kmajor, int b_kmajor, const float* A, int lda, const float* B, int ldb,
+                                float* C, int ldc, int M, int N, int K, int accumulate, rfn_stream_t stream) {
+  RFN_CHECK_ARG(engine >= 0 && engine <= 2, "rfn_gemm_general_f32_engine: engine %d not in {0,1,2}", engine);
+  if (engine >= 1) {
+    RFN_CHECK_ARG(a_kmajor && !b_kmajor && A && B && C && tc_general_ok(A, lda, B, ldb, C, ldc, N, K),
+                  "rfn_gemm_general_f32_engine: the tensor engine takes the (1, 0) layout with 16-byte aligned rows");
+    return gemm_general_tc(A, lda, B, ldb, C, ldc, M, N, K, accumulate, engine == 1 ? 3 : 1, (cudaStream_t)stream);
+  }
+  RFN_CHECK_ARG(A && B && C && M >= 0 && N >= 0 && K >= 0, "rfn_gemm_general_f32_engine: bad arguments");
+  return gemm_general_simt(a_kmajor != 0, b_kmajor != 0, A, lda, B, ldb, C, ldc, M, N, K, accumulate, (cudaStream_t)stream);
 }
 int rfn_gemm_general_f32(int a_kmajor, int b_kmajor, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
                          int M, int N, int K, int accumulate, rfn_stream_t stream) {

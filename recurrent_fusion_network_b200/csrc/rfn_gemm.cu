@@ -14,6 +14,11 @@ int gemm_engine(const GemmArgs& a, int engine, cudaStream_t st) {
 int gemm(const GemmArgs& a, cudaStream_t st) {
   const int mode = gemm_mode();
   if (mode >= 1 && a.M >= 128 && gemm_tc_supported(a)) return gemm_engine(a, mode, st);
+  if (mode >= 1 && a.splitk_ok && gemm_tc_supported(a)) {   // training: few rows, the weights are streamed once
+    long wk = 0;
+    for (int s = 0; s < a.nsrc; ++s) wk += a.src[s].K;
+    if (wk * a.N >= (1L << 20)) return gemm_tc_splitk(a, false, mode == 1 ? 3 : 1, st);
+  }
   return gemm_simt(a, st);
 }
 

@@ -70,6 +70,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 
   int total_kb = 0;
   for (int s = 0; s < a.nsrc; ++s) total_kb += (a.K[s] + TC_BK - 1) / TC_BK;
+  // split-K (store epilogue only): blockIdx.z owns k-blocks [kb_first, kb_first + total_kb) of the concatenated sources
+  int kb_first = 0;
+  if (EPI == 0 && a.ksplit > 1) {
+    const int kper = (total_kb + a.ksplit - 1) / a.ksplit;
+    kb_first = (int)blockIdx.z * kper;
+    total_kb = min(total_kb, kb_first + kper) - kb_first;
+  }
+  const bool b_mn = (EPI == 0) && a.b_mn;
   const int nchunk = DRAIN ? (total_kb + CH - 1) / CH : 1;
 
   if (warp == 0 && lane == 0) {
@@ -94,24 +102,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int it = 0;
+      int it = 0, gkb = 0;
       for (int s = 0; s < a.nsrc; ++s) {
         const int nkb = (a.K[s] + TC_BK - 1) / TC_BK;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
+        for (int kb = 0; kb < nkb; ++kb, ++gkb) {
+          if (gkb < kb_first || gkb >= kb_first + total_kb) continue;
           const int st = it % STAGES;
           const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          ++it;
           mbar_wait(smem_u32(&empty[st]), ph ^ 1u);
           const uint32_t fb = smem_u32(&full[st]);
           mbar_arrive_expect_tx(fb, (uint32_t)S::TILE_BYTES);
           uint8_t* stage = smem + st * S::STAGE_BYTES;
           tma_load_2d(&a.tm_x[s], fb, smem_u32(stage), kb * TC_BK, m0);
-          tma_load_2d(&a.tm_w[s], fb, smem_u32(stage + TC_A_BYTES), kb * TC_BK, n0);
+          if (b_mn) {   // (K, N) row-major W: BN / 32 boxes of 32 contraction rows x 32 columns, one 4 KB group each
+#pragma unroll
+            for (int q = 0; q < BN / 32; ++q)
+              tma_load_2d(&a.tm_w[s], fb, smem_u32(stage + TC_A_BYTES + q * 4096), n0 + q * 32, kb * TC_BK);
+          } else {
+            tma_load_2d(&a.tm_w[s], fb, smem_u32(stage + TC_A_BYTES), kb * TC_BK, n0);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc_tf32(BN);
+    const uint32_t idesc = make_idesc_tf32(BN) | (b_mn ? IDESC_B_MN : 0u);
+    const uint64_t bstep = b_mn ? 64ull : 2ull;   // descriptor advance per k-step of 8: 8 rows of 128 bytes / 32 bytes
     for (int it = 0; it < total_kb; ++it) {
       const int st = it % STAGES;
       const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
@@ -126,12 +143,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       const uint32_t td = tmem_base + (uint32_t)(b * BN);
       const uint32_t sa = smem_u32(smem + st * S::STAGE_BYTES);
       const uint64_t da_hi = make_desc_sw128(sa);
-      const uint64_t db_hi = make_desc_sw128(sa + TC_A_BYTES);
+      const uint64_t db_hi = b_mn ? make_desc_sw128_mn(sa + TC_A_BYTES) : make_desc_sw128(sa + TC_A_BYTES);
       if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < TC_BK / 8; ++k) {
           const uint64_t adv = (uint64_t)(k * 2);  // 8 tf32 = 32 bytes = 2 x 16-byte units inside the swizzle atom
-          umma_tf32(td, da_hi + adv, db_hi + adv, idesc, (chunk_start && k == 0) ? 0u : 1u);
+          umma_tf32(td, da_hi + adv, db_hi + k * bstep, idesc, (chunk_start && k == 0) ? 0u : 1u);
         }
       }
       if (PASSES == 3) {
@@ -141,12 +158,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
       if (lane == 0) {
         if (PASSES == 3) {
           const uint64_t da_lo = make_desc_sw128(sa + S::TILE_BYTES);
-          const uint64_t db_lo = make_desc_sw128(sa + S::TILE_BYTES + TC_A_BYTES);
+          const uint64_t db_lo = b_mn ? make_desc_sw128_mn(sa + S::TILE_BYTES + TC_A_BYTES)
+                                      : make_desc_sw128(sa + S::TILE_BYTES + TC_A_BYTES);
 #pragma unroll
           for (int k = 0; k < TC_BK / 8; ++k) {
             const uint64_t adv = (uint64_t)(k * 2);
-            umma_tf32(td, da_lo + adv, db_hi + adv, idesc, 1u);
-            umma_tf32(td, da_hi + adv, db_lo + adv, idesc, 1u);
+            umma_tf32(td, da_lo + adv, db_hi + k * bstep, idesc, 1u);
+            umma_tf32(td, da_hi + adv, db_lo + k * bstep, idesc, 1u);
           }
         }
         umma_commit(smem_u32(&empty[st]));   // stage reusable once these MMAs retire
@@ -164,7 +182,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     float acc[COLS];
 #pragma unroll
     for (int i = 0; i < COLS; ++i) acc[i] = 0.f;
-    tc_stage_bias<BN>(a, n0, wt, s_bias, EPI == 1 ? s_wv : nullptr);
+    tc_stage_bias<BN>(a, n0, wt, s_bias, EPI == 1 ? s_wv : nullptr, kb_first == 0);
 
     auto drain = [&](int d) {
       const int b = d & 1;
@@ -215,7 +233,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     if (EPI == 0) {
       // all MMAs have retired (last chunk drained), so the operand ring is free: stage the tile through it
       float* stage = reinterpret_cast<float*>(smem) + (size_t)(warp - 2) * 32 * (COLS + 4);
-      tc_epilogue_store<COLS>(acc, stage, a, m0 + wq * 32, nb, lane, s_bias + half * COLS);
+      tc_epilogue_store<COLS>(acc, stage, a, m0 + wq * 32, nb, lane, s_bias + half * COLS, a.ksplit > 1);
     } else if (EPI == 1) {
       // fused additive-attention score (misc/AttentionModelCore.py:37-42):
       //   score[tile][m] = sum_{n in this thread's columns} w[n] * tanh(acc[m,n] + U_b[n] + g[m / natt, n])
@@ -320,7 +338,7 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2-D fp32 tensor map over a row-major (rows, K) matrix with leading dimension ld: box = 32 floats x box_rows
-int tc_make_map(CUtensorMap* tm, const float* base, int rows, int K, int ld, int box_rows) {
+int tc_make_map(CUtensorMap* tm, const float* base, int rows, int K, int ld, int box_rows, bool atom32) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -331,7 +349,8 @@ int tc_make_map(CUtensorMap* tm, const float* base, int rows, int K, int ld, int
   cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) rows=%d K=%d ld=%d", (int)r, rows, K, ld);
     return RFN_ERR_CUDA;
@@ -348,7 +367,7 @@ static int launch_tc_epi(const TcArgs& t, cudaStream_t st) {
     RFN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, PASSES, CH, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  dim3 grid((t.N + BN - 1) / BN, (t.M + TC_BM - 1) / TC_BM);
+  dim3 grid((t.N + BN - 1) / BN, (t.M + TC_BM - 1) / TC_BM, (EPI == 0 && t.ksplit > 1) ? t.ksplit : 1);
   gemm_tc_kernel<BN, STAGES, PASSES, CH, EPI><<<grid, TC_THREADS, smem, st>>>(t);
   RFN_LAUNCH_CHECK();
   return RFN_OK;
@@ -429,6 +448,41 @@ int gemm_tc(const GemmArgs& a, int passes, const float* g, int ldg, const float*
   if (cluster) return (g_tc_cluster.load() >= 2 && passes == 3 && t.epi != 0) ? launch_tc2p(t, st) : launch_tc2(t, passes, st);
   if (passes == 3) return bn == 256 ? launch_tc<256, 2, 3, 4>(t, st) : launch_tc<128, 3, 3, 4>(t, st);
   return bn == 256 ? launch_tc<256, 4, 1, 1>(t, st) : launch_tc<128, 6, 1, 1>(t, st);
+}
+
+// Small-row / general-layout route (training): 128 x 128 tiles of the 1-CTA kernel with the contraction split over
+// blockIdx.z so that ~one wave of CTAs streams the weights (a GEMM with <= 127 rows has only N / 128 output tiles);
+// partial tiles are added atomically.  b_mn: W given as (K, N) row-major (dX = dY . W on nn.Linear weights).
+int gemm_tc_splitk(const GemmArgs& a, bool b_mn, int passes, cudaStream_t st) {
+  ProfScope prof__(TAG_GEMM_OTHER, st);
+  if (a.M == 0 || a.N == 0) return RFN_OK;
+  TcArgs t{};
+  t.nsrc = a.nsrc;
+  int nkb = 0;
+  for (int s = 0; s < a.nsrc; ++s) {
+    const GemmSrc& g = a.src[s];
+    RFN_TRY(tc_make_map(&t.tm_x[s], g.x, a.M, g.K, g.ldx, TC_BM));
+    if (b_mn) RFN_TRY(tc_make_map(&t.tm_w[s], g.w, g.K, a.N, g.ldw, 32, true));   // rows = contraction, inner = N
+    else RFN_TRY(tc_make_map(&t.tm_w[s], g.w, a.N, g.K, g.ldw, 128));
+    t.K[s] = g.K;
+    t.bias[s] = g.bias;
+    nkb += (g.K + TC_BK - 1) / TC_BK;
+  }
+  t.y = a.y; t.ldy = a.ldy; t.M = a.M; t.N = a.N; t.accumulate = a.accumulate;
+  t.epi = 0;
+  t.b_mn = b_mn ? 1 : 0;
+  const int tiles = ((a.M + TC_BM - 1) / TC_BM) * ((a.N + 127) / 128);
+  int ks = std::max(1, std::min(148 / std::max(tiles, 1), nkb / 4));
+  if (ks > 1) {
+    const int kper = (nkb + ks - 1) / ks;
+    ks = (nkb + kper - 1) / kper;               // every slice non-empty
+  }
+  if (ks > 1) {
+    t.ksplit = ks;
+    if (!a.accumulate)
+      RFN_CUDA(cudaMemset2DAsync(a.y, (size_t)a.ldy * sizeof(float), 0, (size_t)a.N * sizeof(float), (size_t)a.M, st));
+  }
+  return passes == 3 ? launch_tc<128, 3, 3, 4>(t, st) : launch_tc<128, 6, 1, 1>(t, st);
 }
 
 // logits GEMM with the fused vocabulary epilogue: returns per-slice statistics instead of logits

@@ -89,6 +89,8 @@ bool gemm_tc_supported(const GemmArgs& a);
 int gemm_tc(const GemmArgs& a, int passes, const float* g, int ldg, const float* wv, float* score, int natt,
             cudaStream_t st);
 int gemm_engine(const GemmArgs& a, int engine, cudaStream_t st);
+// 1-CTA tensor kernel with the contraction split over CTAs (atomic partial sums); b_mn: W stored (K, N) row-major
+int gemm_tc_splitk(const GemmArgs& a, bool b_mn, int passes, cudaStream_t st);
 int tc_score_slices(int N);
 // logits GEMM whose epilogue keeps only per-(slice,row) max / sum-exp / top-k (slices = tc_score_slices(N))
 int gemm_tc_vocab(const GemmArgs& a, int passes, float* st_max, float* st_sum, float* st_val, int32_t* st_idx, int ktop,

@@ -21,6 +21,9 @@ struct TcArgs {
   // partial tile with red.global.add (y pre-zeroed or accumulated into); used by the weight-gradient GEMMs whose output
   // has few tiles and whose contraction runs over rows x attention locations
   int ksplit;
+  // 1-CTA store kernel only: W is given as (K, N) row-major (contraction index slow), i.e. the B operand is MN-major;
+  // dX = dY . W reads nn.Linear weights (out, in) this way without a transposed copy
+  int b_mn;
   // fused attention-score epilogue (epi == 1)
   int epi;
   const float* g;   // (rows, ldg)   h_2_att_h(h)
@@ -40,6 +43,7 @@ struct TcArgs {
 };
 
 // host helpers (rfn_gemm_tc.cu)
-int tc_make_map(CUtensorMap* tm, const float* base, int rows, int K, int ld, int box_rows);
+// atom32: 128-byte swizzle with 32-byte atoms (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B), the layout an MN-major tf32 operand needs
+int tc_make_map(CUtensorMap* tm, const float* base, int rows, int K, int ld, int box_rows, bool atom32 = false);
 
 }  // namespace rfn

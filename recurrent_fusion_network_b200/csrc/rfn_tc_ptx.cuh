@@ -90,6 +90,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// MN-major tf32 operand (the contraction index is the slow one: element (k, n) at k * ld + n).  The only layout the
+// tensor core accepts for it is the 128-byte swizzle with 32-byte atoms (layout type 1; TMA's SWIZZLE_128B_ATOM_32B;
+// with plain SWIZZLE_128B and the transpose bit set the MMA returns zeros -- measured).  The tile is held as groups of
+// 32 MN-elements; a group is 32 contraction rows of 128 bytes (4 KB, what one TMA box of 32 x 32 floats lands), 4-row
+// swizzle atoms 512 bytes apart (SBO), groups 4096 bytes apart (LBO).  One tf32 MMA (K = 8) consumes two atoms per
+// group: advance the start address by 1024 bytes (64 units) per k-step.
+__device__ __forceinline__ uint64_t make_desc_sw128_mn(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (256ull << 16) | (32ull << 32) | (1ull << 46) | (1ull << 61);
+}
+constexpr uint32_t IDESC_B_MN = 1u << 16;   // instruction descriptor bit: B operand is MN-major
+constexpr uint32_t IDESC_A_MN = 1u << 15;
 // instruction descriptor: D fp32, A/B tf32, both K-major, M = 128, N = BN
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int bn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);

@@ -225,3 +225,47 @@ def test_attention_backward_tensor_engine_weight_gradient():
     for a, b in zip(grads[1], grads[0]):
         assert maxdiff(a, b) <= 2e-5 * max(1.0, float(b.abs().max()))
     assert float(grads[1][1].abs().max()) > 0
+
+
+@pytest.mark.parametrize("M,N,Ks", [(80, 2048, [512, 2560, 2048]), (16, 2048, [2048]), (80, 9488, [512]), (127, 516, [2052]),
+                                    (1, 1024, [1024])])
+def test_small_row_split_k_linear(M, N, Ks):
+    """rfn_linear_f32 with RFN_GEMM_SPLITK and < 128 rows: 1-CTA tensor kernel, contraction split over blockIdx.z."""
+    from recurrent_fusion_network_b200._capi import check, lib, ptr, ptr_array, stream
+    g = torch.Generator().manual_seed(M + N)
+    xs = cuda_list([torch.randn(M, k, generator=g) for k in Ks])
+    ws = cuda_list([(torch.rand(N, k, generator=g) * 2 - 1) * 0.1 for k in Ks])
+    bs = cuda_list([torch.randn(N, generator=g) for _ in Ks])
+    want = sum(x.double() @ w.double().t() + b.double() for x, w, b in zip(xs, ws, bs))
+    scale = float(want.abs().max())
+    n = len(Ks)
+    ld = (C.c_int * n)(*[x.stride(0) for x in xs])
+    ks = (C.c_int * n)(*Ks)
+    for acc in (0, 1):
+        y0 = torch.randn(M, N, generator=g).cuda()
+        y = y0.clone()
+        check(lib().rfn_linear_f32(n, ptr_array(xs), ld, ptr_array(ws), ks, ptr_array(bs), ptr(y), N, M, N, acc | 2, stream()),
+              "rfn_linear_f32")
+        assert maxdiff(y, want + (y0.double() if acc else 0)) <= 3e-6 * scale
+
+
+@pytest.mark.parametrize("M,N,K", [(80, 2560, 2048), (80, 2048, 9488), (16, 2208, 2048), (300, 516, 1028), (80, 132, 4096)])
+def test_general_gemm_dx_on_tensor_engine(M, N, K):
+    """rfn_gemm_general_f32(1, 0): dX[M,N] = dY[M,K] . W[K,N] with W row-major (K, N) -- the MN-major B operand path --
+    against fp64 and against the SIMT kernel."""
+    from recurrent_fusion_network_b200 import _capi
+    from recurrent_fusion_network_b200.autograd import _gemm_general
+    g = torch.Generator().manual_seed(M + N + K)
+    dY = torch.randn(M, K, generator=g).cuda()
+    W = ((torch.rand(K, N, generator=g) * 2 - 1) * 0.1).cuda()
+    want = dY.double() @ W.double()
+    scale = float(want.abs().max())
+    out = {}
+    for mode in (1, 0):
+        _capi.check(_capi.lib().rfn_set_gemm_mode(mode))
+        for acc in (0, 1):
+            y0 = torch.randn(M, N, generator=g).cuda()
+            y = y0.clone()
+            _gemm_general(1, 0, dY, K, W, N, y, N, M, N, K, accumulate=acc)
+            assert maxdiff(y, want + (y0.double() if acc else 0)) <= 3e-6 * scale, (mode, acc)
+    _capi.check(_capi.lib().rfn_set_gemm_mode(1))
