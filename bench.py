@@ -385,9 +385,11 @@ def xe_train_bench(model, device, world, rank, steps, timed):
                 ms_per_step=round(ms, 2), deduplicated=dict(value=round(tokens / (ms_dd / 1e3), 1), ms_per_step=round(ms_dd, 2)),
                 cuda_graph=graphed,
                 kernel_ms_and_launches=train_shares, rows_per_gpu=rows, tokens_per_step=int(tokens), loss=round(float(loss_box[0]), 4),
-                note="value: as written (80 replicated rows); deduplicated: stages 1-2 once per image (SURVEY D9); per-op autograd "
-                     "over our kernels, small-row GEMMs on the skinny weight-streaming kernel, backward GEMMs fp32 SIMT with "
-                     "split-K; clip_gradient + Adam (train.py:56,160-163) fused in rfn_adam_step_f32", gpu_launches_per_step=launches // max(1, steps))
+                note="value: as written (80 replicated rows), eager per-op autograd over our kernels (host-bound); deduplicated: "
+                     "stages 1-2 once per image (SURVEY D9); cuda_graph: the same step replayed from CUDA graphs (training.GraphedXEStep: "
+                     "forward+backward | gradient all-reduce | clamp+Adam).  Small-row GEMMs and dX on the split-K tcgen05 kernel (B operand "
+                     "MN-major for dX), dU = dP^T.A on the split-K 2-CTA kernel, dW with an 80-row contraction on the fp32 SIMT kernel; "
+                     "clip_gradient + Adam (train.py:56,160-163) fused in rfn_adam_step_f32", gpu_launches_per_step=launches // max(1, steps))
 
 
 def ciderd_bench(device):

@@ -17,7 +17,7 @@ int gemm(const GemmArgs& a, cudaStream_t st) {
   if (mode >= 1 && a.splitk_ok && gemm_tc_supported(a)) {   // training: few rows, the weights are streamed once
     long wk = 0;
     for (int s = 0; s < a.nsrc; ++s) wk += a.src[s].K;
-    if (wk * a.N >= (1L << 20)) return gemm_tc_splitk(a, false, mode == 1 ? 3 : 1, st);
+    if (wk * a.N >= (a.M > 32 ? (1L << 17) : (1L << 20))) return gemm_tc_splitk(a, false, mode == 1 ? 3 : 1, st);
   }
   return gemm_simt(a, st);
 }
