@@ -274,6 +274,14 @@ def run_ours(args):
         torch.cuda.empty_cache()
         xe = xe_train_bench(model, device, world, rank, args.train_steps, timed)
 
+    # ---- BASELINE.json configs[3] and configs[4] as secondary lines (parity: tests/test_gpu_training.py, test_gpu_parity.py) ----
+    rl = ens = None
+    if args.train_steps > 0:
+        rl = rl_train_bench(model, device, world, rank, args.train_steps, timed)
+        torch.cuda.empty_cache()
+        if world == 1:
+            ens = ensemble_bench(model, device, timed)
+
     # ---- next-row component: CIDEr-D self-critical reward, device vs the oracle port on the host ----
     ciderd = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -298,7 +306,8 @@ def run_ours(args):
                                 parity="fp32 mode; tests/test_gpu_parity.py vs the reference fixtures"),
                     clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=dominant,
                     roofline_attention=roof_attn, roofline_gemm=roof_gemm, kernel_time_shares=shares,
-                    cpu_baseline=cpu, xe_train=xe, ciderd_reward=ciderd, seq_checksum=seq_checksum)
+                    cpu_baseline=cpu, xe_train=xe, rl_train=rl, ensemble=ens, ciderd_reward=ciderd,
+                    seq_checksum=seq_checksum)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -390,6 +399,97 @@ def xe_train_bench(model, device, world, rank, steps, timed):
                      "forward+backward | gradient all-reduce | clamp+Adam).  Small-row GEMMs and dX on the split-K tcgen05 kernel (B operand "
                      "MN-major for dX), dU = dP^T.A on the split-K 2-CTA kernel, dW with an 80-row contraction on the fp32 SIMT kernel; "
                      "clip_gradient + Adam (train.py:56,160-163) fused in rfn_adam_step_f32", gpu_launches_per_step=launches // max(1, steps))
+
+
+def rl_train_bench(model, device, world, rank, steps, timed):
+    """BASELINE.json configs[3]: one self-critical RL iteration (train_rl.py:150-191): 50 images x 5 multinomial samples
+    per GPU with the tape on, greedy baseline decode (no grad), CIDEr-D(sample) - CIDEr-D(greedy) on the device, RL
+    criterion + multi-label margin terms, backward, gradient all-reduce, clamp + Adam."""
+    from types import SimpleNamespace
+    from recurrent_fusion_network_b200 import dist as D, reward as RW
+    from recurrent_fusion_network_b200.criteria import ReviewNetRewardCriterion
+    from recurrent_fusion_network_b200.optim import FusedAdam
+    g = torch.Generator(device=device).manual_seed(300 + rank)
+    imgs, spi, L = 50, 5, model.seq_length
+    rows = imgs * spi
+    fc = [torch.randn(imgs, f, device=device, generator=g).repeat_interleave(spi, 0) for (_, _, f) in ENC]
+    att = [torch.randn(imgs, n, d, device=device, generator=g).repeat_interleave(spi, 0) for (n, d, _) in ENC]
+    cg = torch.Generator().manual_seed(400 + rank)
+    gts, df = [], {}
+    for _ in range(imgs):
+        refs, seen = [], set()
+        for _ in range(5):
+            n = int(torch.randint(5, L + 1, (1,), generator=cg))
+            r = torch.randint(1, 9488, (n,), generator=cg).tolist() + [0]
+            refs.append(r)
+            for k in range(1, 5):
+                seen.update(tuple(r[j:j + k]) for j in range(len(r) - k + 1))
+        gts.append(refs)
+        for ng in seen:
+            df[ng] = df.get(ng, 0.0) + 1.0
+    table = RW.DocumentFrequency(df, imgs, device)     # the role of data/coco-train-idxs.p
+    top = torch.full((rows, 1000), -1, dtype=torch.int64)
+    for b in range(rows):
+        n = int(torch.randint(2, 30, (1,), generator=cg))
+        top[b, :n] = torch.randperm(1000, generator=cg)[:n]
+    top = top.to(device)
+    ropt = SimpleNamespace(cider_weight=1.0, bleu4_weight=0, spice_weight=0, use_baseline=1, use_ppo=0)
+    crit = ReviewNetRewardCriterion(SimpleNamespace(use_label_smoothing=0, label_smoothing_epsilon=0.1))
+    params = [p for p in model.parameters()]
+    opt = FusedAdam(params, lr=5e-5, weight_decay=1e-5, grad_clip=1.0)
+    box = [None, 0]
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        model.train()
+        seq, slp, lp_all, rp = model.sample(fc, att, {"sample_max": 0})          # tape on (train_rl.py:160)
+        with torch.no_grad():                                                    # get_rewards.py:115-129
+            model.eval()
+            greedy = model.sample(fc, att, {"sample_max": 1})[0]
+            model.train()
+            T = seq.shape[1]
+            if greedy.shape[1] < T:
+                greedy = torch.nn.functional.pad(greedy, (0, T - greedy.shape[1]))
+            reward, _ = RW.compute_reward(seq, greedy[:, :T].contiguous(), gts, table, ropt, seq_per_img=spi)
+        loss = crit(slp, seq, reward, lp_all, 0.0, rp, top, 10.0, None, ropt)
+        loss.backward()
+        D.average_gradients(params)
+        opt.step()
+        box[0], box[1] = loss.detach(), int(seq.shape[1])
+        return box[0], box[0]
+
+    ms, launches, _ = timed(step, steps, 3)
+    model.eval()
+    for p in params:
+        p.grad = None
+    return dict(metric="rl_train_samples_per_sec", value=round(rows * world / (ms / 1e3), 1), unit="sampled captions/s",
+                ms_per_step=round(ms, 2), rows_per_gpu=rows, sampled_length=box[1], loss=round(float(box[0]), 4),
+                gpu_launches_per_step=launches // max(1, steps),
+                note="BASELINE.json configs[3]; eager per-op autograd (the sampling loop reads one flag per step back to the "
+                     "host as the reference's early break does); reward scored on the device")
+
+
+def ensemble_bench(model, device, timed):
+    """BASELINE.json configs[4]: eval_ensemble, 4 full models, logit-mean of the per-step log-probs, beam 3, 500 images."""
+    from recurrent_fusion_network_b200 import make_opt, setup
+    from recurrent_fusion_network_b200.ensemble import ensemble_sample_beam
+    models = [model]
+    for k in range(3):
+        torch.manual_seed(2000 + k)
+        models.append(setup(make_opt()).to(device).eval())
+    fc, att = make_features(500, device, 77)
+
+    def step():
+        out = ensemble_sample_beam(models, fc, att, {"beam_size": BEAM})
+        return out[0], out[1]
+
+    ms, launches, out = timed(step, 2, 1)
+    res = dict(metric="ensemble4_beam3_captions_per_sec", value=round(500 / (ms / 1e3), 1), unit="captions/s",
+               ms_per_step=round(ms, 2), models=4, images=500, gpu_launches_per_step=launches // 2,
+               seq_checksum=int(out[0].sum().item()))
+    del models, fc, att
+    torch.cuda.empty_cache()
+    return res
 
 
 def ciderd_bench(device):
