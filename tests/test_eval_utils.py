@@ -1,0 +1,102 @@
+"""eval_utils drivers (eval_utils.py:66-265, 387-719) over a loader double with the reference's protocol."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import rfnet_oracle as O
+
+
+class FakeLoader:
+    """Protocol of dataloader.DataLoader used by the drivers: batches of `batch_size` images, each replicated seq_per_img
+    times, bounds with it_pos_now / it_max / wrapped."""
+
+    def __init__(self, cfg, n_images, batch_size, seq_per_img, seed=0):
+        self.cfg, self.n, self.batch_size, self.seq_per_img = cfg, n_images, batch_size, seq_per_img
+        self.fc, self.att = O.make_inputs(cfg, n_images, seed=seed)
+        self.labels, self.masks, self.top = O.make_labels(cfg, n_images * seq_per_img, seed=seed + 1)
+        self.vocab = {str(i): "w%d" % i for i in range(1, cfg.V1)}
+        self.pos = 0
+
+    def reset_iterator(self, split):
+        self.pos = 0
+
+    def get_vocab(self):
+        return self.vocab
+
+    def get_batch(self, split, batch_size=None):
+        b = batch_size or self.batch_size
+        idx, wrapped = [], False
+        for _ in range(b):
+            idx.append(self.pos)
+            self.pos += 1
+            if self.pos >= self.n:
+                self.pos, wrapped = 0, True
+        rep = np.repeat(np.array(idx), self.seq_per_img)
+        rows = np.concatenate([np.arange(i * self.seq_per_img, (i + 1) * self.seq_per_img) for i in idx])
+        return {"fc_feats_array": [f.numpy()[rep] for f in self.fc], "att_feats_array": [a.numpy()[rep] for a in self.att],
+                "labels": self.labels.numpy()[rows], "masks": self.masks.numpy()[rows], "top_words": self.top.numpy()[rows],
+                "infos": [{"id": 1000 + i} for i in idx],
+                "bounds": {"it_pos_now": self.pos, "it_max": self.n, "wrapped": wrapped}}
+
+
+def test_decode_sequence_stops_at_first_zero():
+    from recurrent_fusion_network_b200.eval_utils import decode_sequence
+    vocab = {"1": "a", "2": "b", "3": "c"}
+    assert decode_sequence(vocab, torch.tensor([[1, 2, 0, 3], [0, 1, 1, 1], [3, 3, 3, 3]])) == ["a b", "", "c c c c"]
+
+
+@pytest.mark.gpu
+def test_eval_split_matches_direct_calls():
+    from recurrent_fusion_network_b200 import eval_utils as EU
+    from recurrent_fusion_network_b200.criteria import ReviewNetEnsembleCriterion
+    from tests._gpu_util import build_model, cuda_list
+    cfg = O.tiny_config(2)
+    sd = O.make_state_dict(cfg, seed=1250, init_range=0.5, logit_scale=3.0, eos_bias=0.8)
+    m = build_model(cfg, sd)
+    crit = ReviewNetEnsembleCriterion(SimpleNamespace(use_label_smoothing=0, label_smoothing_epsilon=0.1, use_cuda=1))
+    loader = FakeLoader(cfg, n_images=7, batch_size=3, seq_per_img=2)
+    kw = {"eval_split": "val", "val_images_use": 7, "beam_size": 3, "language_eval": 0, "verbose": False,
+          "feature_type": "feat_array", "reason_weight": 10}
+    loss, preds, stats = EU.eval_split(m, crit, loader, kw)
+    assert stats is None and m.training                                   # switched back to train mode (:261)
+    assert [p["image_id"] for p in preds] == [1000 + i for i in range(7)]  # 9 decoded, 2 beyond the split end popped
+    with torch.no_grad():
+        m.eval()
+        seq = m.sample(cuda_list(loader.fc), cuda_list(loader.att), {"beam_size": 3})[0]
+        want = EU.decode_sequence(loader.vocab, seq)
+        assert [p["caption"] for p in preds] == want
+        # loss of the first batch through the same public calls
+        loader.reset_iterator("val")
+        d = loader.get_batch("val")
+        lp, tp = m([torch.from_numpy(a).cuda() for a in d["fc_feats_array"]], [torch.from_numpy(a).cuda() for a in d["att_feats_array"]],
+                   torch.from_numpy(d["labels"]).cuda())
+        l0 = float(crit(lp, torch.from_numpy(d["labels"]).cuda()[:, 1:], torch.from_numpy(d["masks"]).cuda()[:, 1:], tp,
+                        torch.from_numpy(d["top_words"]).cuda(), 10))
+    loader2 = FakeLoader(cfg, n_images=7, batch_size=3, seq_per_img=2)
+    loss1, preds1, _ = EU.eval_split(m, crit, loader2, dict(kw, val_images_use=3))
+    assert abs(loss1 - l0) <= 1e-5 * max(1.0, abs(l0)) and len(preds1) == 3
+    with pytest.raises(RuntimeError):
+        EU.eval_split(m, crit, FakeLoader(cfg, 3, 3, 2), dict(kw, language_eval=1, val_images_use=3))
+    seen = {}
+    EU.eval_split(m, crit, FakeLoader(cfg, 3, 3, 2), dict(kw, language_eval=1, val_images_use=3, id="x",
+                                                          language_eval_fn=lambda ds, p, mid, sp: seen.update(n=len(p), id=mid) or {"CIDEr": 0.0}))
+    assert seen == {"n": 3, "id": "eval_split_x_0"}
+
+
+@pytest.mark.gpu
+def test_eval_ensemble_matches_ensemble_beam():
+    from recurrent_fusion_network_b200 import eval_utils as EU
+    from recurrent_fusion_network_b200.ensemble import ensemble_sample_beam
+    from tests._gpu_util import build_model, cuda_list
+    cfg = O.tiny_config(2)
+    models = [build_model(cfg, O.make_state_dict(cfg, seed=s, init_range=0.5, logit_scale=3.0, eos_bias=0.8)) for s in (1250, 1251)]
+    loader = FakeLoader(cfg, n_images=5, batch_size=2, seq_per_img=2)
+    _, preds, _ = EU.eval_ensemble(models, loader, {"eval_split": "test", "num_images": 5, "beam_size": 3, "batch_size": 2,
+                                                    "verbose": False, "language_eval": 0})
+    with torch.no_grad():
+        seq, slp = ensemble_sample_beam(models, cuda_list(loader.fc), cuda_list(loader.att), {"beam_size": 3})[:2]
+    assert [p["caption"] for p in preds] == EU.decode_sequence(loader.vocab, seq)
+    want_lp = (slp * (seq > 0).float()).sum(1).cpu()
+    assert max(abs(p["log_prob"] - float(w)) for p, w in zip(preds, want_lp)) <= 1e-4
