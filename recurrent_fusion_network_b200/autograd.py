@@ -149,8 +149,8 @@ class AttentionFn(Function):
         dev = h.device
         dP = torch.empty(rows * N, Ah, dtype=torch.float32, device=dev)
         dg = torch.empty(rows, Ah, dtype=torch.float32, device=dev)
-        dw = torch.zeros(1, Ah, dtype=torch.float32, device=dev)
-        dwb = torch.zeros(1, dtype=torch.float32, device=dev)
+        dwv = torch.zeros(Ah + 1, dtype=torch.float32, device=dev)     # one fill for both accumulators
+        dw, dwb = dwv[:Ah].view(1, Ah), dwv[Ah:]
         need_dA = ctx.needs_input_grad[1]
         dA = torch.zeros(rows, N, D, dtype=torch.float32, device=dev) if need_dA else None
         check(lib().rfn_attention_step_bwd_f32(ptr(A), ptr(P), ptr(g), ptr(v_w), ptr(alpha), ptr(dz), D, ptr(dP), ptr(dg),

@@ -110,6 +110,12 @@ def lstm_cell(G: torch.Tensor, c_prev: torch.Tensor):
     return h, c
 
 
+def _last_layer(t: torch.Tensor) -> torch.Tensor:
+    """state[-1] of a (num_layers, rows, R) state tensor.  num_layers is 1 on this path: a squeeze is a view whose backward
+    is a view too, where select's backward zero-fills a full tensor and copies (one fill + one copy kernel per use)."""
+    return t.squeeze(0) if t.shape[0] == 1 else t[-1]
+
+
 def _attention(att_mod, pre_h: torch.Tensor, att_seq: torch.Tensor) -> torch.Tensor:
     """AttentionModelCore.forward through rfn_attention_core_f32."""
     pre_h, att_seq = _f32c(pre_h), _f32c(att_seq)
@@ -168,7 +174,7 @@ class LSTMFusionNoInputCore(nn.Module):
         self.z2h.weight.data.uniform_(-_INIT, _INIT)
 
     def forward(self, H, att_feat, state):
-        pre_h, pre_c = state[0][-1], state[1][-1]
+        pre_h, pre_c = _last_layer(state[0]), _last_layer(state[1])
         z = self.att_model(pre_h, att_feat)
         G = linear([(H, self.H2h), (z, self.z2h)], pre_h.shape[0], 4 * self.rnn_size)
         next_h, next_c = lstm_cell(G, _f32c(pre_c))
@@ -192,7 +198,7 @@ class FeatArrayFusionNoInputCore(nn.Module):
         self.dropout = nn.Dropout(drop_prob_fusion)
 
     def forward(self, att_seq, state_list):
-        H = torch.cat([state_list[i][0][-1] for i in range(self.num_feat_array)], 1)   # previous states (:102-107)
+        H = torch.cat([_last_layer(state_list[i][0]) for i in range(self.num_feat_array)], 1)   # previous states (:102-107)
         output_list = []
         for i in range(self.num_feat_array):
             output, state_list[i] = self.lstm[i](H, att_seq[i], state_list[i])
@@ -219,7 +225,7 @@ class LSTMSoftMultiAttentionFeatArrayNoInputCore(nn.Module):
         _uniform_(self.h2h)                            # z_2_h keeps nn.Linear's default init (:35-38)
 
     def forward(self, att_seq, state):
-        pre_h, pre_c = state[0][-1], state[1][-1]
+        pre_h, pre_c = _last_layer(state[0]), _last_layer(state[1])
         zs = [self.att_model[i](pre_h, att_seq[i]) for i in range(self.num_feat_array)]
         srcs = [(pre_h, self.h2h)] + [(zs[i], self.z_2_h[i]) for i in range(self.num_feat_array)]
         G = linear(srcs, pre_h.shape[0], 4 * self.rnn_size)
@@ -248,7 +254,7 @@ class LSTMSoftAttentionCore(nn.Module):
             _uniform_(m)
 
     def forward(self, xt, att_seq, state):
-        pre_h, pre_c = state[0][-1], state[1][-1]
+        pre_h, pre_c = _last_layer(state[0]), _last_layer(state[1])
         z = _attention(self, pre_h, att_seq)
         G = linear([(xt, self.i2h), (pre_h, self.h2h), (z, self.z2h)], pre_h.shape[0], 4 * self.rnn_size)
         next_h, next_c = lstm_cell(G, _f32c(pre_c))
@@ -279,7 +285,7 @@ class LSTMSoftAttentionNoInputCore(nn.Module):
         self.z2h.bias.data.fill_(-1)
 
     def forward(self, att_seq, mil_feats, matching_feats, state):
-        pre_h, pre_c = state[0][-1], state[1][-1]
+        pre_h, pre_c = _last_layer(state[0]), _last_layer(state[1])
         z = _attention(self, pre_h, att_seq)
         G = linear([(pre_h, self.h2h), (z, self.z2h)], pre_h.shape[0], 4 * self.rnn_size)
         next_h, next_c = lstm_cell(G, _f32c(pre_c))

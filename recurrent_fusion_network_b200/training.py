@@ -19,8 +19,8 @@ def thought_vectors(model, att, state_list):
             reason_mat[j].append(AG.linear([(output_list[j], model.reason_linear_individual[j])]))
     thought_vectors_ = [torch.stack(tv_list[j], 1).contiguous() for j in range(J)]
     reason_pred = [AG.MaxOverStepsFn.apply(torch.stack(reason_mat[j], 1).contiguous()) for j in range(J)]
-    h = AG.MeanFn.apply(*[st[0][-1] for st in state_list])
-    c = AG.MeanFn.apply(*[st[1][-1] for st in state_list])
+    h = AG.MeanFn.apply(*[st[0].squeeze(0) for st in state_list])
+    c = AG.MeanFn.apply(*[st[1].squeeze(0) for st in state_list])
     state = (h.unsqueeze(0), c.unsqueeze(0))
     comb, reason_comb = [], []
     for i in range(model.num_review_steps):
@@ -44,12 +44,13 @@ def _stages(model, fc, att):
         attu = [a[::g].contiguous() for a in att]
         TVc, reason_pred, (h, c) = thought_vectors(model, attu, model.get_init_state(fcu))
         ex = lambda t: AG.ExpandRowsFn.apply(t, g)
-        return ex(TVc), [ex(r) for r in reason_pred], (ex(h[0]).unsqueeze(0), ex(c[0]).unsqueeze(0))
+        return ex(TVc), [ex(r) for r in reason_pred], (ex(h.squeeze(0)).unsqueeze(0), ex(c.squeeze(0)).unsqueeze(0))
     return thought_vectors(model, att, model.get_init_state(fc))
 
 
-def _step(model, it, TVc, state):
-    xt = AG.EmbedFn.apply(it, model.embed.weight)
+def _step(model, it, TVc, state, xt=None):
+    if xt is None:
+        xt = AG.EmbedFn.apply(it, model.embed.weight)
     output, state = model.decoder(xt, TVc, state)
     lp = AG.LogSoftmaxFn.apply(AG.linear([(output, model.logit)]))
     return lp, state
@@ -65,6 +66,12 @@ def forward_xe(model, fc_feats, att_feats, seq, col_any=None):
     outputs = []
     if col_any is None:
         col_any = (seq != 0).any(dim=0).cpu().tolist()
+    xts = None
+    if model.ss_prob <= 0.0:
+        # teacher forcing only: all input tokens are known, one embedding gather (and one dense dE in backward) for the
+        # whole sequence instead of one per step
+        T = seq.size(1)
+        xts = AG.EmbedFn.apply(seq.t().reshape(-1), model.embed.weight).view(T, rows, -1).unbind(0)
     for i in range(seq.size(1)):
         it = seq[:, i].clone()
         if i >= 1 and model.ss_prob > 0.0:                              # scheduled sampling (:260-270)
@@ -75,7 +82,7 @@ def forward_xe(model, fc_feats, att_feats, seq, col_any=None):
                 it = torch.where(sample_mask, sampled, it)
         if i >= 1 and not col_any[i]:                                   # :274-275
             break
-        lp, state = _step(model, it, TVc, state)
+        lp, state = _step(model, it, TVc, state, xt=None if xts is None else xts[i])
         outputs.append(lp)
     return torch.stack(outputs, 1).contiguous(), [r.squeeze() for r in reason_pred]
 
