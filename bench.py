@@ -263,9 +263,23 @@ def run_ours(args):
         model.chunk_images = args.e2e_chunk
         ms_e2e, _, _ = timed(step_e2e, max(1, min(args.steps, args.e2e_steps)), max(1, min(args.warmup, 2)))
         model.chunk_images = args.chunk
-        del hfc, hatt
+        # what bounds e2e: the plain pinned-host -> device copy rate of this box, measured on the largest feature tensor
+        big = max(hatt, key=lambda t: t.numel())
+        dst = torch.empty(big.shape, dtype=big.dtype, device=device)
+        dst.copy_(big, non_blocking=True)
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(3):
+            dst.copy_(big, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        h2d_peak = 3 * big.numel() * 4 / (c0.elapsed_time(c1) / 1e3) / 1e9
+        del hfc, hatt, dst
         e2e = dict(value=round(args.images / (ms_e2e / 1e3), 2), unit=UNIT, ms_per_step=round(ms_e2e, 2),
                    h2d_bytes_per_step=int(h2d * world), d2h_bytes_per_step=int(d2h_box[0] * world),
+                   h2d_gbs_per_gpu=round(h2d / (ms_e2e / 1e3) / 1e9, 2), h2d_copy_peak_gbs=round(h2d_peak, 2),
+                   bound="host->device copy (PCIe): every caption needs 3.19 MB of fp32 features",
                    api="model.sample(fc_feats, att_feats, {'beam_size': 3}) on pinned host tensors")
 
     # ---- secondary metric: XE teacher-forced training tokens/s (BASELINE.json configs[1]) -----------
@@ -308,7 +322,7 @@ def run_ours(args):
                     roofline_attention=roof_attn, roofline_gemm=roof_gemm, kernel_time_shares=shares,
                     cpu_baseline=cpu, xe_train=xe, rl_train=rl, ensemble=ens, ciderd_reward=ciderd,
                     seq_checksum=seq_checksum)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -587,7 +601,19 @@ def run_reference(args):
                             images=args.images, sample_images=n, beam=BEAM),
                 cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind="port", sample=sample),
                 e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -606,6 +632,12 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE line (the JSON): anything a library prints there (NCCL's version banner, warnings) is sent
+    # to stderr by pointing fd 1 at fd 2 for the duration of the run; emit() writes the line to the real stdout
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     if not torch.cuda.is_available():

@@ -593,6 +593,8 @@ class RecurrentFusionModel(nn.Module):
                              for _ in range(2)]
             self._staging_key = key
         staging = self._staging
+        # (tapering the final chunks to shorten the exposed last decode was measured: 352 ms against 336 ms per 5000
+        # images -- small chunks decode less efficiently than they copy)
         spans = [(k0, min(rows, k0 + step)) for k0 in range(0, rows, step)]
         ready, free = [None, None], [None, None]
 
