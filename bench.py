@@ -358,7 +358,7 @@ def xe_train_bench(model, device, world, rank, steps, timed):
     crit = ReviewNetEnsembleCriterion(SimpleNamespace(use_label_smoothing=1, label_smoothing_epsilon=0.1, use_cuda=1))
     params = [p for p in model.parameters()]
     from recurrent_fusion_network_b200.optim import FusedAdam
-    opt = FusedAdam(params, lr=5e-4, weight_decay=1e-5, grad_clip=1.0)   # clamp + Adam in one HBM pass
+    opt = FusedAdam(params, lr=5e-4, weight_decay=1e-5, grad_clip=1.0, grad_scale=1.0 / world)   # mean + clamp + Adam, one pass
     loss_box = [None]
 
     def step():
@@ -366,7 +366,7 @@ def xe_train_bench(model, device, world, rank, steps, timed):
         lp, rp = model(fc, att, labels)
         loss = crit(lp, labels[:, 1:], masks[:, 1:], rp, top, 10.0)
         loss.backward()
-        D.average_gradients(params)   # NCCL all-reduce (mean); the reference's clamp rides in the optimizer kernel
+        D.average_gradients(params, divide=False)   # NCCL all-reduce (sum); mean and clamp ride in the optimizer kernel
         opt.step()
         loss_box[0] = loss.detach()
         return loss_box[0], loss_box[0]
@@ -380,9 +380,9 @@ def xe_train_bench(model, device, world, rank, steps, timed):
     graphed = {}
     for name, dd in (("as_written", 1), ("deduplicated", spi)):
         model.dedup_rows = dd
-        opt_g = FusedAdam(params, lr=5e-4, weight_decay=1e-5, grad_clip=1.0, capturable=True)
+        opt_g = FusedAdam(params, lr=5e-4, weight_decay=1e-5, grad_clip=1.0, capturable=True, grad_scale=1.0 / world)
         gs = TR.GraphedXEStep(model, crit, opt_g, fc, att, labels, masks, top, 10.0, warmup=2,
-                              between=(lambda: D.average_gradients(params)) if world > 1 else None)
+                              between=(lambda: D.average_gradients(params, divide=False)) if world > 1 else None)
 
         def gstep(gs=gs):
             l = gs(fc, att, labels, masks, top)   # includes the copies into the graph's static input buffers
@@ -450,7 +450,7 @@ def rl_train_bench(model, device, world, rank, steps, timed):
     ropt = SimpleNamespace(cider_weight=1.0, bleu4_weight=0, spice_weight=0, use_baseline=1, use_ppo=0)
     crit = ReviewNetRewardCriterion(SimpleNamespace(use_label_smoothing=0, label_smoothing_epsilon=0.1))
     params = [p for p in model.parameters()]
-    opt = FusedAdam(params, lr=5e-5, weight_decay=1e-5, grad_clip=1.0)
+    opt = FusedAdam(params, lr=5e-5, weight_decay=1e-5, grad_clip=1.0, grad_scale=1.0 / world)
     box = [None, 0]
 
     def step():
@@ -467,7 +467,7 @@ def rl_train_bench(model, device, world, rank, steps, timed):
             reward, _ = RW.compute_reward(seq, greedy[:, :T].contiguous(), gts, table, ropt, seq_per_img=spi)
         loss = crit(slp, seq, reward, lp_all, 0.0, rp, top, 10.0, None, ropt)
         loss.backward()
-        D.average_gradients(params)
+        D.average_gradients(params, divide=False)
         opt.step()
         box[0], box[1] = loss.detach(), int(seq.shape[1])
         return box[0], box[0]

@@ -295,12 +295,14 @@ int rfn_multilabel_margin_bwd_f32(const float* pred, const int64_t* target, int 
 
 /* Fused clip_gradient (element-wise clamp to +-grad_clip, misc/utils.py:292-296; <= 0 disables) + Adam step with
  * L2 weight decay (torch.optim.Adam semantics, train.py:56,160-163) over n_tensors parameter tensors; `step` is the
- * 1-based update count (bias correction).  HOST arrays of device pointers / element counts.  d_hyper (nullable):
+ * 1-based update count (bias correction).  grad_scale multiplies the gradient first (1 / world_size turns the sum of a
+ * data-parallel all-reduce into the mean without another pass; 1 otherwise).  HOST arrays of device pointers / element
+ * counts.  d_hyper (nullable):
  * device float[2] = {step, lr} read by the kernel instead of the two host arguments, so that a captured CUDA graph
  * of the training step follows the update count and the learning-rate schedule. */
 int rfn_adam_step_f32(int n_tensors, float* const* p, const float* const* g, float* const* m, float* const* v,
                       const int64_t* numel, float lr, float beta1, float beta2, float eps, float weight_decay,
-                      float grad_clip, int step, const float* d_hyper, rfn_stream_t stream);
+                      float grad_clip, float grad_scale, int step, const float* d_hyper, rfn_stream_t stream);
 
 /* ---- CIDEr-D reward scorer (cider/pyciderevalcap/ciderD/ciderD_scorer.py:114-199 as driven by
  * get_rewards.py:39-112).  Captions are int32 token rows (the tokens up to and including the first 0 form the

@@ -100,7 +100,7 @@ _SIGNATURES = {
     "rfn_ciderd_reward_f32": (_i, [_vp, _i, _i, C.c_double, _i, _vp, _vp]),
     "rfn_ciderd_hash": (C.c_uint64, [C.POINTER(C.c_int32)]),
     "rfn_transpose_f32": (_i, [_vp, _i, _i, _i, _vp, _i, _vp]),
-    "rfn_adam_step_f32": (_i, [_i, _pp, _pp, _pp, _pp, C.POINTER(C.c_int64), _f, _f, _f, _f, _f, _f, _i, _vp, _vp]),
+    "rfn_adam_step_f32": (_i, [_i, _pp, _pp, _pp, _pp, C.POINTER(C.c_int64), _f, _f, _f, _f, _f, _f, _f, _i, _vp, _vp]),
     "rfn_rl_loss_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
 }
 

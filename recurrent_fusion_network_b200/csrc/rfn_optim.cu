@@ -20,8 +20,8 @@ struct AdamChunk {
 };
 
 __global__ void __launch_bounds__(256)
-adam_kernel(AdamChunk c, float lr, float beta1, float beta2, float eps, float wd, float clip, float bc1, float bc2_sqrt,
-            const float* __restrict__ d_hyper) {
+adam_kernel(AdamChunk c, float lr, float beta1, float beta2, float eps, float wd, float clip, float gscale, float bc1,
+            float bc2_sqrt, const float* __restrict__ d_hyper) {
   if (d_hyper) {   // capturable mode: {step, lr} live in device memory so that a CUDA graph replay sees new values
     const float step = d_hyper[0];
     lr = d_hyper[1];
@@ -41,7 +41,7 @@ adam_kernel(AdamChunk c, float lr, float beta1, float beta2, float eps, float wd
   for (int i = threadIdx.x; i < AD_BLOCK_ELEMS; i += 256) {
     const long long k = base + i;
     if (k >= n) break;
-    float gk = g[k];
+    float gk = g[k] * gscale;                                  // 1 / world: the mean of data-parallel gradient sums
     if (clip > 0.f) gk = fminf(fmaxf(gk, -clip), clip);      // clip_gradient: element-wise clamp
     const float pk = p[k];
     gk = fmaf(wd, pk, gk);                                     // L2 weight decay added to the gradient
@@ -59,7 +59,7 @@ adam_kernel(AdamChunk c, float lr, float beta1, float beta2, float eps, float wd
 using namespace rfn;
 extern "C" int rfn_adam_step_f32(int n_tensors, float* const* p, const float* const* g, float* const* m, float* const* v,
                                  const int64_t* numel, float lr, float beta1, float beta2, float eps, float weight_decay,
-                                 float grad_clip, int step, const float* d_hyper, rfn_stream_t stream) {
+                                 float grad_clip, float grad_scale, int step, const float* d_hyper, rfn_stream_t stream) {
   RFN_CHECK_ARG(n_tensors >= 0 && p && g && m && v && numel && (step >= 1 || d_hyper), "rfn_adam_step_f32: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   const float bc1 = 1.f - powf(beta1, (float)step);
@@ -78,7 +78,7 @@ extern "C" int rfn_adam_step_f32(int n_tensors, float* const* p, const float* co
     c.block_start[c.nt] = blocks;
     if (blocks == 0) continue;
     ProfScope prof__(TAG_MISC, st);
-    adam_kernel<<<blocks, 256, 0, st>>>(c, lr, beta1, beta2, eps, weight_decay, grad_clip, bc1, bc2_sqrt, d_hyper);
+    adam_kernel<<<blocks, 256, 0, st>>>(c, lr, beta1, beta2, eps, weight_decay, grad_clip, grad_scale, bc1, bc2_sqrt, d_hyper);
     RFN_LAUNCH_CHECK();
   }
   return RFN_OK;

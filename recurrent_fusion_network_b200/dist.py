@@ -5,6 +5,7 @@ gradient path is used) is plain data parallelism: every loss term of the referen
 LOCAL row count (misc/utils.py:72,177,184,188), so with equal rows per rank the MEAN of the rank gradients
 equals the single-process gradient on the concatenated batch; the element-wise clamp of
 misc/utils.py:292-296 must be applied AFTER the average."""
+import os
 from typing import Callable, Iterable, Optional, Sequence, Tuple
 
 import torch
@@ -72,9 +73,12 @@ def _broadcast_width(L, group):
 
 
 def average_gradients(params: Iterable[torch.nn.Parameter], group=None, bucket_bytes: int = 256 << 20,
-                      grad_clip: Optional[float] = None) -> None:
-    """Bucketed all-reduce(sum)/world of the gradients, then the reference's element-wise clamp.
-    1.958 GB of fp32 gradients per step for the full model; buckets bound launch latency."""
+                      grad_clip: Optional[float] = None, divide: bool = True) -> None:
+    """All-reduce of the gradients (sum, then / world unless divide=False), then the reference's element-wise clamp.
+    1.958 GB of fp32 gradients per step for the full model.
+    NCCL: the gradient tensors are reduced IN PLACE as coalesced groups (one ncclGroup per <= 256 tensors): no
+    flatten / copy-back passes over HBM.  divide=False leaves the SUM for FusedAdam(grad_scale=1/world), which folds the
+    division (and the clamp) into the optimizer pass.  Other backends (gloo in the CPU tests): flat buckets."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         if grad_clip is not None:
             for p in params:
@@ -82,6 +86,19 @@ def average_gradients(params: Iterable[torch.nn.Parameter], group=None, bucket_b
                     p.grad.clamp_(-grad_clip, grad_clip)
         return
     world = dist.get_world_size(group)
+    grads = [p.grad for p in params if p.grad is not None]
+    if grads and grads[0].is_cuda and dist.get_backend(group) == "nccl" and not os.environ.get("RFN_FLAT_ALLREDUCE"):
+        from torch.distributed.distributed_c10d import _coalescing_manager
+        for i in range(0, len(grads), 256):
+            with _coalescing_manager(group=group, device=grads[0].device):
+                for g in grads[i:i + 256]:
+                    dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
+        if divide:
+            torch._foreach_div_(grads, float(world))
+        if grad_clip is not None:
+            torch._foreach_clamp_min_(grads, -grad_clip)
+            torch._foreach_clamp_max_(grads, grad_clip)
+        return
     bucket, size = [], 0
 
     def flush():
@@ -90,7 +107,8 @@ def average_gradients(params: Iterable[torch.nn.Parameter], group=None, bucket_b
             return
         flat = torch.cat([g.reshape(-1) for g in bucket])
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        flat.div_(world)
+        if divide:
+            flat.div_(world)
         if grad_clip is not None:
             flat.clamp_(-grad_clip, grad_clip)
         off = 0

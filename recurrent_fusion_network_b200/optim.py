@@ -3,6 +3,9 @@ clip_gradient (misc/utils.py:292-296) folded in, as one HBM pass per step throug
 Same constructor arguments / param_groups / state conventions as torch.optim.Adam, so misc/utils.set_lr and the
 reference's checkpoint code keep working.
 
+grad_scale (1 / world_size) turns the SUM of dist.average_gradients(..., divide=False) into the mean inside the same
+pass, before the clamp, exactly where the reference's averaged gradient would be clamped.
+
 capturable=True keeps {step, lr} of each group in a device tensor that the kernel reads, so that step() can be
 captured in a CUDA graph (training.GraphedXEStep): the update count advances on the device and `sync_lr()` pushes a
 changed param_group['lr'] before the next replay."""
@@ -14,8 +17,10 @@ from ._capi import check, lib, ptr, ptr_array, stream
 
 
 class FusedAdam(torch.optim.Optimizer):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_clip=0.0, capturable=False):
-        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, grad_clip=grad_clip, capturable=capturable)
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_clip=0.0, capturable=False,
+                 grad_scale=1.0):
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, grad_clip=grad_clip, capturable=capturable,
+                        grad_scale=grad_scale)
         super().__init__(params, defaults)
         self._hyper_t = {}     # group index -> (device {step, lr}, device {1, 0}); kept out of param_groups / state_dict
 
@@ -76,6 +81,7 @@ class FusedAdam(torch.optim.Optimizer):
                                           ptr_array([self.state[p]["exp_avg"] for p in ps]),
                                           ptr_array([self.state[p]["exp_avg_sq"] for p in ps]), numel, float(group["lr"]),
                                           float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
-                                          float(group.get("grad_clip", 0.0)), int(step), ptr(hyper), stream()),
+                                          float(group.get("grad_clip", 0.0)), float(group.get("grad_scale", 1.0)), int(step),
+                                          ptr(hyper), stream()),
                   "rfn_adam_step_f32")
         return loss

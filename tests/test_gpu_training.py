@@ -169,6 +169,18 @@ def test_fused_adam_matches_clip_gradient_plus_torch_adam():
         assert maxdiff(pa, pb) <= 2e-6
     ob.param_groups[0]["lr"] = 1e-4   # set_lr works through param_groups
     ob.step()
+    # grad_scale = 1 / world: the optimizer pass turns an all-reduced SUM into the mean before the clamp
+    c = [torch.nn.Parameter(p.detach().clone()) for p in a]
+    d = [torch.nn.Parameter(p.detach().clone()) for p in a]
+    oc = torch.optim.Adam(c, lr=5e-4, weight_decay=1e-5)
+    od = FusedAdam(d, lr=5e-4, weight_decay=1e-5, grad_clip=1.0, grad_scale=0.25)
+    for pc, pd in zip(c, d):
+        gr = torch.randn(pc.shape, generator=g).cuda() * 8
+        pc.grad = gr / 4; pd.grad = gr.clone()
+    clip_gradient(oc, 1.0)
+    oc.step(); od.step()
+    for pc, pd in zip(c, d):
+        assert maxdiff(pc, pd) <= 2e-6
 
 
 def test_graphed_xe_step_matches_eager_steps():
