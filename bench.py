@@ -381,8 +381,9 @@ def xe_train_bench(model, device, world, rank, steps, timed):
     for name, dd in (("as_written", 1), ("deduplicated", spi)):
         model.dedup_rows = dd
         opt_g = FusedAdam(params, lr=5e-4, weight_decay=1e-5, grad_clip=1.0, capturable=True, grad_scale=1.0 / world)
+        # N > 1: the gradient all-reduce is captured inside the backward graph, bucket by bucket on a side stream
         gs = TR.GraphedXEStep(model, crit, opt_g, fc, att, labels, masks, top, 10.0, warmup=2,
-                              between=(lambda: D.average_gradients(params, divide=False)) if world > 1 else None)
+                              grad_sync=D.OverlappedGradSync(params) if world > 1 else None)
 
         def gstep(gs=gs):
             l = gs(fc, att, labels, masks, top)   # includes the copies into the graph's static input buffers
@@ -406,7 +407,8 @@ def xe_train_bench(model, device, world, rank, steps, timed):
         p.grad = None
     ga, gd = graphed["as_written"], graphed["deduplicated"]
     return dict(metric="xe_train_tokens_per_sec", value=ga["value"], unit="target tokens/s", ms_per_step=ga["ms_per_step"],
-                api="training.GraphedXEStep (forward + backward | gradient all-reduce | clamp + Adam replayed from CUDA graphs)",
+                api="training.GraphedXEStep: forward + backward (with the bucketed NCCL gradient all-reduce overlapped inside, "
+                    "dist.OverlappedGradSync) | mean + clamp + Adam, replayed from CUDA graphs",
                 eager=dict(value=round(tokens / (ms / 1e3), 1), ms_per_step=round(ms, 2),
                            note="the same step issued op by op from Python (~2,100 kernels): bound by the host"),
                 deduplicated=dict(value=gd["value"], ms_per_step=gd["ms_per_step"],

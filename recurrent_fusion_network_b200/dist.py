@@ -125,3 +125,53 @@ def average_gradients(params: Iterable[torch.nn.Parameter], group=None, bucket_b
         if size >= bucket_bytes:
             flush()
     flush()
+
+
+class OverlappedGradSync:
+    """Gradient all-reduce that overlaps the backward pass: post-accumulate-grad hooks collect the gradients as autograd
+    finishes them (decoder first, stage-1 steps last) and, every `bucket_bytes`, launch one coalesced in-place NCCL
+    all-reduce (SUM) on a side stream that waits only for the work issued so far.  finish() flushes the rest and joins
+    the side stream.  Usable eagerly or inside a CUDA-graph capture (training.GraphedXEStep), where the fork / join
+    become graph dependencies and the collectives are replayed with the graph.  The mean is left to
+    FusedAdam(grad_scale=1/world)."""
+
+    def __init__(self, params, group=None, bucket_bytes: int = 96 << 20):
+        self.params = [p for p in params if p.requires_grad]
+        self.group, self.bucket_bytes = group, int(bucket_bytes)
+        self.side = torch.cuda.Stream()
+        self.pending, self.pending_bytes, self.handles = [], 0, []
+        self.buckets_launched = 0
+
+    def install(self):
+        self.remove()
+        for p in self.params:
+            self.handles.append(p.register_post_accumulate_grad_hook(self._hook))
+
+    def remove(self):
+        for h in self.handles:
+            h.remove()
+        self.handles = []
+
+    def _hook(self, p):
+        self.pending.append(p.grad)
+        self.pending_bytes += p.grad.numel() * p.grad.element_size()
+        if self.pending_bytes >= self.bucket_bytes:
+            self._flush()
+
+    def _flush(self):
+        if not self.pending:
+            return
+        from torch.distributed.distributed_c10d import _coalescing_manager
+        cur = torch.cuda.current_stream()
+        self.side.wait_stream(cur)
+        with torch.cuda.stream(self.side):
+            for i in range(0, len(self.pending), 256):
+                with _coalescing_manager(group=self.group, device=self.pending[0].device):
+                    for g in self.pending[i:i + 256]:
+                        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
+        self.pending, self.pending_bytes = [], 0
+        self.buckets_launched += 1
+
+    def finish(self):
+        self._flush()
+        torch.cuda.current_stream().wait_stream(self.side)

@@ -148,13 +148,15 @@ class GraphedXEStep:
     CUDA graphs and replayed: the eager step issues ~2,600 kernels from Python and is bound by the host, not the device.
 
     Two graphs -- forward+backward, and the optimizer -- so that the data-parallel gradient all-reduce
-    (dist.average_gradients) runs between them.  Inputs are copied into static buffers before each replay.  The decode
+    (dist.average_gradients, `between`) can run between them; or pass grad_sync=dist.OverlappedGradSync(params) to have
+    the all-reduce captured inside the first graph, overlapped with the backward pass.  Inputs are copied into static buffers before each replay.  The decode
     loop is captured over seq_length + 1 label columns (the reference stops at the first all-zero column, :274-275,
     which is at most that many; columns it would have skipped carry mask 0 and contribute nothing to the loss or the
     gradients).  Needs ss_prob == 0 (scheduled sampling
     reads a mask back to the host) and a FusedAdam(capturable=True)."""
 
-    def __init__(self, model, crit, optimizer, fc, att, labels, masks, top_true, reason_weight, warmup=3, between=None):
+    def __init__(self, model, crit, optimizer, fc, att, labels, masks, top_true, reason_weight, warmup=3, between=None,
+                 grad_sync=None):
         if model.ss_prob > 0.0:
             raise RuntimeError("GraphedXEStep: scheduled sampling is not capturable (ss_prob must be 0)")
         if not all(g.get("capturable") for g in optimizer.param_groups):
@@ -175,8 +177,16 @@ class GraphedXEStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.g_fb = torch.cuda.CUDAGraph()
+        # grad_sync (dist.OverlappedGradSync): the data-parallel all-reduce is captured INSIDE the forward+backward graph,
+        # bucket by bucket on a side stream while the backward of the earlier layers still runs (then `between` is unused)
         with torch.cuda.graph(self.g_fb):
+            if grad_sync is not None:
+                grad_sync.install()
             self.loss = self._fwd_bwd()
+            if grad_sync is not None:
+                grad_sync.finish()
+        if grad_sync is not None:
+            grad_sync.remove()
         self.g_opt = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.g_opt, pool=self.g_fb.pool()):
             optimizer.step()
