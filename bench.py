@@ -225,10 +225,10 @@ def run_ours(args):
     # traffic: dram__bytes_read+write of ONE launch from the committed ncu --set full captures (resnet encoder,
     # 1024 images per launch; profiles/r1_gemm_tc2p_score_ncu.txt, profiles/r1_attention_step_ncu.txt); the
     # algorithmic bytes of that same launch are given beside it.
-    passes = {0: 1, 1: 3, 2: 1}[args.gemm_mode]
+    passes = {0: 1, 1: 3, 2: 1, 3: 2}[args.gemm_mode]   # tensor-core cost per product in TF32-MMA units (mode 3: 1 TF32 + 2 BF16 at half cost)
     roof_gemm = dict(kernel="gemm_att2att_stage1", bound="tensor", achieved=round(tf, 2), peak=peaks["bf16_sustained"],
                      unit="TFLOP/s", frac=round(tf / peaks["bf16_sustained"], 4),
-                     traffic=1.718e9 if args.gemm_mode == 1 else None,
+                     traffic=1.718e9 if args.gemm_mode in (1, 3) else None,
                      traffic_note="ncu capture of one launch (resnet encoder, 1024 images, persistent 2-CTA kernel): 1.711 GB read "
                                   "+ 0.007 GB written vs 1.648 GB algorithmic (A once + W once); tensor pipe 97.7 % active",
                      mma_tflops_executed=round(tf * passes, 1),
@@ -555,7 +555,8 @@ def ciderd_bench(device):
 
 
 def args_dtype(args):
-    return {0: "fp32", 1: "fp32 (3xTF32 tcgen05 contraction, fp32 accumulate)", 2: "bf16"}[args.gemm_mode]
+    return {0: "fp32", 1: "fp32 (3xTF32 tcgen05 contraction, fp32 accumulate)", 2: "bf16",
+            3: "fp32 (TF32 + 2 BF16 cross-term tcgen05 contraction, fp32 accumulate)"}[args.gemm_mode]
 
 
 def cpu_baseline(model, n_images, threads=None):

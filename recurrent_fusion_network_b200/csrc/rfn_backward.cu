@@ -145,7 +145,7 @@ int gemm_general(bool a_kmajor, bool b_kmajor, const float* A, int lda, const fl
   // dX = dY . W with W = nn.Linear weights (out, in) = (K, N) row-major: tensor engine, B operand MN-major
   if (a_kmajor && !b_kmajor && gemm_mode() >= 1 && (long)M * N * K >= (1L << 25) && N >= 128 &&
       tc_general_ok(A, lda, B, ldb, C, ldc, N, K))
-    return gemm_general_tc(A, lda, B, ldb, C, ldc, M, N, K, accumulate, gemm_mode() == 1 ? 3 : 1, st);
+    return gemm_general_tc(A, lda, B, ldb, C, ldc, M, N, K, accumulate, tc_passes(gemm_mode()), st);
   return gemm_general_simt(a_kmajor, b_kmajor, A, lda, B, ldb, C, ldc, M, N, K, accumulate, st);
 }
 
@@ -661,11 +661,11 @@ int rfn_transpose_f32(const float* src, int ld_src, int rows, int cols, float* d
 }
 int rfn_gemm_general_f32_engine(int engine, int a_kmajor, int b_kmajor, const float* A, int lda, const float* B, int ldb,
                                 float* C, int ldc, int M, int N, int K, int accumulate, rfn_stream_t stream) {
-  RFN_CHECK_ARG(engine >= 0 && engine <= 2, "rfn_gemm_general_f32_engine: engine %d not in {0,1,2}", engine);
+  RFN_CHECK_ARG(engine >= 0 && engine <= 3, "rfn_gemm_general_f32_engine: engine %d not in {0,1,2,3}", engine);
   if (engine >= 1) {
     RFN_CHECK_ARG(a_kmajor && !b_kmajor && A && B && C && tc_general_ok(A, lda, B, ldb, C, ldc, N, K),
                   "rfn_gemm_general_f32_engine: the tensor engine takes the (1, 0) layout with 16-byte aligned rows");
-    return gemm_general_tc(A, lda, B, ldb, C, ldc, M, N, K, accumulate, engine == 1 ? 3 : 1, (cudaStream_t)stream);
+    return gemm_general_tc(A, lda, B, ldb, C, ldc, M, N, K, accumulate, tc_passes(engine), (cudaStream_t)stream);
   }
   RFN_CHECK_ARG(A && B && C && M >= 0 && N >= 0 && K >= 0, "rfn_gemm_general_f32_engine: bad arguments");
   return gemm_general_simt(a_kmajor != 0, b_kmajor != 0, A, lda, B, ldb, C, ldc, M, N, K, accumulate, (cudaStream_t)stream);

@@ -75,7 +75,7 @@ int rfn_check_device(void) {
 }
 
 int rfn_set_gemm_mode(int mode) {
-  RFN_CHECK_ARG(mode >= 0 && mode <= 2, "gemm mode %d not in {0,1,2}", mode);
+  RFN_CHECK_ARG(mode >= 0 && mode <= 3, "gemm mode %d not in {0,1,2,3}", mode);
   rfn::g_gemm_mode.store(mode);
   return RFN_OK;
 }

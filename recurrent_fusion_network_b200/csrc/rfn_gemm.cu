@@ -8,7 +8,7 @@ namespace rfn {
 
 int gemm_engine(const GemmArgs& a, int engine, cudaStream_t st) {
   if (engine == 0) return gemm_simt(a, st);
-  return gemm_tc(a, engine == 1 ? 3 : 1, nullptr, 0, nullptr, nullptr, 0, st);
+  return gemm_tc(a, tc_passes(engine), nullptr, 0, nullptr, nullptr, 0, st);
 }
 
 int gemm(const GemmArgs& a, cudaStream_t st) {
@@ -17,7 +17,7 @@ int gemm(const GemmArgs& a, cudaStream_t st) {
   if (mode >= 1 && a.splitk_ok && gemm_tc_supported(a)) {   // training: few rows, the weights are streamed once
     long wk = 0;
     for (int s = 0; s < a.nsrc; ++s) wk += a.src[s].K;
-    if (wk * a.N >= (a.M > 32 ? (1L << 17) : (1L << 20))) return gemm_tc_splitk(a, false, mode == 1 ? 3 : 1, st);
+    if (wk * a.N >= (a.M > 32 ? (1L << 17) : (1L << 20))) return gemm_tc_splitk(a, false, tc_passes(mode), st);
   }
   return gemm_simt(a, st);
 }
@@ -27,7 +27,7 @@ int gemm(const GemmArgs& a, cudaStream_t st) {
 extern "C" int rfn_linear_f32_engine(int engine, int n_src, const float* const* x, const int* ldx, const float* const* W,
                                      const int* K, const float* const* bias, float* y, int ldy, int M, int N,
                                      int accumulate, rfn_stream_t stream) {
-  RFN_CHECK_ARG(engine >= 0 && engine <= 2, "rfn_linear_f32_engine: engine %d not in {0,1,2}", engine);
+  RFN_CHECK_ARG(engine >= 0 && engine <= 3, "rfn_linear_f32_engine: engine %d not in {0,1,2,3}", engine);
   RFN_CHECK_ARG(n_src >= 1 && n_src <= 3 && x && ldx && W && K, "rfn_linear_f32_engine: bad source arrays");
   rfn::GemmArgs a{};
   a.nsrc = n_src;

@@ -358,6 +358,25 @@ int tc_make_map(CUtensorMap* tm, const float* base, int rows, int K, int ld, int
   return RFN_OK;
 }
 
+int tc_make_map_bf16_tiles(CUtensorMap* tm, const void* base, int Ng, int Kp) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return RFN_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)Kp * 8, (cuuint64_t)Ng};
+  cuuint64_t gstr[1] = {(cuuint64_t)Kp * 8 * 2};
+  cuuint32_t box[2] = {256, 16};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (bf16 tiles) failed (%d) Ng=%d Kp=%d", (int)r, Ng, Kp);
+    return RFN_ERR_CUDA;
+  }
+  return RFN_OK;
+}
+
 template <int BN, int STAGES, int PASSES, int CH, int EPI>
 static int launch_tc_epi(const TcArgs& t, cudaStream_t st) {
   using S = TcSmem<BN, PASSES>;
@@ -407,6 +426,8 @@ int tc_score_slices(int N) { return ((N + 255) / 256) * 2; }
 int gemm_tc(const GemmArgs& a, int passes, const float* g, int ldg, const float* wv, float* score, int natt,
             cudaStream_t st) {
   ProfScope prof__(TAG_GEMM_OTHER, st);
+  const bool bf16x = (passes == 2);   // engine mode 3: BF16 cross terms, persistent kernel only
+  if (bf16x) passes = 3;
   RFN_CHECK_ARG(gemm_tc_supported(a), "gemm_tc: operands must be 16-byte aligned with K, N, ld multiples of 4");
   if (a.M == 0) return RFN_OK;
   TcArgs t{};
@@ -445,7 +466,17 @@ int gemm_tc(const GemmArgs& a, int passes, const float* g, int ldg, const float*
   }
   // persistent clusters for the fused-epilogue GEMMs; the plain-store GEMMs keep the 3-stage one-tile kernel
   // (the persistent store epilogue needs staging memory that costs a pipeline stage: measured slower)
-  if (cluster) return (g_tc_cluster.load() >= 2 && passes == 3 && t.epi != 0) ? launch_tc2p(t, st) : launch_tc2(t, passes, st);
+  if (cluster && g_tc_cluster.load() >= 2 && passes == 3 && (t.epi != 0 || (bf16x && !t.ksplit && a.nsrc == 1))) {
+    void* scratch = nullptr;
+    if (bf16x && a.nsrc == 1) {   // engine mode 3 (single-source GEMMs): bf16 cross terms
+      t.bf16x = 1;
+      RFN_TRY(tc2p_prepare_bf16_w(t, a.src[0].w, a.src[0].ldw, a.N, a.src[0].K, &scratch, st));
+    }
+    const int rc = launch_tc2p(t, st);
+    if (scratch) cudaFreeAsync(scratch, st);
+    return rc;
+  }
+  if (cluster) return launch_tc2(t, passes, st);
   if (passes == 3) return bn == 256 ? launch_tc<256, 2, 3, 4>(t, st) : launch_tc<128, 3, 3, 4>(t, st);
   return bn == 256 ? launch_tc<256, 4, 1, 1>(t, st) : launch_tc<128, 6, 1, 1>(t, st);
 }
@@ -455,6 +486,7 @@ int gemm_tc(const GemmArgs& a, int passes, const float* g, int ldg, const float*
 // partial tiles are added atomically.  b_mn: W given as (K, N) row-major (dX = dY . W on nn.Linear weights).
 int gemm_tc_splitk(const GemmArgs& a, bool b_mn, int passes, cudaStream_t st) {
   ProfScope prof__(TAG_GEMM_OTHER, st);
+  if (passes == 2) passes = 3;
   if (a.M == 0 || a.N == 0) return RFN_OK;
   TcArgs t{};
   t.nsrc = a.nsrc;
@@ -489,6 +521,8 @@ int gemm_tc_splitk(const GemmArgs& a, bool b_mn, int passes, cudaStream_t st) {
 int gemm_tc_vocab(const GemmArgs& a, int passes, float* st_max, float* st_sum, float* st_val, int32_t* st_idx, int ktop,
                   cudaStream_t st) {
   ProfScope prof__(TAG_GEMM_LOGIT, st);
+  const bool bf16x = (passes == 2);
+  if (bf16x) passes = 3;
   RFN_CHECK_ARG(gemm_tc_supported(a) && a.nsrc == 1 && ktop >= 1 && ktop <= RFN_MAX_BEAM, "gemm_tc_vocab: unsupported arguments");
   if (a.M == 0) return RFN_OK;
   TcArgs t{};
@@ -502,7 +536,17 @@ int gemm_tc_vocab(const GemmArgs& a, int passes, float* st_max, float* st_sum, f
   t.epi = 2;
   t.st_max = st_max; t.st_sum = st_sum; t.st_val = st_val; t.st_idx = st_idx; t.ktop = ktop;
   t.dbg = (g_tc_dbg_epi.load() < 0 || g_tc_dbg_epi.load() == 2) ? g_tc_dbg.load() : nullptr;
-  if (cluster) return (g_tc_cluster.load() >= 2 && passes == 3) ? launch_tc2p(t, st) : launch_tc2(t, passes, st);
+  if (cluster && g_tc_cluster.load() >= 2 && passes == 3) {
+    void* scratch = nullptr;
+    if (bf16x) {
+      t.bf16x = 1;
+      RFN_TRY(tc2p_prepare_bf16_w(t, a.src[0].w, a.src[0].ldw, a.N, a.src[0].K, &scratch, st));
+    }
+    const int rc = launch_tc2p(t, st);
+    if (scratch) cudaFreeAsync(scratch, st);
+    return rc;
+  }
+  if (cluster) return launch_tc2(t, passes, st);
   return passes == 3 ? launch_tc<256, 2, 3, 4>(t, st) : launch_tc<256, 4, 1, 1>(t, st);
 }
 

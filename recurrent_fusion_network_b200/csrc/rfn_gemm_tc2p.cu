@@ -13,6 +13,8 @@
 // Tiles are assigned round-robin (tile = cluster, cluster + #clusters, ...) with the n-tile index fastest, so
 // every role derives the same sequence without communication.
 #include <cuda.h>
+#include <algorithm>
+#include <cuda_bf16.h>
 
 #include "rfn_internal.cuh"
 #include "rfn_tc_args.cuh"
@@ -99,10 +101,15 @@ __global__ void __launch_bounds__(TP_THREADS, 1) gemm_tc2p_kernel(const __grid_c
             const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
             mbar_wait(smem_u32(&empty[st]), ph ^ 1u);
             const uint32_t fb = smem_u32(&full[st]);
-            mbar_arrive_expect_tx(fb, (uint32_t)TP_TILE_BYTES);
+            mbar_arrive_expect_tx(fb, (uint32_t)(TP_TILE_BYTES + (a.bf16x ? 16384 : 0)));
             uint8_t* stage = smem + st * TP_STAGE_BYTES;
             tma_load_2d(&a.tm_x[s], fb, smem_u32(stage), kb * TC_BK, m0);
             tma_load_2d(&a.tm_w[s], fb, smem_u32(stage + TC_A_BYTES), kb * TC_BK, n0 + (int)rank * TP_BH);
+            if (a.bf16x) {   // this CTA's 128 W rows as 16 groups x 512 bytes of bf16 core matrices, twice (w, w_lo)
+              const int grp = (n0 + (int)rank * TP_BH) >> 3;
+              tma_load_2d(&a.tm_wb[0], fb, smem_u32(stage + TP_TILE_BYTES + 16384), kb * 256, grp);
+              tma_load_2d(&a.tm_wb[1], fb, smem_u32(stage + TP_TILE_BYTES + 24576), kb * 256, grp);
+            }
           }
         }
       }
@@ -126,14 +133,31 @@ __global__ void __launch_bounds__(TP_THREADS, 1) gemm_tc2p_kernel(const __grid_c
             const uint32_t sa = smem_u32(smem + st * TP_STAGE_BYTES);
             const uint64_t da_hi = make_desc_sw128(sa);
             const uint64_t db_hi = make_desc_sw128(sa + TC_A_BYTES);
-            const uint64_t da_lo = make_desc_sw128(sa + TP_TILE_BYTES);
-            const uint64_t db_lo = make_desc_sw128(sa + TP_TILE_BYTES + TC_A_BYTES);
+            if (a.bf16x) {
+              // hi.hi in TF32 (raw tile, truncated by the tensor core); x_lo.w and x.w_lo in BF16 from the four 8 KB
+              // tiles the splitter wrote: [x | x_lo | w | w_lo]
+              constexpr uint32_t idesc_b = make_idesc_bf16_m(2 * TC_BM, TP_BN);
+              const uint32_t sb = sa + TP_TILE_BYTES;
+              const uint64_t dxb = make_desc_bf16_interleaved(sb), dxl = make_desc_bf16_interleaved(sb + 8192);
+              const uint64_t dwb = make_desc_bf16_interleaved(sb + 16384), dwl = make_desc_bf16_interleaved(sb + 24576);
 #pragma unroll
-            for (int k = 0; k < TC_BK / 8; ++k) {
-              const uint64_t adv = (uint64_t)(k * 2);
-              umma2_tf32(td, da_hi + adv, db_hi + adv, idesc, (chunk_start && k == 0) ? 0u : 1u);
-              umma2_tf32(td, da_lo + adv, db_hi + adv, idesc, 1u);
-              umma2_tf32(td, da_hi + adv, db_lo + adv, idesc, 1u);
+              for (int k = 0; k < TC_BK / 8; ++k)
+                umma2_tf32(td, da_hi + (uint64_t)(k * 2), db_hi + (uint64_t)(k * 2), idesc, (chunk_start && k == 0) ? 0u : 1u);
+#pragma unroll
+              for (int k = 0; k < TC_BK / 16; ++k) {
+                umma2_bf16(td, dxl + (uint64_t)(k * 16), dwb + (uint64_t)(k * 16), idesc_b, 1u);
+                umma2_bf16(td, dxb + (uint64_t)(k * 16), dwl + (uint64_t)(k * 16), idesc_b, 1u);
+              }
+            } else {
+              const uint64_t da_lo = make_desc_sw128(sa + TP_TILE_BYTES);
+              const uint64_t db_lo = make_desc_sw128(sa + TP_TILE_BYTES + TC_A_BYTES);
+#pragma unroll
+              for (int k = 0; k < TC_BK / 8; ++k) {
+                const uint64_t adv = (uint64_t)(k * 2);
+                umma2_tf32(td, da_hi + adv, db_hi + adv, idesc, (chunk_start && k == 0) ? 0u : 1u);
+                umma2_tf32(td, da_lo + adv, db_hi + adv, idesc, 1u);
+                umma2_tf32(td, da_hi + adv, db_lo + adv, idesc, 1u);
+              }
             }
             umma2_commit(smem_u32(&empty[st]));
             if (kb % TP_CH == TP_CH - 1 || kb == total_kb - 1) umma2_commit(smem_u32(&cfull[b]));
@@ -154,6 +178,34 @@ __global__ void __launch_bounds__(TP_THREADS, 1) gemm_tc2p_kernel(const __grid_c
         mbar_wait(smem_u32(&full[st]), ph);
         const uint4* hi = reinterpret_cast<const uint4*>(smem + st * TP_STAGE_BYTES);
         uint4* lo = reinterpret_cast<uint4*>(smem + st * TP_STAGE_BYTES + TP_TILE_BYTES);
+        if (a.bf16x) {
+          // x tile only (the W side arrives as bf16 by TMA).  item = (row r, 8-element k-chunk c): two swizzled 16-byte
+          // pieces of the raw fp32 row in, one 16-byte core-matrix row of bf16(v) and one of bf16(v - trunc_tf32(v)) out
+          uint8_t* base = smem + st * TP_STAGE_BYTES + TP_TILE_BYTES;
+          // rows fastest across the lanes: a quarter-warp reads 8 distinct swizzled chunks and writes one whole 128-byte
+          // core matrix (both bank-conflict free)
+#pragma unroll 8
+          for (int i = t; i < 128 * 4; i += 64) {
+            const int r = i & 127, c = i >> 7;
+            const uint4* row = hi + r * 8;
+            const uint4 v0 = row[(2 * c) ^ (r & 7)], v1 = row[(2 * c + 1) ^ (r & 7)];
+            const float f[8] = {__uint_as_float(v0.x), __uint_as_float(v0.y), __uint_as_float(v0.z), __uint_as_float(v0.w),
+                                __uint_as_float(v1.x), __uint_as_float(v1.y), __uint_as_float(v1.z), __uint_as_float(v1.w)};
+            uint32_t pb[4], pl[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float a0 = f[2 * e], a1 = f[2 * e + 1];
+              const float l0 = a0 - __uint_as_float(__float_as_uint(a0) & 0xffffe000u);
+              const float l1 = a1 - __uint_as_float(__float_as_uint(a1) & 0xffffe000u);
+              __nv_bfloat162 b2 = __floats2bfloat162_rn(a0, a1), l2 = __floats2bfloat162_rn(l0, l1);
+              pb[e] = *reinterpret_cast<uint32_t*>(&b2);
+              pl[e] = *reinterpret_cast<uint32_t*>(&l2);
+            }
+            const int off = (r >> 3) * 512 + c * 128 + (r & 7) * 16;
+            *reinterpret_cast<uint4*>(base + off) = make_uint4(pb[0], pb[1], pb[2], pb[3]);
+            *reinterpret_cast<uint4*>(base + off + 8192) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+          }
+        } else
 #pragma unroll 8
         for (int i = t; i < TP_TILE_BYTES / 16; i += 64) {
           const uint4 v = hi[i];
@@ -325,6 +377,52 @@ __global__ void __launch_bounds__(TP_THREADS, 1) gemm_tc2p_kernel(const __grid_c
     tc_fence_after();
     tmem_dealloc2(tmem_base, 512);
   }
+}
+
+// bf16(W) and bf16(W - trunc_tf32(W)) in the layout the bf16 MMA descriptors expect, so that one plain TMA box lands a
+// 128-row x 32-element tile as 16 groups x 4 core matrices: element (n, k) at ((n/8) * (Kp/8) + k/8) * 64 + (n%8) * 8 + k%8
+__global__ void __launch_bounds__(256) w_bf16_tiles_kernel(const float* __restrict__ W, int ldw, int N, int K, int Ng, int Kp,
+                                                           __nv_bfloat16* __restrict__ Wb, __nv_bfloat16* __restrict__ Wl) {
+  const long total = (long)Ng * 8 * (Kp / 8);
+  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+    const int kc = (int)(i % (Kp / 8));
+    const int n = (int)(i / (Kp / 8));
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = kc * 8 + e;
+      f[e] = (n < N && k < K) ? __ldg(W + (size_t)n * ldw + k) : 0.f;
+    }
+    uint32_t pb[4], pl[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float l0 = f[2 * e] - __uint_as_float(__float_as_uint(f[2 * e]) & 0xffffe000u);
+      const float l1 = f[2 * e + 1] - __uint_as_float(__float_as_uint(f[2 * e + 1]) & 0xffffe000u);
+      __nv_bfloat162 b2 = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]), l2 = __floats2bfloat162_rn(l0, l1);
+      pb[e] = *reinterpret_cast<uint32_t*>(&b2);
+      pl[e] = *reinterpret_cast<uint32_t*>(&l2);
+    }
+    const size_t off = ((size_t)(n >> 3) * (Kp / 8) + kc) * 64 + (size_t)(n & 7) * 8;
+    *reinterpret_cast<uint4*>(Wb + off) = make_uint4(pb[0], pb[1], pb[2], pb[3]);
+    *reinterpret_cast<uint4*>(Wl + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+  }
+}
+
+// prepares the bf16 W tiles of engine mode 3 in stream-ordered scratch memory (freed after the GEMM on the same stream)
+int tc2p_prepare_bf16_w(TcArgs& t, const float* W, int ldw, int N, int K, void** scratch, cudaStream_t st) {
+  const int Ng = (N + 7) / 8, Kp = (K + TC_BK - 1) / TC_BK * TC_BK;
+  const size_t elems = (size_t)Ng * 8 * Kp;
+  void* p = nullptr;
+  RFN_CUDA(cudaMallocAsync(&p, 2 * elems * sizeof(__nv_bfloat16), st));
+  *scratch = p;
+  __nv_bfloat16* Wb = (__nv_bfloat16*)p;
+  __nv_bfloat16* Wl = Wb + elems;
+  const long items = (long)Ng * 8 * (Kp / 8);
+  w_bf16_tiles_kernel<<<(unsigned)std::min<long>((items + 255) / 256, 4096), 256, 0, st>>>(W, ldw, N, K, Ng, Kp, Wb, Wl);
+  RFN_LAUNCH_CHECK();
+  for (int i = 0; i < 2; ++i)
+    RFN_TRY(tc_make_map_bf16_tiles(&t.tm_wb[i], i == 0 ? Wb : Wl, Ng, Kp));
+  return RFN_OK;
 }
 
 template <int EPI>

@@ -11,6 +11,9 @@ namespace rfn {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int gemm_mode();
+// tensor-engine pass count of an engine mode: 1 -> 3 (3xTF32), 2 -> 1 (single-pass TF32), 3 -> 2 (TF32 hi.hi + two BF16 cross
+// terms in the persistent kernel; 3xTF32 wherever another kernel runs)
+inline int tc_passes(int mode) { return mode == 1 ? 3 : (mode == 3 ? 2 : 1); }
 
 // kernel classes for the optional CUDA-event profile (rfn_profile_*)
 enum Tag {

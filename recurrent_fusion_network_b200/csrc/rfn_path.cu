@@ -142,7 +142,7 @@ static int attention_module(const rfn_dims& d, const float* h, int ldh, const fl
   if (gemm_mode() >= 1 && rows * N >= 128 && gemm_tc_supported(pa)) {
     {
       TagScope ts(tag_gemm);
-      RFN_TRY(gemm_tc(pa, gemm_mode() == 1 ? 3 : 1, g, A, v_w, P, N, st));
+      RFN_TRY(gemm_tc(pa, tc_passes(gemm_mode()), g, A, v_w, P, N, st));
     }
     TagScope ts(tag_attn);
     return attention_from_scores(Afeat, P, tc_score_slices(A), v_b, z, ldz, nullptr, rows, N, D, 1, st);
@@ -340,7 +340,7 @@ static int decoder_step(const rfn_dims& d, const float* const* prm, const float*
   if (logits) {
     GemmArgs la = gemm1(hout, R, prm[ix.logit(0)], prm[ix.logit(1)], R, logits, V, rows, V);
     if (fuse_topk > 0 && gemm_mode() >= 1 && rows >= 128 && gemm_tc_supported(la)) {
-      RFN_TRY(gemm_tc_vocab(la, gemm_mode() == 1 ? 3 : 1, w.st_max, w.st_sum, w.st_val, w.st_idx, fuse_topk, st));
+      RFN_TRY(gemm_tc_vocab(la, tc_passes(gemm_mode()), w.st_max, w.st_sum, w.st_val, w.st_idx, fuse_topk, st));
       RFN_TRY(vocab_merge(w.st_max, w.st_sum, w.st_val, w.st_idx, tc_score_slices(V), rows, fuse_topk, w.rowmax, w.logsum,
                           w.top_val, w.top_idx, st));
       if (fused) *fused = 1;

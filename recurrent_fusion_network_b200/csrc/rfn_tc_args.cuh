@@ -24,6 +24,11 @@ struct TcArgs {
   // 1-CTA store kernel only: W is given as (K, N) row-major (contraction index slow), i.e. the B operand is MN-major;
   // dX = dY . W reads nn.Linear weights (out, in) this way without a transposed copy
   int b_mn;
+  // persistent kernel only: the two cross terms of the split product run as BF16 MMAs (x_lo . w and x . w_lo with bf16
+  // operands written by the splitter) instead of TF32 MMAs: 8 instead of 12 tensor-core units per k-block, relative error
+  // ~1.3e-6 instead of ~4e-7 (engine mode 3)
+  int bf16x;
+  CUtensorMap tm_wb[2];   // bf16x: bf16(W) and bf16(W - trunc_tf32(W)) in the core-matrix-tiled layout written by w_bf16_tiles_kernel
   // fused attention-score epilogue (epi == 1)
   int epi;
   const float* g;   // (rows, ldg)   h_2_att_h(h)
@@ -45,5 +50,9 @@ struct TcArgs {
 // host helpers (rfn_gemm_tc.cu)
 // atom32: 128-byte swizzle with 32-byte atoms (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B), the layout an MN-major tf32 operand needs
 int tc_make_map(CUtensorMap* tm, const float* base, int rows, int K, int ld, int box_rows, bool atom32 = false);
+
+// 2-D bf16 map over the core-matrix-tiled W copy: rows = Ng groups of 8 W rows, Kp * 8 elements each; box = 256 x 16
+int tc_make_map_bf16_tiles(CUtensorMap* tm, const void* base, int Ng, int Kp);
+int tc2p_prepare_bf16_w(TcArgs& t, const float* W, int ldw, int N, int K, void** scratch, cudaStream_t st);
 
 }  // namespace rfn

@@ -145,6 +145,28 @@ __device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint64_t desc_a, uin
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// the same with BF16 operands (K = 16 per instruction); accumulates into the same fp32 TMEM tile as the tf32 MMAs
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// instruction descriptor: D fp32, A/B bf16, both K-major
+__host__ __device__ constexpr uint32_t make_idesc_bf16_m(int bm, int bn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(bm >> 4) << 24);
+}
+// K-major bf16 operand without swizzle ("interleaved" canonical layout): 8-row x 16-byte core matrices of 128 contiguous
+// bytes; the next core matrix along K is LBO = 128 bytes away, the next 8-row group SBO = 512 bytes away (a 128-row x
+// 32-element tile is 16 groups x 4 core matrices = 8 KB).  One bf16 MMA (K = 16) consumes two core matrices per group:
+// advance the start address by 256 bytes (16 units) per k-step.
+__device__ __forceinline__ uint64_t make_desc_bf16_interleaved(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (8ull << 16) | (32ull << 32) | (1ull << 46);
+}
 // commit: arrive on the mbarrier at this offset in BOTH CTAs once all prior MMAs of the pair retired
 __device__ __forceinline__ void umma2_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),

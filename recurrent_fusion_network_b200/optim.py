@@ -27,7 +27,8 @@ class FusedAdam(torch.optim.Optimizer):
     def _hyper(self, gi, group):
         if gi not in self._hyper_t:
             dev = group["params"][0].device
-            self._hyper_t[gi] = (torch.tensor([0.0, float(group["lr"])], dtype=torch.float32, device=dev),
+            steps = [int(self.state[p]["step"]) for p in group["params"] if self.state.get(p)]
+            self._hyper_t[gi] = (torch.tensor([float(max(steps, default=0)), float(group["lr"])], dtype=torch.float32, device=dev),
                                  torch.tensor([1.0, 0.0], dtype=torch.float32, device=dev))
         return self._hyper_t[gi]
 
@@ -43,6 +44,21 @@ class FusedAdam(torch.optim.Optimizer):
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
             if group.get("capturable"):
                 self._hyper(gi, group)
+
+    def state_dict(self):
+        """capturable mode: graph replays advance the update count on the device only; bring the host mirror up to date
+        before the state is saved (a checkpoint then resumes with the right bias correction)."""
+        for gi, group in enumerate(self.param_groups):
+            if gi in self._hyper_t:
+                step = int(self._hyper_t[gi][0][0].item())
+                for p in group["params"]:
+                    if self.state.get(p):
+                        self.state[p]["step"] = step
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._hyper_t = {}     # re-created from the loaded update count at the next step
 
     def sync_lr(self):
         """capturable mode: copy each group's lr to the device (call after misc/utils.set_lr)."""

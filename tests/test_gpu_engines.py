@@ -61,7 +61,7 @@ def test_strided_operands():
         assert maxdiff(got, want) <= tol * float(want.abs().max())
 
 
-@pytest.mark.parametrize("mode,tol", [(1, 2e-5), (2, 5e-3)])
+@pytest.mark.parametrize("mode,tol", [(1, 2e-5), (3, 2e-5), (2, 5e-3)])
 def test_stage1_with_fused_score_epilogue(mode, tol):
     """Full thought-vector pass with the tensor engine (fused tanh-score epilogue) vs the oracle."""
     from recurrent_fusion_network_b200 import _capi
@@ -122,7 +122,7 @@ def tc_cluster(request):
 
 @pytest.mark.parametrize("M,N,Ks", [(256, 256, [32]), (256, 512, [2048]), (1000, 2048, [2560, 1280]), (300, 9488, [512]),
                                     (777, 260, [36, 64, 128]), (20000, 768, [96])])
-@pytest.mark.parametrize("engine,tol", [(1, 3e-6), (2, 3e-3)])
+@pytest.mark.parametrize("engine,tol", [(1, 3e-6), (3, 4e-6), (2, 3e-3)])
 def test_two_cta_cluster_engine(tc_cluster, engine, tol, M, N, Ks):
     """cta_group::2 pairs (256 x 256 tiles, operands split across the two CTAs)."""
     g = torch.Generator().manual_seed(M + N)

@@ -181,6 +181,21 @@ def test_fused_adam_matches_clip_gradient_plus_torch_adam():
     oc.step(); od.step()
     for pc, pd in zip(c, d):
         assert maxdiff(pc, pd) <= 2e-6
+    # capturable mode: the update count lives on the device and survives a state_dict round trip
+    e = [torch.nn.Parameter(p.detach().clone()) for p in a[:3]]
+    oe = FusedAdam(e, lr=5e-4, capturable=True)
+    for _ in range(3):
+        for pe in e:
+            pe.grad = torch.ones_like(pe)
+        oe.step()
+    sd = oe.state_dict()
+    assert sd["state"][0]["step"] == 3
+    of = FusedAdam(e, lr=5e-4, capturable=True)
+    of.load_state_dict(sd)
+    for pe in e:
+        pe.grad = torch.ones_like(pe)
+    of.step()
+    assert float(of._hyper_t[0][0][0]) == 4.0
 
 
 def test_graphed_xe_step_matches_eager_steps():
