@@ -230,10 +230,12 @@ def run_ours(args):
                      unit="TFLOP/s", frac=round(tf / peaks["bf16_sustained"], 4),
                      traffic=1.718e9 if args.gemm_mode in (1, 3) else None,
                      traffic_note="ncu capture of one launch (resnet encoder, 1024 images, persistent 2-CTA kernel): 1.711 GB read "
-                                  "+ 0.007 GB written vs 1.648 GB algorithmic (A once + W once); tensor pipe 97.7 % active",
+                                  "+ 0.007 GB written vs 1.648 GB algorithmic (A once + W once); tensor pipe 97.7 % active in mode 1 "
+                                  "(profiles/r1_gemm_tc2p_score_ncu.txt), 69 % in mode 3 (bound by the x splitter; profiles/r1_gemm_tc2p_mode3_ncu.txt)",
                      mma_tflops_executed=round(tf * passes, 1),
                      frac_of_3xtf32_ceiling=(round(tf * passes / (peaks["bf16_burst"] / 2), 4) if args.gemm_mode >= 1 else None),
-                     ceiling_note="fp32-equivalent = 3 TF32 MMAs per product; TF32 peak taken as half the measured bf16 burst peak",
+                     ceiling_note=("fp32-equivalent = 1 TF32 + 2 BF16 MMAs per product = 2 TF32-MMA units (mode 3)" if args.gemm_mode == 3 else
+                                   "fp32-equivalent = 3 TF32 MMAs per product") + "; TF32 peak taken as half the measured bf16 burst peak",
                      launches=g_n, avg_launch_ms=round(g_ms / max(1, g_n), 4), share_of_step=shares.get("gemm_att2att_stage1"),
                      peak_source=peaks["source"] + ", dense bf16 sustained; this engine computes in " + args_dtype(args))
     roof_attn = dict(kernel="attention_step_stage1", bound="hbm", achieved=round(gbs, 1), peak=peaks["hbm"], unit="GB/s",
@@ -632,7 +634,7 @@ def main():
     ap.add_argument("--images", type=int, default=5000)
     ap.add_argument("--chunk", type=int, default=5000, help="images per device call when the features are resident")
     ap.add_argument("--e2e-chunk", type=int, default=500, help="images per device call when streaming host features")
-    ap.add_argument("--gemm-mode", type=int, default=int(os.environ.get("RFN_GEMM_MODE", "1")))
+    ap.add_argument("--gemm-mode", type=int, default=int(os.environ.get("RFN_GEMM_MODE", "3")))
     ap.add_argument("--train-steps", type=int, default=3, help="XE training steps timed for the secondary metric (0 = skip)")
     ap.add_argument("--cpu-images", type=int, default=24)
     ap.add_argument("--e2e-steps", type=int, default=2)

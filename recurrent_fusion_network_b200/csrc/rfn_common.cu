@@ -9,7 +9,7 @@
 namespace rfn {
 static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
-static std::atomic<int> g_gemm_mode{1};  // default: tcgen05 3xTF32 (fp32-equivalent)
+static std::atomic<int> g_gemm_mode{3};  // default: tcgen05 3xTF32, BF16 cross terms in the fused-epilogue GEMMs (fp32-grade)
 
 void set_error(const char* fmt, ...) {
   va_list ap;

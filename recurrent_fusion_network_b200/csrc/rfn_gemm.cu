@@ -13,7 +13,9 @@ int gemm_engine(const GemmArgs& a, int engine, cudaStream_t st) {
 
 int gemm(const GemmArgs& a, cudaStream_t st) {
   const int mode = gemm_mode();
-  if (mode >= 1 && a.M >= 128 && gemm_tc_supported(a)) return gemm_engine(a, mode, st);
+  // plain-store GEMMs of mode 3 stay on the 3xTF32 kernels (3-stage ring); its BF16 cross terms live in the persistent
+  // kernel, which the fused-epilogue GEMMs of the path use (and rfn_linear_f32_engine(3, ...) for the parity tests)
+  if (mode >= 1 && a.M >= 128 && gemm_tc_supported(a)) return gemm_engine(a, mode == 3 ? 1 : mode, st);
   if (mode >= 1 && a.splitk_ok && gemm_tc_supported(a)) {   // training: few rows, the weights are streamed once
     long wk = 0;
     for (int s = 0; s < a.nsrc; ++s) wk += a.src[s].K;
