@@ -82,13 +82,14 @@ class FusedAdam(torch.optim.Optimizer):
                     st["step"] = 0
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                st["step"] += 1     # host mirror; not advanced by graph replays
                 if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.grad.is_contiguous()):
                     raise RuntimeError("FusedAdam needs contiguous fp32 CUDA parameters and gradients")
             hyper = None
             if group.get("capturable"):
-                hyper, one = self._hyper(gi, group)
-                hyper.add_(one)                    # step += 1 on the device (captured with the graph)
+                hyper, one = self._hyper(gi, group)   # created from the update count BEFORE this step
+                hyper.add_(one)                        # step += 1 on the device (captured with the graph)
+            for p in ps:
+                self.state[p]["step"] += 1             # host mirror; not advanced by graph replays
             step = self.state[ps[0]]["step"]
             n = len(ps)
             numel = (C.c_int64 * n)(*[p.numel() for p in ps])
