@@ -412,6 +412,18 @@ __global__ void __launch_bounds__(256) w_bf16_tiles_kernel(const float* __restri
 int tc2p_prepare_bf16_w(TcArgs& t, const float* W, int ldw, int N, int K, void** scratch, cudaStream_t st) {
   const int Ng = (N + 7) / 8, Kp = (K + TC_BK - 1) / TC_BK * TC_BK;
   const size_t elems = (size_t)Ng * 8 * Kp;
+  // keep freed scratch in the device's default stream-ordered pool (its default release threshold of 0 hands the memory
+  // back to the driver at every synchronisation, which would make each cudaMallocAsync below a real allocation)
+  static bool pool_ready[64] = {};
+  int dev = 0;
+  RFN_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !pool_ready[dev]) {
+    cudaMemPool_t pool;
+    RFN_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    uint64_t keep = UINT64_MAX;
+    RFN_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    pool_ready[dev] = true;
+  }
   void* p = nullptr;
   RFN_CUDA(cudaMallocAsync(&p, 2 * elems * sizeof(__nv_bfloat16), st));
   *scratch = p;
