@@ -38,8 +38,12 @@ def _worker(rank, world, port, n_images, out_q):
     p = torch.nn.Parameter(torch.zeros(5))
     p.grad = torch.tensor([4.0, -4.0, 0.5, 1.0, 3.0]) * (rank + 1)
     D.average_gradients([p], grad_clip=1.0, bucket_bytes=8)
+    # divide=False: the SUM is left for FusedAdam(grad_scale=1/world), which divides and clamps in the optimizer pass
+    q = torch.nn.Parameter(torch.zeros(3))
+    q.grad = torch.tensor([1.0, -2.0, 0.25]) * (rank + 1)
+    D.average_gradients([q], divide=False)
     if rank == 0:
-        out_q.put((seq, slp, p.grad.clone()))
+        out_q.put((seq, slp, p.grad.clone(), q.grad.clone()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -52,7 +56,7 @@ def test_sharded_decode_equals_single_process(n_images):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, n_images, q)) for r in range(2)]
     for p in procs:
         p.start()
-    seq, slp, grad = q.get(timeout=120)
+    seq, slp, grad, grad_sum = q.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -64,6 +68,7 @@ def test_sharded_decode_equals_single_process(n_images):
     assert torch.equal(slp, want_slp)
     # mean of (g, 2g) = 1.5 g, clamped to +-1 afterwards
     assert torch.allclose(grad, (torch.tensor([4.0, -4.0, 0.5, 1.0, 3.0]) * 1.5).clamp(-1, 1))
+    assert torch.allclose(grad_sum, torch.tensor([1.0, -2.0, 0.25]) * 3)
 
 
 def test_shard_range_covers_everything():
