@@ -3,13 +3,15 @@
 // mainloop.  The per-tile timeline of the one-tile-per-cluster kernel (rfn_gemm_tc2.cu) showed 15 % of an
 // att_2_att_h tile and ~60 % of a K = 512 logits tile outside the tensor-bound mainloop.
 //
-// Roles per CTA (384 threads):
+// Roles per CTA (512 threads = 4 warpgroups; setmaxnreg moves registers from warpgroups 0 and 3 (72 each) to the drain
+// warpgroups 1 and 2 (184 each)):
 //   warp 0        TMA producer: runs ahead through the tiles, bounded only by the stage ring
 //   warp 1        MMA issuer (leader CTA): alternates the two TMEM accumulators per chunk ACROSS tiles, so it can
 //                 be two chunks (8 k-blocks) into the next tile while the previous tile's epilogue runs
-//   warps 2..3    3xTF32 splitters (lo = x - trunc_tf32(x)), never blocked by an epilogue
+//   warps 2..3    splitters (3xTF32: lo = x - trunc_tf32(x); mode 3: bf16(x), bf16(x_lo)), never blocked by an epilogue
 //   warps 4..11   drain + epilogue: round-to-nearest accumulation of the finished chunks in registers, then the
 //                 store / attention-score / vocabulary epilogue of the tile
+//   warps 12..15  four more splitter warps in engine mode 3 (idle in 3xTF32 mode), where the x split bounds the kernel
 // Tiles are assigned round-robin (tile = cluster, cluster + #clusters, ...) with the n-tile index fastest, so
 // every role derives the same sequence without communication.
 #include <cuda.h>
@@ -23,7 +25,7 @@
 
 namespace rfn {
 
-constexpr int TP_THREADS = 384;
+constexpr int TP_THREADS = 512;   // 4 warpgroups: {TMA, MMA, 2 splitters}, 2 x drain, {4 more splitters (mode 3)}
 constexpr int TP_BN = 256;
 constexpr int TP_BH = TP_BN / 2;
 constexpr int TP_TILE_BYTES = TC_A_BYTES + TP_BH * 128;   // 32 KB landed per CTA per k-block
@@ -71,7 +73,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) gemm_tc2p_kernel(const __grid_c
     for (int s = 0; s < a.nsrc; ++s) { tma_prefetch_desc(&a.tm_x[s]); tma_prefetch_desc(&a.tm_w[s]); }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(&full[s]), 1);
-      mbar_init(smem_u32(&ready[s]), 4);      // 2 splitter warps x 2 CTAs
+      mbar_init(smem_u32(&ready[s]), a.bf16x ? 12 : 4);   // splitter warps x 2 CTAs (mode 3: warps 2, 3 and 12..15)
       mbar_init(smem_u32(&empty[s]), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -87,6 +89,10 @@ __global__ void __launch_bounds__(TP_THREADS, 1) gemm_tc2p_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // 512 threads start with 128 registers each; the drain / epilogue warpgroups hold a 128-column fp32 tile per thread and
+  // take 184, the producer / MMA / splitter warpgroups keep 72 (128 x (72 + 72 + 184 + 184) = 65,536)
+  if (warp < 4 || warp >= 12) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -167,11 +173,12 @@ __global__ void __launch_bounds__(TP_THREADS, 1) gemm_tc2p_kernel(const __grid_c
         }
       }
     }
-  } else if (warp < 4) {
-    // ===================== 3xTF32 splitters (64 threads) =====================
-    const int t = threadIdx.x - 64;
+  } else {
+    // ===================== splitters: warps 2, 3 (both modes) and 12..15 (mode 3 only) =====================
+    const int t = (warp < 4) ? (int)threadIdx.x - 64 : 64 + ((int)threadIdx.x - 384);
     int it = 0;
-    for (int tile = cluster; tile < total_tiles; tile += n_clusters) {
+    const int first_tile = (warp >= 12 && !a.bf16x) ? total_tiles : cluster;   // the extra warpgroup idles in 3xTF32 mode
+    for (int tile = first_tile; tile < total_tiles; tile += n_clusters) {
       for (int kb = 0; kb < total_kb; ++kb, ++it) {
         const int st = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
@@ -184,8 +191,8 @@ __global__ void __launch_bounds__(TP_THREADS, 1) gemm_tc2p_kernel(const __grid_c
           uint8_t* base = smem + st * TP_STAGE_BYTES + TP_TILE_BYTES;
           // rows fastest across the lanes: a quarter-warp reads 8 distinct swizzled chunks and writes one whole 128-byte
           // core matrix (both bank-conflict free)
-#pragma unroll 8
-          for (int i = t; i < 128 * 4; i += 64) {
+#pragma unroll 3
+          for (int i = t; i < 128 * 4; i += 192) {
             const int r = i & 127, c = i >> 7;
             const uint4* row = hi + r * 8;
             const uint4 v0 = row[(2 * c) ^ (r & 7)], v1 = row[(2 * c + 1) ^ (r & 7)];
@@ -223,7 +230,9 @@ __global__ void __launch_bounds__(TP_THREADS, 1) gemm_tc2p_kernel(const __grid_c
         }
       }
     }
+  }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
     // ===================== drain + epilogue (256 threads) =====================
     const int wq = warp & 3;
     const int ew = warp - 4;                   // 0..7
