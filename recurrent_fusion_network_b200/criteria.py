@@ -3,7 +3,6 @@
 Without autograd (evaluation) the sequence terms run in the fused reduction kernels, which need only
 lp[y], sum_v lp_v and sum_v p log p per (row, t) -- the reference materialises a (rows,T,V) one-hot.
 With autograd enabled the same math runs through recurrent_fusion_network_b200.training."""
-import ctypes as C
 
 import torch
 import torch.nn as nn

@@ -8,7 +8,7 @@ import torch
 
 from . import _capi
 from ._capi import check, lib, ptr, ptr_array, stream
-from .model import _WS, _f32c
+from .model import _WS
 
 
 def model_ensemble_feat_array_one_step(model_list, xt_list, state_list, thought_vector_list):

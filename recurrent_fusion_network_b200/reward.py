@@ -6,7 +6,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
-from collections import OrderedDict, defaultdict
+from collections import defaultdict
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
