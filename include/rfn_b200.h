@@ -65,6 +65,11 @@ int rfn_check_device(void);
 int rfn_num_params(const rfn_dims* dims);
 /* number of kernels this library has launched in the calling process (bench accounting) */
 uint64_t rfn_launch_count(void);
+/* launches per GEMM kernel family since the process started (rfn_engine_num() families, named by rfn_engine_name()):
+ * the tests and smoke() use it to prove WHICH kernel instantiation a configuration actually ran */
+int rfn_engine_num(void);
+const char* rfn_engine_name(int engine);
+int rfn_engine_launch_counts(uint64_t* out, int n);
 /* selects the contraction engine for GEMMs with >= 128 rows: 0 = fp32 SIMT FMA; 1 = tcgen05 3xTF32 with chunked
  * round-to-nearest accumulation (fp32-equivalent); 2 = tcgen05 single-pass TF32 (reduced precision); 3 (the default) =
  * mode 1, except that the two fused-epilogue GEMMs of the path (attention projection, logits) compute the cross terms
@@ -113,6 +118,20 @@ int rfn_linear_f32(int n_src, const float* const* x, const int* ldx, const float
 int rfn_linear_f32_engine(int engine, int n_src, const float* const* x, const int* ldx,
                           const float* const* W, const int* K, const float* const* bias, float* y,
                           int ldy, int M, int N, int accumulate, rfn_stream_t stream);
+
+/* Split-fp16 tensor engine (engine mode 4, the default; mode 5 = its single-pass bf16 sibling), operator level.
+ * rfn_split_rows_f32 turns fp32 rows (n_src matrices that share the row index, e.g. the concatenated inputs H | z of
+ * H2h(H) + z2h(z), misc/RecurrentFusionModel.py:53, or the rows of their weight matrices) into a power-of-two row scale
+ * and two fp16 pieces per element, x = (x0 + x1) / s with 22 mantissa bits (bf16 != 0: one bf16 piece, no scale);
+ * `out` needs rfn_split_bytes(rows, n_src, K, bf16) bytes.  rfn_linear_split then computes the same contraction as
+ * rfn_linear_f32 from two such buffers (x: M rows, W: N rows) as x0.w0 + x1.w0 + x0.w1 on the tcgen05 tensor cores
+ * (three kind::f16 MMAs per product, fp32 accumulation drained into round-to-nearest registers); M, N >= 256. */
+size_t rfn_split_bytes(int rows, int n_src, const int* K, int bf16);
+int rfn_split_rows_f32(int n_src, const float* const* x, const int* ldx, const int* K, int rows, int bf16,
+                       void* out, size_t out_bytes, rfn_stream_t stream);
+int rfn_linear_split(int bf16, int n_src, const void* x_split, const void* w_split, const int* K,
+                     const float* const* bias, float* y, int ldy, int M, int N, int accumulate,
+                     rfn_stream_t stream);
 
 /* Additive soft attention given P = att_2_att_h(A) (misc/AttentionModelCore.py:36-47):
  *   e[r,n] = w . tanh(P[r/div, n, :] + g[r, :]) + wb ; a = softmax_n(e) ; z[r,:] = sum_n a[r,n] A[r/div,n,:]

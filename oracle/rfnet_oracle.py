@@ -398,10 +398,13 @@ def _topk_desc(lp: Tensor, k: int):
 
 
 def beam_merge(beam: int, t: int, L: int, ys: Tensor, ix: Tensor, beam_seq: Tensor,
-               beam_lp: Tensor, beam_sum: Tensor, done: list):
+               beam_lp: Tensor, beam_sum: Tensor, done: list, margins: Optional[list] = None):
     """One beam merge step (:465-514) on CPU tensors.  ys/ix: (beam, >=beam) sorted top logprobs.
     Mutates beam_seq (L,beam) i64, beam_lp (L,beam) f32, beam_sum (beam,) f32, appends to done.
-    Returns the list of source beams q per new slot, or None when no candidate is live (:480)."""
+    Returns the list of source beams q per new slot, or None when no candidate is live (:480).
+    ``margins`` (near-tie policy): receives this step's decision margin = the smallest
+    gap between neighbours among the first beam+1 sorted candidates, i.e. by how much a candidate
+    sum would have to move to change which beams survive or in which slot order."""
     cand = []
     rows = 1 if t == 1 else beam                                                  # :468-469
     for c in range(min(beam, ys.shape[1])):                                       # c OUTER :470
@@ -414,6 +417,9 @@ def beam_merge(beam: int, t: int, L: int, ys: Tensor, ix: Tensor, beam_seq: Tens
     if not cand:
         return None
     cand.sort(key=lambda v: -v[2])                                                # stable :482
+    if margins is not None:
+        top = [v[2] for v in cand[:beam + 1]]
+        margins.append(min([a - b for a, b in zip(top, top[1:])], default=float("inf")))
     prev_seq = beam_seq[:t - 1].clone()
     prev_lp = beam_lp[:t - 1].clone()
     src = []
@@ -433,11 +439,12 @@ def beam_merge(beam: int, t: int, L: int, ys: Tensor, ix: Tensor, beam_seq: Tens
 
 
 def sample_beam(sd: StateDict, cfg: RFNConfig, fc, att, beam_size: int = 3,
-                logit_fn=None):
+                logit_fn=None, margins_out: Optional[list] = None):
     """Per image, serial, ``beam_size`` identical rows -- the reference's own batching, kept
     because the reference is not batch-invariant.
     Returns (seq (B,L) i64, seqLogprobs (B,L) f32, top_seq list[(n_done,L)], top_prob list[list],
-    reason_pred_batch)."""
+    reason_pred_batch).  ``margins_out`` receives one dict per image: ``steps`` = the merge decision
+    margin of every step (see beam_merge) and ``final`` = best minus second-best finished beam."""
     B = fc[0].shape[0]
     L = cfg.seq_length
     assert beam_size <= cfg.V1                                                    # :360
@@ -454,13 +461,14 @@ def sample_beam(sd: StateDict, cfg: RFNConfig, fc, att, beam_size: int = 3,
         beam_lp = torch.zeros(L, beam_size, dtype=torch.float32)
         beam_sum = torch.zeros(beam_size, dtype=torch.float32)
         done: list = []
+        step_margins: list = []
         lp = None
         for t in range(L + 1):
             if t == 0:
                 it = torch.zeros(beam_size, dtype=torch.int64)                    # :453
             else:
                 ys, ix = _topk_desc(lp, beam_size)
-                src = beam_merge(beam_size, t, L, ys, ix, beam_seq, beam_lp, beam_sum, done)
+                src = beam_merge(beam_size, t, L, ys, ix, beam_seq, beam_lp, beam_sum, done, step_margins)
                 if src is None:
                     break
                 idx = torch.tensor(src, dtype=torch.int64)
@@ -479,6 +487,9 @@ def sample_beam(sd: StateDict, cfg: RFNConfig, fc, att, beam_size: int = 3,
         top_seq.append(torch.stack([d["seq"] for d in done], 0))
         top_prob.append([d["p"] for d in done])
         all_done.append(done)
+        if margins_out is not None:
+            margins_out.append({"steps": step_margins,
+                                "final": done[0]["p"] - done[1]["p"] if len(done) > 1 else float("inf")})
     return seq.t().contiguous(), seq_lp.t().contiguous(), top_seq, top_prob, reason_batch
 
 

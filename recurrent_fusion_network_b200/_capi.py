@@ -48,6 +48,9 @@ _SIGNATURES = {
     "rfn_check_device": (_i, []),
     "rfn_num_params": (_i, [_dims]),
     "rfn_launch_count": (C.c_uint64, []),
+    "rfn_engine_num": (_i, []),
+    "rfn_engine_name": (C.c_char_p, [_i]),
+    "rfn_engine_launch_counts": (_i, [C.POINTER(C.c_uint64), _i]),
     "rfn_set_gemm_mode": (_i, [_i]),
     "rfn_get_gemm_mode": (_i, []),
     "rfn_set_tc_cluster": (_i, [_i]),
@@ -60,6 +63,9 @@ _SIGNATURES = {
     "rfn_profile_read": (_i, [C.POINTER(C.c_float), C.POINTER(C.c_uint64), _i]),
     "rfn_linear_f32": (_i, [_i, _pp, C.POINTER(_i), _pp, C.POINTER(_i), _pp, _vp, _i, _i, _i, _i, _vp]),
     "rfn_linear_f32_engine": (_i, [_i, _i, _pp, C.POINTER(_i), _pp, C.POINTER(_i), _pp, _vp, _i, _i, _i, _i, _vp]),
+    "rfn_split_bytes": (_sz, [_i, _i, C.POINTER(_i), _i]),
+    "rfn_split_rows_f32": (_i, [_i, _pp, C.POINTER(_i), C.POINTER(_i), _i, _i, _vp, _sz, _vp]),
+    "rfn_linear_split": (_i, [_i, _i, _vp, _vp, C.POINTER(_i), _pp, _vp, _i, _i, _i, _i, _vp]),
     "rfn_attention_step_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
     "rfn_attention_core_f32": (_i, [_vp] * 10 + [_i] * 5 + [_vp, _sz, _vp]),
     "rfn_lstm_cell_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
@@ -175,6 +181,14 @@ def make_dims(encoders, rnn_size, att_hid_size, input_encoding_size, vocab_plus1
     d.vocab_plus1, d.top_words_count = vocab_plus1, top_words_count
     d.num_review_steps_0, d.num_review_steps, d.seq_length = num_review_steps_0, num_review_steps, seq_length
     return d
+
+
+def engine_launch_counts():
+    """-> {GEMM kernel family: launches since the process started}."""
+    n = lib().rfn_engine_num()
+    cnt = (C.c_uint64 * n)()
+    check(lib().rfn_engine_launch_counts(cnt, n), "rfn_engine_launch_counts")
+    return {lib().rfn_engine_name(i).decode(): int(cnt[i]) for i in range(n)}
 
 
 def profile_enable(on: bool) -> None:

@@ -43,8 +43,10 @@ class ReviewNetEnsembleCriterion(nn.Module):
             return training.xe_criterion(self, log_prob, target, mask, top_pred, top_true, reason_weight)
         log_prob = _f32c(log_prob)
         rows, T, V = log_prob.shape
-        target = target.to(torch.int64).contiguous()
-        mask = _f32c(mask)
+        # the reference truncates target and mask to log_prob.size(1) separately (misc/utils.py:163-164), so their widths
+        # may differ: slice before making them contiguous (the kernel addresses both with one leading dimension)
+        target = target[:, :T].to(torch.int64).contiguous()
+        mask = _f32c(mask[:, :T])
         out = torch.zeros(1, dtype=torch.float32, device=log_prob.device)
         eps = float(self.label_smoothing_epsilon) if self.use_label_smoothing else 0.0
         check(lib().rfn_xe_loss_f32(ptr(log_prob), ptr(target), ptr(mask), target.stride(0), rows, T, V, eps, ptr(out),

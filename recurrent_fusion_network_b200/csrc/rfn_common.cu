@@ -18,6 +18,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+static std::atomic<uint64_t> g_engine_launches[ENG_COUNT];
+void count_engine(int engine) {
+  if (engine >= 0 && engine < ENG_COUNT) g_engine_launches[engine].fetch_add(1, std::memory_order_relaxed);
+}
 int gemm_mode() { return g_gemm_mode.load(std::memory_order_relaxed); }
 
 // ---- optional per-kernel-class timing with CUDA events on the launching stream -------------------
@@ -60,6 +64,19 @@ extern "C" {
 const char* rfn_last_error(void) { return rfn::g_err; }
 int rfn_version(void) { return 100; }
 uint64_t rfn_launch_count(void) { return rfn::g_launches.load(); }
+int rfn_engine_num(void) { return rfn::ENG_COUNT; }
+const char* rfn_engine_name(int e) {
+  static const char* names[rfn::ENG_COUNT] = {"simt_skinny", "simt_tiled", "tcgen05_1cta", "tcgen05_1cta_splitk", "tcgen05_2cta",
+                                              "tcgen05_2cta_persistent_store", "tcgen05_2cta_persistent_score",
+                                              "tcgen05_2cta_persistent_vocab", "tcgen05_2cta_persistent_fp16x3",
+                                              "tcgen05_2cta_persistent_bf16"};
+  return (e >= 0 && e < rfn::ENG_COUNT) ? names[e] : "?";
+}
+int rfn_engine_launch_counts(uint64_t* out, int n) {
+  RFN_CHECK_ARG(out && n >= rfn::ENG_COUNT, "rfn_engine_launch_counts: need %d slots", rfn::ENG_COUNT);
+  for (int i = 0; i < rfn::ENG_COUNT; ++i) out[i] = rfn::g_engine_launches[i].load();
+  return RFN_OK;
+}
 
 int rfn_check_device(void) {
   int dev = 0;
@@ -75,7 +92,7 @@ int rfn_check_device(void) {
 }
 
 int rfn_set_gemm_mode(int mode) {
-  RFN_CHECK_ARG(mode >= 0 && mode <= 3, "gemm mode %d not in {0,1,2,3}", mode);
+  RFN_CHECK_ARG(mode >= 0 && mode <= 5, "gemm mode %d not in 0..5", mode);
   rfn::g_gemm_mode.store(mode);
   return RFN_OK;
 }
@@ -89,7 +106,8 @@ int rfn_profile_num_tags(void) { return rfn::TAG_COUNT; }
 const char* rfn_profile_tag_name(int tag) {
   static const char* names[rfn::TAG_COUNT] = {"misc", "gemm_att2att_stage1", "attention_step_stage1", "gemm_gates",
                                               "gemm_logit", "gemm_other", "attention_step_small", "lstm_cell",
-                                              "vocab_stats_select", "beam_merge", "gemm_backward", "attention_backward"};
+                                              "vocab_stats_select", "beam_merge", "gemm_backward", "attention_backward",
+                                              "operand_split"};
   return (tag >= 0 && tag < rfn::TAG_COUNT) ? names[tag] : "?";
 }
 int rfn_profile_read(float* ms, uint64_t* launches, int n) {

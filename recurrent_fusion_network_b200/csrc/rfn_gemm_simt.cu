@@ -198,6 +198,7 @@ static int launch_skinny(const GemmArgs& a, cudaStream_t st) {
   }
   gemm_skinny_kernel<MMAX><<<(a.N + SK_WARPS - 1) / SK_WARPS, SK_WARPS * 32, smem, st>>>(a);
   RFN_LAUNCH_CHECK();
+  count_engine(ENG_SIMT_SKINNY);
   return RFN_OK;
 }
 
@@ -227,6 +228,7 @@ int gemm_simt(const GemmArgs& a, cudaStream_t st) {
     }
     return RFN_OK;
   }
+  count_engine(ENG_SIMT_TILED);
   if (a.M <= 64) {
     dim3 grid((a.N + 63) / 64, (a.M + 63) / 64);
     gemm_tn_simt_kernel<64, 64, 4, 4><<<grid, 256, 0, st>>>(a);

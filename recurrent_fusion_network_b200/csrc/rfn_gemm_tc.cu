@@ -389,6 +389,7 @@ static int launch_tc_epi(const TcArgs& t, cudaStream_t st) {
   dim3 grid((t.N + BN - 1) / BN, (t.M + TC_BM - 1) / TC_BM, (EPI == 0 && t.ksplit > 1) ? t.ksplit : 1);
   gemm_tc_kernel<BN, STAGES, PASSES, CH, EPI><<<grid, TC_THREADS, smem, st>>>(t);
   RFN_LAUNCH_CHECK();
+  count_engine(t.ksplit > 1 ? ENG_TC1_SPLITK : ENG_TC1);
   return RFN_OK;
 }
 

@@ -320,6 +320,7 @@ static int launch_tc2_epi(const TcArgs& t, cudaStream_t st) {
   cfg.numAttrs = 1;
   RFN_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<STAGES, PASSES, CH, EPI>, t, n_tiles));
   RFN_LAUNCH_CHECK();
+  count_engine(ENG_TC2);
   return RFN_OK;
 }
 

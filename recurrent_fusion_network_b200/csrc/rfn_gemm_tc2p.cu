@@ -476,6 +476,7 @@ static int launch_tc2p_epi(const TcArgs& t, cudaStream_t st) {
   cfg.numAttrs = 1;
   RFN_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2p_kernel<EPI>, t, n_tiles, total));
   RFN_LAUNCH_CHECK();
+  count_engine(EPI == 0 ? ENG_TC2P_STORE : (EPI == 1 ? ENG_TC2P_SCORE : ENG_TC2P_VOCAB));
   return RFN_OK;
 }
 

@@ -10,15 +10,24 @@ namespace rfn {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+// per-engine launch accounting (rfn_engine_launch_counts): which GEMM kernel family actually ran
+enum Engine {
+  ENG_SIMT_SKINNY = 0, ENG_SIMT_TILED = 1, ENG_TC1 = 2, ENG_TC1_SPLITK = 3, ENG_TC2 = 4, ENG_TC2P_STORE = 5,
+  ENG_TC2P_SCORE = 6, ENG_TC2P_VOCAB = 7, ENG_H3 = 8, ENG_BF16 = 9, ENG_COUNT = 10
+};
+void count_engine(int engine);
 int gemm_mode();
 // tensor-engine pass count of an engine mode: 1 -> 3 (3xTF32), 2 -> 1 (single-pass TF32), 3 -> 2 (TF32 hi.hi + two BF16 cross
 // terms in the persistent kernel; 3xTF32 wherever another kernel runs)
-inline int tc_passes(int mode) { return mode == 1 ? 3 : (mode == 3 ? 2 : 1); }
+// modes 4 (split fp16, rfn_h3.cuh) and 5 (single-pass bf16) have their own engine; GEMMs too small for it fall back to
+// 3xTF32 (mode 4) / single-pass TF32 (mode 5)
+inline int tc_passes(int mode) { return (mode == 1 || mode == 4) ? 3 : (mode == 3 ? 2 : 1); }
 
 // kernel classes for the optional CUDA-event profile (rfn_profile_*)
 enum Tag {
   TAG_MISC = 0, TAG_GEMM_ATT2ATT = 1, TAG_ATTN_S1 = 2, TAG_GEMM_GATES = 3, TAG_GEMM_LOGIT = 4, TAG_GEMM_OTHER = 5,
-  TAG_ATTN_SMALL = 6, TAG_CELL = 7, TAG_VOCAB = 8, TAG_BEAM = 9, TAG_GEMM_BWD = 10, TAG_ATTN_BWD = 11, TAG_COUNT = 12
+  TAG_ATTN_SMALL = 6, TAG_CELL = 7, TAG_VOCAB = 8, TAG_BEAM = 9, TAG_GEMM_BWD = 10, TAG_ATTN_BWD = 11, TAG_SPLIT = 12,
+  TAG_COUNT = 13
 };
 bool prof_enabled();
 struct TagScope {  // call-site override of a launcher's default class

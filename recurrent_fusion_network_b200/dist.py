@@ -54,22 +54,25 @@ def sharded_decode(decode: Callable, fc_feats: Sequence[torch.Tensor], att_feats
         seq, slp = decode([f[k0:k1] for f in fc_feats], [a[k0:k1] for a in att_feats])
     else:
         seq = slp = None
+    # greedy / multinomial decodes return seq[:, :T] with a rank-dependent T (the early break of
+    # misc/RecurrentFusionModel.py:645): every rank pads to the widest shard before the gather
+    L = _max_width(0 if seq is None else seq.shape[1], group)
     if seq is None:  # empty shard: contribute zero rows of the right width
-        L = _broadcast_width(None, group)
         dev = device or torch.device("cpu")
         seq = torch.zeros(0, L, dtype=torch.int64, device=dev)
         slp = torch.zeros(0, L, dtype=torch.float32, device=dev)
-    else:
-        _broadcast_width(seq.shape[1], group)
+    elif seq.shape[1] < L:
+        seq = torch.nn.functional.pad(seq, (0, L - seq.shape[1]))
+        slp = torch.nn.functional.pad(slp, (0, L - slp.shape[1]))
     return gather_captions(seq, slp, n_total, group)
 
 
-def _broadcast_width(L, group):
+def _max_width(L, group):
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return L
-    objs = [L if dist.get_rank(group) == 0 else None]
-    dist.broadcast_object_list(objs, src=0, group=group)
-    return objs[0]
+    objs = [None] * dist.get_world_size(group)
+    dist.all_gather_object(objs, int(L), group=group)
+    return max(objs)
 
 
 def average_gradients(params: Iterable[torch.nn.Parameter], group=None, bucket_bytes: int = 256 << 20,
@@ -79,6 +82,7 @@ def average_gradients(params: Iterable[torch.nn.Parameter], group=None, bucket_b
     NCCL: the gradient tensors are reduced IN PLACE as coalesced groups (one ncclGroup per <= 256 tensors): no
     flatten / copy-back passes over HBM.  divide=False leaves the SUM for FusedAdam(grad_scale=1/world), which folds the
     division (and the clamp) into the optimizer pass.  Other backends (gloo in the CPU tests): flat buckets."""
+    params = list(params)   # iterated more than once below: a generator (model.parameters()) must not be exhausted
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         if grad_clip is not None:
             for p in params:

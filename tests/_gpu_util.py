@@ -48,3 +48,21 @@ def assert_tokens_match_with_tie_policy(got, want, oracle_lp_all, what, margin=1
         assert m < margin, f"{what}: row {r} diverges at t={t} with oracle margin {m:.3g}"
         ties += 1
     return ties
+
+
+def assert_beam_match_with_tie_policy(got_seq, got_lp, want_seq, want_lp, margins, what, margin=1e-5, lp_tol=LP_TOL):
+    """Beam captions: exact token match per image; an image whose caption differs is excused only when the
+    ORACLE's own search had a decision (a merge step or the final ranking of the finished beams) whose margin is
+    < `margin` (oracle.sample_beam(margins_out=...)).  Log-probs of equal captions must agree
+    to `lp_tol`.  Returns the number of tie-broken images."""
+    got_seq, got_lp = got_seq.cpu(), got_lp.cpu()
+    ties = 0
+    for k in range(want_seq.shape[0]):
+        if torch.equal(got_seq[k], want_seq[k]):
+            d = float((got_lp[k] - want_lp[k]).abs().max())
+            assert d <= lp_tol, f"{what}: image {k} log-probs differ by {d:.3g}"
+            continue
+        m = min(min(margins[k]["steps"], default=float("inf")), margins[k]["final"])
+        assert m < margin, f"{what}: image {k} caption differs and the oracle's smallest decision margin is {m:.3g}"
+        ties += 1
+    return ties

@@ -269,3 +269,82 @@ def test_general_gemm_dx_on_tensor_engine(M, N, K):
             _gemm_general(1, 0, dY, K, W, N, y, N, M, N, K, accumulate=acc)
             assert maxdiff(y, want + (y0.double() if acc else 0)) <= 3e-6 * scale, (mode, acc)
     _capi.check(_capi.lib().rfn_set_gemm_mode(1))
+
+
+# ---- split-fp16 ("fp16x3", engine 4) and single-pass bf16 (engine 5) ------------------------------------------------
+H3_SHAPES = [(256, 256, [64]), (256, 512, [2048]), (1000, 2048, [2560, 1280]), (300, 9488, [512]), (777, 260, [36, 64, 128]),
+             (20000, 768, [96]), (5000, 512, [2208]), (513, 516, [100])]
+
+
+@pytest.mark.parametrize("M,N,Ks", H3_SHAPES)
+@pytest.mark.parametrize("engine,tol", [(4, 3e-6), (5, 2e-2)])
+def test_split_fp16_engine_matches_fp64(engine, tol, M, N, Ks):
+    """rfn_linear_f32_engine(4 | 5): operands split into scaled fp16 pairs (or bf16), x0.w0 + x1.w0 + x0.w1 on kind::f16 MMAs."""
+    g = torch.Generator().manual_seed(M + N)
+    xs = [torch.randn(M, k, generator=g) for k in Ks]
+    ws = [(torch.rand(N, k, generator=g) * 2 - 1) * 0.1 for k in Ks]
+    bs = [torch.randn(N, generator=g) for _ in Ks]
+    want = sum(x.double() @ w.double().t() + b.double() for x, w, b in zip(xs, ws, bs))
+    got = _linear_engine(engine, cuda_list(xs), cuda_list(ws), cuda_list(bs), M, N)
+    torch.cuda.synchronize()
+    scale = float(want.abs().max())
+    err = maxdiff(got, want)
+    assert err <= tol * scale, f"engine {engine}: err {err:.3g} vs scale {scale:.3g}"
+    if engine == 4:
+        ref = _linear_engine(0, cuda_list(xs), cuda_list(ws), cuda_list(bs), M, N)
+        assert err <= 4 * maxdiff(ref, want) + 1e-6 * scale          # as good as the fp32 FFMA engine
+        acc = _linear_engine(engine, cuda_list(xs), cuda_list(ws), cuda_list(bs), M, N, accumulate_into=ref.clone())
+        assert maxdiff(acc, 2 * want) <= 2 * tol * scale
+
+
+def test_split_fp16_engine_row_scaling():
+    """Rows of x and of W whose magnitudes span 2^-40 .. 2^+40 (and all-zero rows): the power-of-two row scales keep every
+    output row at fp32-grade accuracy RELATIVE TO ITS OWN SCALE -- an unscaled fp16 split would flush the small rows."""
+    g = torch.Generator().manual_seed(5)
+    M, N, K = 512, 384, 520
+    x = torch.randn(M, K, generator=g) * torch.pow(2.0, torch.randint(-40, 41, (M, 1), generator=g).float())
+    w = torch.randn(N, K, generator=g) * torch.pow(2.0, torch.randint(-30, 31, (N, 1), generator=g).float())
+    x[7] = 0
+    w[11] = 0
+    b = torch.zeros(N)
+    want = x.double() @ w.double().t()
+    got = _linear_engine(4, [x.cuda()], [w.cuda()], [b.cuda()], M, N).double().cpu()
+    ref = (x.abs().double() @ w.abs().double().t()) + 1e-300        # per-element scale of the dot product
+    rel = ((got - want).abs() / ref).max()
+    assert float(rel) <= 1e-6, float(rel)
+    assert float(got[7].abs().max()) == 0.0 and float(got[:, 11].abs().max()) == 0.0
+
+
+def test_split_operator_api_and_bf16():
+    """rfn_split_rows_f32 + rfn_linear_split (the pre-split operator API the path uses: features split once, reused by the
+    eight fusion steps); pieces reconstruct x to 2^-22 relative to the row maximum; bf16 flavour within bf16 rounding."""
+    from recurrent_fusion_network_b200._capi import check, lib, ptr, ptr_array, stream
+    g = torch.Generator().manual_seed(2)
+    M, N, K = 640, 512, 264
+    x = torch.randn(M, K, generator=g).cuda() * 3
+    w = ((torch.rand(N, K, generator=g) * 2 - 1) * 0.1).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    want = x.double() @ w.double().t() + bias.double()
+    for bf16, tol in ((0, 3e-6), (1, 2e-2)):
+        ks = (C.c_int * 1)(K)
+        bufs = []
+        for t, rows in ((x, M), (w, N)):
+            nbytes = lib().rfn_split_bytes(rows, 1, ks, bf16)
+            buf = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+            ld = (C.c_int * 1)(t.stride(0))
+            check(lib().rfn_split_rows_f32(1, ptr_array([t]), ld, ks, rows, bf16, ptr(buf), nbytes, stream()), "rfn_split_rows_f32")
+            bufs.append(buf)
+        y = torch.empty(M, N, device="cuda")
+        check(lib().rfn_linear_split(bf16, 1, ptr(bufs[0]), ptr(bufs[1]), ks, ptr_array([bias]), ptr(y), N, M, N, 0, stream()),
+              "rfn_linear_split")
+        assert maxdiff(y, want) <= tol * float(want.abs().max())
+        if not bf16:
+            inv = bufs[0][:M * 4].view(torch.float32)
+            off = (M * 4 + 255) // 256 * 256
+            sz = (M * K * 2 + 255) // 256 * 256
+            p0 = bufs[0][off:off + M * K * 2].view(torch.float16).view(M, K).double()
+            p1 = bufs[0][off + sz:off + sz + M * K * 2].view(torch.float16).view(M, K).double()
+            rec = (p0 + p1) * inv.double().unsqueeze(1)
+            rowmax = x.abs().max(dim=1, keepdim=True)[0].double()
+            assert float(((rec - x.double()).abs() / rowmax).max()) <= 2.0 ** -21
+            assert float((p0.abs().max(dim=1)[0]).min()) >= 2.0 ** 14 - 16 and float(p0.abs().max()) <= 2.0 ** 15
