@@ -225,17 +225,19 @@ def run_ours(args):
     # traffic: dram__bytes_read+write of ONE launch from the committed ncu --set full captures (resnet encoder,
     # 1024 images per launch; profiles/r1_gemm_tc2p_score_ncu.txt, profiles/r1_attention_step_ncu.txt); the
     # algorithmic bytes of that same launch are given beside it.
-    passes = {0: 1, 1: 3, 2: 1, 3: 2}[args.gemm_mode]   # tensor-core cost per product in TF32-MMA units (mode 3: 1 TF32 + 2 BF16 at half cost)
+    # tensor-core cost per product in TF32-MMA units (mode 3: 1 TF32 + 2 BF16 at half cost; mode 4: 3 fp16 MMAs at half cost)
+    passes = {0: 1, 1: 3, 2: 1, 3: 2, 4: 1.5, 5: 0.5}[args.gemm_mode]
     roof_gemm = dict(kernel="gemm_att2att_stage1", bound="tensor", achieved=round(tf, 2), peak=peaks["bf16_sustained"],
                      unit="TFLOP/s", frac=round(tf / peaks["bf16_sustained"], 4),
-                     traffic=1.718e9 if args.gemm_mode in (1, 3) else None,
-                     traffic_note="ncu capture of one launch (resnet encoder, 1024 images, persistent 2-CTA kernel): 1.711 GB read "
-                                  "+ 0.007 GB written vs 1.648 GB algorithmic (A once + W once); tensor pipe 97.7 % active in mode 1 "
-                                  "(profiles/r1_gemm_tc2p_score_ncu.txt), 69 % in mode 3 (bound by the x splitter; profiles/r1_gemm_tc2p_mode3_ncu.txt)",
+                     traffic=GEMM_TRAFFIC.get(args.gemm_mode, (None, ""))[0],
+                     traffic_note=GEMM_TRAFFIC.get(args.gemm_mode, (None, "no ncu capture for this engine mode"))[1],
                      mma_tflops_executed=round(tf * passes, 1),
                      frac_of_3xtf32_ceiling=(round(tf * passes / (peaks["bf16_burst"] / 2), 4) if args.gemm_mode >= 1 else None),
-                     ceiling_note=("fp32-equivalent = 1 TF32 + 2 BF16 MMAs per product = 2 TF32-MMA units (mode 3)" if args.gemm_mode == 3 else
-                                   "fp32-equivalent = 3 TF32 MMAs per product") + "; TF32 peak taken as half the measured bf16 burst peak",
+                     ceiling_note={3: "fp32-equivalent = 1 TF32 + 2 BF16 MMAs per product = 2 TF32-MMA units (mode 3)",
+                                   4: "fp32-equivalent = 3 fp16 MMAs per product (x0.w0 + x1.w0 + x0.w1) = 1.5 TF32-MMA units (mode 4): "
+                                      "the ceiling is a third of the fp16 / bf16 peak",
+                                   5: "single bf16 MMA per product"}.get(args.gemm_mode, "fp32-equivalent = 3 TF32 MMAs per product")
+                                  + "; TF32 peak taken as half the measured bf16 burst peak",
                      launches=g_n, avg_launch_ms=round(g_ms / max(1, g_n), 4), share_of_step=shares.get("gemm_att2att_stage1"),
                      peak_source=peaks["source"] + ", dense bf16 sustained; this engine computes in " + args_dtype(args))
     roof_attn = dict(kernel="attention_step_stage1", bound="hbm", achieved=round(gbs, 1), peak=peaks["hbm"], unit="GB/s",
@@ -557,8 +559,20 @@ def ciderd_bench(device):
 
 
 def args_dtype(args):
-    return {0: "fp32", 1: "fp32 (3xTF32 tcgen05 contraction, fp32 accumulate)", 2: "bf16",
-            3: "fp32 (TF32 + 2 BF16 cross-term tcgen05 contraction, fp32 accumulate)"}[args.gemm_mode]
+    return {0: "fp32", 1: "fp32 (3xTF32 tcgen05 contraction, fp32 accumulate)", 2: "tf32 (single-pass TF32 tcgen05 contraction, fp32 storage)",
+            3: "fp32 (TF32 + 2 BF16 cross-term tcgen05 contraction, fp32 accumulate)",
+            4: "fp32 (split-fp16 tcgen05 contraction: 3 kind::f16 MMAs per product on scaled fp16 pairs, fp32 accumulate)",
+            5: "bf16 (single-pass bf16 tcgen05 contraction, fp32 accumulate)"}[args.gemm_mode]
+
+
+# dram__bytes_read + write of ONE launch of the stage-1 projection GEMM from the committed `ncu --set full` captures (resnet
+# encoder, 1024 images), per engine mode
+GEMM_TRAFFIC = {
+    1: (1.718e9, "ncu capture of one launch (resnet encoder, 1024 images, persistent 2-CTA 3xTF32 kernel): 1.711 GB read + 0.007 GB "
+                 "written vs 1.648 GB algorithmic (A once + W once); tensor pipe 97.7 % active (profiles/r1_gemm_tc2p_score_ncu.txt)"),
+    3: (1.743e9, "ncu capture of the round-1 headline kernel as shipped (512 threads): 1.735 GB read + 0.008 GB written vs 1.648 GB "
+                 "algorithmic; tensor pipe 80 % active, shared-memory pipe saturated (profiles/r2_tc2p_score_shipped_ncu.txt)"),
+}
 
 
 def cpu_baseline(model, n_images, threads=None):
@@ -634,7 +648,7 @@ def main():
     ap.add_argument("--images", type=int, default=5000)
     ap.add_argument("--chunk", type=int, default=5000, help="images per device call when the features are resident")
     ap.add_argument("--e2e-chunk", type=int, default=500, help="images per device call when streaming host features")
-    ap.add_argument("--gemm-mode", type=int, default=int(os.environ.get("RFN_GEMM_MODE", "3")))
+    ap.add_argument("--gemm-mode", type=int, default=int(os.environ.get("RFN_GEMM_MODE", "4")))
     ap.add_argument("--train-steps", type=int, default=3, help="XE training steps timed for the secondary metric (0 = skip)")
     ap.add_argument("--cpu-images", type=int, default=24)
     ap.add_argument("--e2e-steps", type=int, default=2)

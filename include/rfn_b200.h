@@ -63,6 +63,17 @@ int rfn_version(void);
 int rfn_check_device(void);
 /* number of entries `params` must hold for these dims (773 for the full model) */
 int rfn_num_params(const rfn_dims* dims);
+/* Weight cache of the split-fp16 / bf16 engine (engine modes 4 / 5): the split of every weight matrix the path's large
+ * GEMMs consume (rfn_split_rows_f32 applied per GEMM, joint row scale over the sources of one GEMM), built once per
+ * weight version into a caller-owned buffer of rfn_wcache_bytes(dims, bf16) bytes (~ the size of the fp32 model).
+ * Every path-level entry point below takes `params` with rfn_num_param_slots(dims) = rfn_num_params(dims) + 1 entries:
+ * the LAST entry is the device pointer of that buffer, or NULL to split the weights on the fly in the workspace (about
+ * 2 x the model size of extra HBM traffic and ~300 extra launches per call).  A cache built with bf16 = 0 serves mode 4,
+ * bf16 = 1 serves mode 5; it must be rebuilt after the weights change (optimizer.step(), load_state_dict). */
+int rfn_num_param_slots(const rfn_dims* dims);
+size_t rfn_wcache_bytes(const rfn_dims* dims, int bf16);
+int rfn_wcache_build(const rfn_dims* dims, const float* const* params, int bf16, void* wcache, size_t wcache_bytes,
+                     rfn_stream_t stream);
 /* number of kernels this library has launched in the calling process (bench accounting) */
 uint64_t rfn_launch_count(void);
 /* launches per GEMM kernel family since the process started (rfn_engine_num() families, named by rfn_engine_name()):

@@ -47,6 +47,9 @@ _SIGNATURES = {
     "rfn_version": (_i, []),
     "rfn_check_device": (_i, []),
     "rfn_num_params": (_i, [_dims]),
+    "rfn_num_param_slots": (_i, [_dims]),
+    "rfn_wcache_bytes": (_sz, [_dims, _i]),
+    "rfn_wcache_build": (_i, [_dims, _pp, _i, _vp, _sz, _vp]),
     "rfn_launch_count": (C.c_uint64, []),
     "rfn_engine_num": (_i, []),
     "rfn_engine_name": (C.c_char_p, [_i]),
@@ -111,6 +114,9 @@ _SIGNATURES = {
 }
 
 _lib = None
+#: bumped whenever this package modifies parameters behind autograd's back (the fused optimizer kernel, CUDA-graph replays
+#: of a training step): derived weight caches (model._params) are keyed on it
+WEIGHTS_EPOCH = [0]
 
 
 class RfnError(RuntimeError):

@@ -9,7 +9,7 @@
 namespace rfn {
 static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
-static std::atomic<int> g_gemm_mode{3};  // default: tcgen05 3xTF32, BF16 cross terms in the fused-epilogue GEMMs (fp32-grade)
+static std::atomic<int> g_gemm_mode{4};  // default: split-fp16 tcgen05 engine (fp32-grade; rfn_h3.cuh), 3xTF32 for the small shapes
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -41,11 +41,11 @@ static cudaEvent_t prof_event() {
 bool prof_enabled() { return g_prof_on.load(std::memory_order_relaxed) != 0; }
 TagScope::TagScope(int tag) : prev(g_tag_override) { g_tag_override = tag; }
 TagScope::~TagScope() { g_tag_override = prev; }
-ProfScope::ProfScope(int default_tag, cudaStream_t st) : st_(st), idx_(-1) {
+ProfScope::ProfScope(int default_tag, cudaStream_t st, bool fixed_tag) : st_(st), idx_(-1) {
   if (!prof_enabled()) return;
   std::lock_guard<std::mutex> lk(g_prof_mu);
   ProfRec r;
-  r.tag = g_tag_override >= 0 ? g_tag_override : default_tag;
+  r.tag = (g_tag_override >= 0 && !fixed_tag) ? g_tag_override : default_tag;
   r.e0 = prof_event();
   r.e1 = prof_event();
   cudaEventRecord(r.e0, st);

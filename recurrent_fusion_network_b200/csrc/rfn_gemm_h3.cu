@@ -475,7 +475,7 @@ size_t h3_split_bytes(int rows, const int* K, int nsrc, bool bf16) {
 
 int h3_split(const float* const* x, const int* ldx, const int* K, int nsrc, int rows, bool bf16, void* scratch, H3Operand* out,
              cudaStream_t st) {
-  ProfScope prof__(TAG_SPLIT, st);
+  ProfScope prof__(TAG_SPLIT, st, true);
   RFN_CHECK_ARG(nsrc >= 1 && nsrc <= 3 && rows >= 0 && scratch, "h3_split: bad arguments");
   if (rows == 0) return RFN_OK;
   SplitArgs a{};
@@ -539,6 +539,24 @@ static int make_map16(CUtensorMap* tm, const void* base, int rows, int K, int ld
 }
 
 bool h3_shape_ok(int M, int N) { return M >= 256 && N >= 256; }
+
+// operand layout of a split buffer: [inv (rows floats)] [piece 0 of source 0] [piece 1 of source 0] [piece 0 of source 1] ...
+void h3_view(const void* buf, int rows, const int* K, int nsrc, bool bf16, H3Operand* out) {
+  const char* p = (const char*)buf;
+  const float* inv = (const float*)p;
+  p += up256((size_t)rows * sizeof(float));
+  for (int s = 0; s < nsrc; ++s) {
+    const int ld = ld16(K[s]);
+    const void* p0 = p;
+    p += up256((size_t)rows * ld * 2);
+    const void* p1 = nullptr;
+    if (!bf16) {
+      p1 = p;
+      p += up256((size_t)rows * ld * 2);
+    }
+    out[s] = H3Operand{p0, p1, ld, inv};
+  }
+}
 
 template <int EPI, int NPROD>
 static int launch_h3(const H3Args& t, int bf16, cudaStream_t st) {
@@ -631,24 +649,6 @@ int gemm_h3_auto(const GemmArgs& a, bool bf16, void* scratch, size_t scratch_byt
 
 }  // namespace rfn
 
-// operand layout of a split buffer: [inv (rows floats)] [piece 0 of source 0] [piece 1 of source 0] [piece 0 of source 1] ...
-static void h3_operands_of(const void* buf, int rows, const int* K, int nsrc, bool bf16, rfn::H3Operand* out) {
-  const char* p = (const char*)buf;
-  const float* inv = (const float*)p;
-  p += rfn::up256((size_t)rows * sizeof(float));
-  for (int s = 0; s < nsrc; ++s) {
-    const int ld = rfn::ld16(K[s]);
-    const void* p0 = p;
-    p += rfn::up256((size_t)rows * ld * 2);
-    const void* p1 = nullptr;
-    if (!bf16) {
-      p1 = p;
-      p += rfn::up256((size_t)rows * ld * 2);
-    }
-    out[s] = rfn::H3Operand{p0, p1, ld, inv};
-  }
-}
-
 extern "C" size_t rfn_split_bytes(int rows, int n_src, const int* K, int bf16) {
   if (rows < 0 || n_src < 1 || n_src > 3 || !K) return 0;
   return rfn::h3_split_bytes(rows, K, n_src, bf16 != 0);
@@ -667,8 +667,8 @@ extern "C" int rfn_linear_split(int bf16, int n_src, const void* x_split, const 
                                 float* y, int ldy, int M, int N, int accumulate, rfn_stream_t stream) {
   RFN_CHECK_ARG(n_src >= 1 && n_src <= 3 && x_split && w_split && K && y, "rfn_linear_split: bad arguments");
   rfn::H3Operand xo[3], wo[3];
-  h3_operands_of(x_split, M, K, n_src, bf16 != 0, xo);
-  h3_operands_of(w_split, N, K, n_src, bf16 != 0, wo);
+  rfn::h3_view(x_split, M, K, n_src, bf16 != 0, xo);
+  rfn::h3_view(w_split, N, K, n_src, bf16 != 0, wo);
   rfn::H3Gemm g{};
   g.nsrc = n_src; g.bf16 = bf16 ? 1 : 0;
   for (int s = 0; s < n_src; ++s) g.src[s] = rfn::H3Src{xo[s], wo[s], K[s], bias ? bias[s] : nullptr};

@@ -59,6 +59,8 @@ size_t h3_split_bytes(int rows, const int* K, int nsrc, bool bf16);
 // splits the fp32 sources (joint power-of-two row scale over all of them) into `scratch`; fills out[s] (all share inv)
 int h3_split(const float* const* x, const int* ldx, const int* K, int nsrc, int rows, bool bf16, void* scratch,
              H3Operand* out, cudaStream_t st);
+// the operands a split buffer written by h3_split holds (same layout computation, no launch)
+void h3_view(const void* buf, int rows, const int* K, int nsrc, bool bf16, H3Operand* out);
 bool h3_shape_ok(int M, int N);
 int gemm_h3(const H3Gemm& a, cudaStream_t st);
 // convenience: split x and W of a GemmArgs into scratch (scratch_bytes must cover both) and run the engine

@@ -38,7 +38,7 @@ struct TagScope {  // call-site override of a launcher's default class
 struct ProfScope {  // records start/stop events around one launcher call when profiling is on
   cudaStream_t st_;
   int idx_;
-  ProfScope(int default_tag, cudaStream_t st);
+  ProfScope(int default_tag, cudaStream_t st, bool fixed_tag = false);   // fixed_tag: ignore a call-site TagScope
   ~ProfScope();
 };
 

@@ -3,8 +3,11 @@
 // host<->device synchronisation, no allocation; everything lives in the caller's workspace.
 #include <algorithm>
 #include <atomic>
+#include <initializer_list>
 #include <mutex>
+#include <vector>
 
+#include "rfn_h3.cuh"
 #include "rfn_internal.cuh"
 #include "rfn_vocab.cuh"
 
@@ -102,10 +105,161 @@ static int for_each_encoder(int J, cudaStream_t st, F&& fn) {
   return RFN_OK;
 }
 
+// ---- split-fp16 / bf16 engine plumbing (engine modes 4 / 5, rfn_h3.cuh) -----------------------------
+// Large GEMMs (M, N >= 256) run on the split engine: their fp32 operands are split into scaled fp16 pairs in the
+// caller's workspace first -- the image features once per call (reused by the S0 fusion steps), the thought vectors
+// once for stage 2, the decoder's weights once per decode loop, everything else right before its GEMM.
+struct H3Ws {   // per-stream scratch for on-the-fly operand splits
+  void* x = nullptr;
+  size_t xcap = 0;
+  void* w = nullptr;
+  size_t wcap = 0;
+};
+static bool h3_mode() { return gemm_mode() >= 4; }
+static bool h3_bf16() { return gemm_mode() == 5; }
+static size_t split1(int rows, int K) { return h3_split_bytes(rows, &K, 1, h3_bf16()); }
+static size_t split2(int rows, int K0, int K1) { const int K[2] = {K0, K1}; return h3_split_bytes(rows, K, 2, h3_bf16()); }
+static size_t split3(int rows, int K0, int K1, int K2) { const int K[3] = {K0, K1, K2}; return h3_split_bytes(rows, K, 3, h3_bf16()); }
+static bool h3_take(const GemmArgs& a) { return h3_mode() && h3_shape_ok(a.M, a.N) && gemm_tc_supported(a); }
+
+// pre-split one operand (rows, K) into `buf` when the GEMM that will consume it (its other dimension being `other`) takes the engine
+static int h3_presplit(const float* x, int ld, int K, int rows, void* buf, size_t cap, H3Operand* out, cudaStream_t st) {
+  if (split1(rows, K) > cap) {
+    set_error("operand split: scratch %zu < %zu bytes", cap, split1(rows, K));
+    return RFN_ERR_WORKSPACE;
+  }
+  return h3_split(&x, &ld, &K, 1, rows, h3_bf16(), buf, out, st);
+}
+
+// fills g's sources: x from xpre or split into sc.x, W from wpre or split into sc.w
+static int h3_prepare(const GemmArgs& a, const H3Ws& sc, const H3Operand* xpre, const H3Operand* wpre, H3Gemm& g, cudaStream_t st) {
+  const bool bf = h3_bf16();
+  const float *xs[3], *ws[3];
+  int K[3], ldx[3], ldw[3];
+  for (int s = 0; s < a.nsrc; ++s) {
+    xs[s] = a.src[s].x; ws[s] = a.src[s].w; ldx[s] = a.src[s].ldx; ldw[s] = a.src[s].ldw; K[s] = a.src[s].K;
+  }
+  H3Operand xo[3], wo[3];
+  if (xpre) {
+    for (int s = 0; s < a.nsrc; ++s) xo[s] = xpre[s];
+  } else {
+    const size_t need = h3_split_bytes(a.M, K, a.nsrc, bf);
+    if (need > sc.xcap) { set_error("operand split (x): scratch %zu < %zu bytes", sc.xcap, need); return RFN_ERR_WORKSPACE; }
+    RFN_TRY(h3_split(xs, ldx, K, a.nsrc, a.M, bf, sc.x, xo, st));
+  }
+  if (wpre) {
+    for (int s = 0; s < a.nsrc; ++s) wo[s] = wpre[s];
+  } else {
+    const size_t need = h3_split_bytes(a.N, K, a.nsrc, bf);
+    if (need > sc.wcap) { set_error("operand split (W): scratch %zu < %zu bytes", sc.wcap, need); return RFN_ERR_WORKSPACE; }
+    RFN_TRY(h3_split(ws, ldw, K, a.nsrc, a.N, bf, sc.w, wo, st));
+  }
+  g = H3Gemm{};
+  g.nsrc = a.nsrc; g.bf16 = bf ? 1 : 0;
+  for (int s = 0; s < a.nsrc; ++s) g.src[s] = H3Src{xo[s], wo[s], K[s], a.src[s].bias};
+  g.y = a.y; g.ldy = a.ldy; g.M = a.M; g.N = a.N; g.accumulate = a.accumulate;
+  return RFN_OK;
+}
+
+// y = sum_i x_i W_i^T + b on the engine the mode selects
+static int path_gemm(const GemmArgs& a, const H3Ws* sc, const H3Operand* xpre, const H3Operand* wpre, cudaStream_t st) {
+  if (sc && h3_take(a)) {
+    H3Gemm g;
+    RFN_TRY(h3_prepare(a, *sc, xpre, wpre, g, st));
+    return gemm_h3(g, st);
+  }
+  return gemm(a, st);
+}
+
+// ---- weight cache: the split of every weight matrix the engine consumes, made once per weight version --------------
+// (inference: the weights do not change between calls; splitting them on the fly costs 2 x 1.96 GB of HBM traffic and ~300
+// launches per call, which is what bounds small shards, e.g. 625 images per GPU at 8 GPUs)
+struct WGroupDesc {
+  int n_rows, nsrc;
+  int K[3], pidx[3];
+  size_t off;
+};
+struct WCache {
+  const char* base = nullptr;
+  bool bf16 = false;
+  int J = 0, S0 = 0, S1 = 0, G2 = 0;      // G2: gate-GEMM groups of a stage-2 step (h2h + 2 z_2_h, then 3 z_2_h each)
+  std::vector<WGroupDesc> g;
+  size_t bytes = 0;
+
+  int i_fc2h(int j) const { return j; }
+  int i_s1(int s, int j, int what /* 0 att_2_att_h, 1 h_2_att_h, 2 H2h|z2h */) const { return J + (s * J + j) * 3 + what; }
+  int i_reason_ind(int j) const { return J + 3 * S0 * J + j; }
+  int i_s2(int s, int k /* 2j: att_2_att_h_j, 2j+1: h_2_att_h_j, 2J+grp: gates group */) const {
+    return 2 * J + 3 * S0 * J + s * (2 * J + G2) + k;
+  }
+  int i_reason() const { return 2 * J + 3 * S0 * J + S1 * (2 * J + G2); }
+  int i_dec(int what /* 0 att_2_att_h, 1 h_2_att_h, 2 i2h|h2h|z2h, 3 logit */) const { return i_reason() + 1 + what; }
+
+  void add(int n_rows, std::initializer_list<int> K, std::initializer_list<int> pidx) {
+    WGroupDesc w{};
+    w.n_rows = n_rows;
+    w.nsrc = (int)K.size();
+    int i = 0;
+    for (int k : K) w.K[i++] = k;
+    i = 0;
+    for (int q : pidx) w.pidx[i++] = q;
+    w.off = bytes;
+    bytes += (h3_split_bytes(n_rows, w.K, w.nsrc, bf16) + 255) & ~(size_t)255;
+    g.push_back(w);
+  }
+  WCache(const rfn_dims& d, bool bf16_) : bf16(bf16_), J(d.J), S0(d.num_review_steps_0), S1(d.num_review_steps) {
+    const PIdx ix(d);
+    const int R = d.rnn_size, A = d.att_hid_size, E = d.input_encoding_size, V = d.vocab_plus1, K = d.top_words_count;
+    G2 = 1 + (std::max(0, J - 2) + 2) / 3;
+    for (int j = 0; j < J; ++j) add(R, {d.fc_feat_size[j]}, {ix.fc2h(j, 0)});
+    for (int s = 0; s < S0; ++s)
+      for (int j = 0; j < J; ++j) {
+        add(A, {d.att_feat_size[j]}, {ix.s1(s, j, 0)});
+        add(A, {R}, {ix.s1(s, j, 2)});
+        add(4 * R, {J * R, d.att_feat_size[j]}, {ix.s1(s, j, 6), ix.s1(s, j, 8)});
+      }
+    for (int j = 0; j < J; ++j) add(K, {R}, {ix.reason_ind(j, 0)});
+    for (int s = 0; s < S1; ++s) {
+      for (int j = 0; j < J; ++j) {
+        add(A, {R}, {ix.s2_att(s, j, 0)});
+        add(A, {R}, {ix.s2_att(s, j, 2)});
+      }
+      int jn = 0;
+      for (int grp = 0; grp < G2; ++grp) {   // the grouping of thought_vectors()'s stage-2 gate GEMMs
+        WGroupDesc w{};
+        w.n_rows = 4 * R;
+        int n = 0;
+        if (grp == 0) { w.K[n] = R; w.pidx[n++] = ix.s2_h2h(s, 0); }
+        while (n < 3 && jn < J) { w.K[n] = R; w.pidx[n++] = ix.s2_z2h(s, jn, 0); ++jn; }
+        w.nsrc = n;
+        w.off = bytes;
+        bytes += (h3_split_bytes(w.n_rows, w.K, w.nsrc, bf16) + 255) & ~(size_t)255;
+        g.push_back(w);
+      }
+    }
+    add(K, {R}, {ix.reason(0)});
+    add(A, {R}, {ix.dec(6)});
+    add(A, {R}, {ix.dec(8)});
+    add(4 * R, {E, R, R}, {ix.dec(0), ix.dec(2), ix.dec(4)});
+    add(V, {R}, {ix.logit(0)});
+  }
+  // the cached operands of group i, or nullptr when there is no cache
+  const H3Operand* get(int i, H3Operand* out) const {
+    if (!base) return nullptr;
+    const WGroupDesc& w = g[i];
+    h3_view(base + w.off, w.n_rows, w.K, w.nsrc, bf16, out);
+    return out;
+  }
+};
+
 // ---- stages 1 + 2 ----------------------------------------------------------------------------------
 struct TVWork {
   float *Hcat[2], *C, *TV, *hx, *rs;
   float *g[RFN_MAX_ENCODERS], *P[RFN_MAX_ENCODERS], *z[RFN_MAX_ENCODERS], *G[RFN_MAX_ENCODERS];
+  size_t p_cap[RFN_MAX_ENCODERS];        // floats available in P[j]
+  H3Ws h3[RFN_MAX_ENCODERS];             // engine modes 4 / 5: split scratch of encoder j's stream
+  void* fsplit[RFN_MAX_ENCODERS];        // pre-split features of encoder j (stage 1), then its thought vectors (stage 2)
+  size_t fsplit_cap[RFN_MAX_ENCODERS];
 };
 static size_t p_floats(const rfn_dims& d, int rows, int N) {
   // SIMT engine: P = att_2_att_h(A) is materialised (rows*N, A); tensor engine: partial scores only
@@ -121,9 +275,22 @@ static size_t carve_tv(const rfn_dims& d, int rows, bool need_tv, bool need_reas
   w.hx = b.take<float>((size_t)rows * R);
   for (int j = 0; j < J; ++j) {
     w.g[j] = b.take<float>((size_t)rows * A);
-    w.P[j] = b.take<float>(p_floats(d, rows, std::max(d.att_num[j], S0)));
+    w.p_cap[j] = p_floats(d, rows, std::max(d.att_num[j], S0));
+    w.P[j] = b.take<float>(w.p_cap[j]);
     w.z[j] = b.take<float>((size_t)rows * std::max(d.att_feat_size[j], R));
     w.G[j] = b.take<float>((size_t)rows * 4 * R);
+    w.h3[j] = H3Ws{};
+    w.fsplit[j] = nullptr;
+    w.fsplit_cap[j] = 0;
+    if (h3_mode()) {
+      const int D = d.att_feat_size[j], F = d.fc_feat_size[j], K = d.top_words_count;
+      w.fsplit_cap[j] = std::max(split1(rows * d.att_num[j], D), split1(rows * S0, R));
+      w.fsplit[j] = b.take<char>(w.fsplit_cap[j]);
+      w.h3[j].xcap = std::max({split2(rows, J * R, D), split1(rows, R), split1(rows, F), split3(rows, R, R, R), split1(rows * S1, R)});
+      w.h3[j].x = b.take<char>(w.h3[j].xcap);
+      w.h3[j].wcap = std::max({split2(4 * R, J * R, D), split1(A, D), split1(A, R), split1(R, F), split3(4 * R, R, R, R), split1(K, R)});
+      w.h3[j].w = b.take<char>(w.h3[j].wcap);
+    }
   }
   w.TV = need_tv ? b.take<float>((size_t)J * rows * S0 * R) : nullptr;
   w.rs = need_reason ? b.take<float>((size_t)rows * std::max(S0, S1) * d.top_words_count) : nullptr;
@@ -134,11 +301,24 @@ static size_t carve_tv(const rfn_dims& d, int rows, bool need_tv, bool need_reas
 // the tensor engine with the fused tanh-score epilogue (U_a A never reaches HBM) or GEMM + fused step kernel
 static int attention_module(const rfn_dims& d, const float* h, int ldh, const float* Afeat, int N, int D,
                             const float* U_w, const float* U_b, const float* Wh_w, const float* Wh_b, const float* v_w,
-                            const float* v_b, float* g, float* P, float* z, int ldz, int rows, int tag_gemm, int tag_attn,
+                            const float* v_b, float* g, float* P, size_t p_cap, float* z, int ldz, int rows, int tag_gemm,
+                            int tag_attn, const H3Ws* sc, const H3Operand* feat_split, const H3Operand* w_u, const H3Operand* w_h,
                             cudaStream_t st) {
   const int R = d.rnn_size, A = d.att_hid_size;
-  RFN_TRY(gemm(gemm1(h, ldh, Wh_w, Wh_b, R, g, A, rows, A), st));                          // :36
+  RFN_TRY(path_gemm(gemm1(h, ldh, Wh_w, Wh_b, R, g, A, rows, A), sc, nullptr, w_h, st));      // :36
   GemmArgs pa = gemm1(Afeat, D, U_w, U_b, D, P, A, rows * N, A);                            // :32-34
+  if (sc && h3_take(pa)) {
+    // split engine with the fused tanh-score epilogue: the features arrive pre-split, U is split here
+    H3Gemm hg;
+    RFN_TRY(h3_prepare(pa, *sc, feat_split, w_u, hg, st));
+    hg.epi = 1; hg.g = g; hg.ldg = A; hg.wv = v_w; hg.score = P; hg.natt = N;
+    {
+      TagScope ts(tag_gemm);
+      RFN_TRY(gemm_h3(hg, st));
+    }
+    TagScope ts(tag_attn);
+    return attention_from_scores(Afeat, P, tc_score_slices(A), v_b, z, ldz, nullptr, rows, N, D, 1, st);
+  }
   if (gemm_mode() >= 1 && rows * N >= 128 && gemm_tc_supported(pa)) {
     {
       TagScope ts(tag_gemm);
@@ -146,6 +326,14 @@ static int attention_module(const rfn_dims& d, const float* h, int ldh, const fl
     }
     TagScope ts(tag_attn);
     return attention_from_scores(Afeat, P, tc_score_slices(A), v_b, z, ldz, nullptr, rows, N, D, 1, st);
+  }
+  // P = att_2_att_h(A) materialised (SIMT engine, or operands the tensor engine cannot take, e.g. unaligned views): the
+  // workspace reserved only the partial-score slices for the tensor route, so check before writing rows * N * A floats
+  if ((size_t)rows * N * A > p_cap) {
+    set_error("attention: operands are not 16-byte aligned for the tensor engine and the workspace holds %zu of the %zu floats "
+              "the fp32 SIMT route needs; pass aligned tensors or select rfn_set_gemm_mode(0) before sizing the workspace",
+              p_cap, (size_t)rows * N * A);
+    return RFN_ERR_UNSUPPORTED;
   }
   {
     TagScope ts(tag_gemm);
@@ -159,6 +347,8 @@ static int thought_vectors(const rfn_dims& d, const float* const* prm, const flo
                            const float* const* init_h, const float* const* init_c, const float* const* att, int rows,
                            float* TVc, float* h_out, float* c_out, float* TV_user, float* reason_pred, void* ws,
                            size_t ws_bytes, cudaStream_t st) {
+  WCache wc(d, h3_bf16());
+  if (h3_mode()) wc.base = (const char*)prm[rfn_num_params(&d)];   // optional trailing slot: rfn_wcache_build's buffer
   const int J = d.J, R = d.rnn_size, S0 = d.num_review_steps_0, S1 = d.num_review_steps;
   const int K = d.top_words_count;
   const PIdx ix(d);
@@ -172,12 +362,26 @@ static int thought_vectors(const rfn_dims& d, const float* const* prm, const flo
   float* TV = TV_user ? TV_user : w.TV;
   const size_t tv_stride = (size_t)rows * S0 * R;
 
+  const bool h3 = h3_mode();
+  const H3Ws* sc0 = h3 ? &w.h3[0] : nullptr;
+  H3Operand featop[RFN_MAX_ENCODERS], tvop[RFN_MAX_ENCODERS];
+  bool have_feat[RFN_MAX_ENCODERS] = {};
+
   // A.0  h_j^0 = c_j^0 = fc2h_j(fc_j)                      (misc/RecurrentFusionModel.py:202-208)
   RFN_TRY(for_each_encoder(J, st, [&](int j, cudaStream_t sj) -> int {
     float* cj = w.C + (size_t)j * rows * R;
     const float* hj = cj;
+    if (h3) {   // the features are the x operand of all S0 att_2_att_h GEMMs of this encoder: split them once
+      const int N = d.att_num[j], D = d.att_feat_size[j];
+      if (h3_take(gemm1(att[j], D, prm[ix.s1(0, j, 0)], nullptr, D, w.P[j], d.att_hid_size, rows * N, d.att_hid_size))) {
+        RFN_TRY(h3_presplit(att[j], D, D, rows * N, w.fsplit[j], w.fsplit_cap[j], &featop[j], sj));
+        have_feat[j] = true;
+      }
+    }
     if (fc) {
-      RFN_TRY(gemm(gemm1(fc[j], d.fc_feat_size[j], prm[ix.fc2h(j, 0)], prm[ix.fc2h(j, 1)], d.fc_feat_size[j], cj, R, rows, R), sj));
+      H3Operand wo[3];
+      RFN_TRY(path_gemm(gemm1(fc[j], d.fc_feat_size[j], prm[ix.fc2h(j, 0)], prm[ix.fc2h(j, 1)], d.fc_feat_size[j], cj, R, rows, R),
+                        h3 ? &w.h3[j] : nullptr, nullptr, wc.get(wc.i_fc2h(j), wo), sj));
     } else {
       RFN_CUDA(cudaMemcpyAsync(cj, init_c[j], (size_t)rows * R * sizeof(float), cudaMemcpyDeviceToDevice, sj));
       hj = init_h[j];
@@ -194,9 +398,12 @@ static int thought_vectors(const rfn_dims& d, const float* const* prm, const flo
       const int N = d.att_num[j], D = d.att_feat_size[j];
       float* cj = w.C + (size_t)j * rows * R;
       // z = Att(h_j, A_j)   -- att_2_att_h is the 89%-of-FLOPs contraction
+      const H3Ws* scj = h3 ? &w.h3[j] : nullptr;
+      H3Operand wu[1], wh[1], wg[3];
       RFN_TRY(attention_module(d, Hin + (size_t)j * R, J * R, att[j], N, D, prm[ix.s1(s, j, 0)], prm[ix.s1(s, j, 1)],
                                prm[ix.s1(s, j, 2)], prm[ix.s1(s, j, 3)], prm[ix.s1(s, j, 4)], prm[ix.s1(s, j, 5)], w.g[j],
-                               w.P[j], w.z[j], D, rows, TAG_GEMM_ATT2ATT, TAG_ATTN_S1, sj));
+                               w.P[j], w.p_cap[j], w.z[j], D, rows, TAG_GEMM_ATT2ATT, TAG_ATTN_S1, scj,
+                               have_feat[j] ? &featop[j] : nullptr, wc.get(wc.i_s1(s, j, 0), wu), wc.get(wc.i_s1(s, j, 1), wh), sj));
       // G = H2h(H) + z2h(z)                                 (misc/RecurrentFusionModel.py:53)
       GemmArgs ga{};
       ga.src[0] = GemmSrc{Hin, prm[ix.s1(s, j, 6)], prm[ix.s1(s, j, 7)], J * R, J * R, J * R};
@@ -204,15 +411,22 @@ static int thought_vectors(const rfn_dims& d, const float* const* prm, const flo
       ga.nsrc = 2; ga.y = w.G[j]; ga.ldy = 4 * R; ga.M = rows; ga.N = 4 * R;
       {
         TagScope ts(TAG_GEMM_GATES);
-        RFN_TRY(gemm(ga, sj));
+        RFN_TRY(path_gemm(ga, scj, nullptr, wc.get(wc.i_s1(s, j, 2), wg), sj));
       }
       return lstm_cell(w.G[j], cj, nullptr, cj, Hout + (size_t)j * R, J * R, TV + j * tv_stride + (size_t)s * R, S0 * R, rows, R, sj);
     }));
   }
   const float* Hfin = w.Hcat[S0 & 1];
+  // the thought vectors TV_j are the x operand of the stage-2 attention projections (S1 steps) and of the reason heads
+  const bool have_tv = h3 && h3_shape_ok(rows * S0, d.att_hid_size);
+  if (have_tv)
+    for (int j = 0; j < J; ++j)
+      RFN_TRY(h3_presplit(TV + j * tv_stride, R, R, rows * S0, w.fsplit[j], w.fsplit_cap[j], &tvop[j], st));
   if (reason_pred) {
     for (int j = 0; j < J; ++j) {  // reason_pred_j = max_s reason_linear_individual_j(h_j^s)   (:291,:303)
-      RFN_TRY(gemm(gemm1(TV + j * tv_stride, R, prm[ix.reason_ind(j, 0)], prm[ix.reason_ind(j, 1)], R, w.rs, K, rows * S0, K), st));
+      H3Operand wo[3];
+      RFN_TRY(path_gemm(gemm1(TV + j * tv_stride, R, prm[ix.reason_ind(j, 0)], prm[ix.reason_ind(j, 1)], R, w.rs, K, rows * S0, K), sc0,
+                        have_tv ? &tvop[j] : nullptr, wc.get(wc.i_reason_ind(j), wo), st));
       RFN_TRY(max_over_steps(w.rs, reason_pred + (size_t)j * rows * K, rows, S0, K, st));
     }
   }
@@ -226,12 +440,14 @@ static int thought_vectors(const rfn_dims& d, const float* const* prm, const flo
     const float* hin = hb[(S1 + s) & 1];
     float* hout = hb[(S1 + s + 1) & 1];
     RFN_TRY(for_each_encoder(J, st, [&](int j, cudaStream_t sj) -> int {
+      H3Operand wu[1], wh[1];
       return attention_module(d, hin, R, TV + j * tv_stride, S0, R, prm[ix.s2_att(s, j, 0)], prm[ix.s2_att(s, j, 1)],
                               prm[ix.s2_att(s, j, 2)], prm[ix.s2_att(s, j, 3)], prm[ix.s2_att(s, j, 4)], prm[ix.s2_att(s, j, 5)],
-                              w.g[j], w.P[j], w.z[j], R, rows, TAG_GEMM_OTHER, TAG_ATTN_SMALL, sj);
+                              w.g[j], w.P[j], w.p_cap[j], w.z[j], R, rows, TAG_GEMM_OTHER, TAG_ATTN_SMALL, h3 ? &w.h3[j] : nullptr,
+                              have_tv ? &tvop[j] : nullptr, wc.get(wc.i_s2(s, 2 * j), wu), wc.get(wc.i_s2(s, 2 * j + 1), wh), sj);
     }));
     // G = h2h(h) + sum_j z_2_h[j](z_j)       (misc/LSTMSoftMultiAttentionFeatArrayNoInputCore.py:50-52)
-    int jn = 0;
+    int jn = 0, grp = 0;
     bool first = true;
     while (first || jn < J) {
       GemmArgs ga{};
@@ -244,14 +460,17 @@ static int thought_vectors(const rfn_dims& d, const float* const* prm, const flo
       ga.nsrc = n; ga.y = w.G[0]; ga.ldy = 4 * R; ga.M = rows; ga.N = 4 * R; ga.accumulate = first ? 0 : 1;
       {
         TagScope ts(TAG_GEMM_GATES);
-        RFN_TRY(gemm(ga, st));
+        H3Operand wo[3];
+        RFN_TRY(path_gemm(ga, sc0, nullptr, wc.get(wc.i_s2(s, 2 * J + grp), wo), st));
       }
       first = false;
+      ++grp;
     }
     RFN_TRY(lstm_cell(w.G[0], c_out, hout, c_out, TVc + (size_t)s * R, S1 * R, nullptr, 0, rows, R, st));
   }
   if (reason_pred) {
-    RFN_TRY(gemm(gemm1(TVc, R, prm[ix.reason(0)], prm[ix.reason(1)], R, w.rs, K, rows * S1, K), st));
+    H3Operand wo[3];
+    RFN_TRY(path_gemm(gemm1(TVc, R, prm[ix.reason(0)], prm[ix.reason(1)], R, w.rs, K, rows * S1, K), sc0, nullptr, wc.get(wc.i_reason(), wo), st));
     RFN_TRY(max_over_steps(w.rs, reason_pred + (size_t)J * rows * K, rows, S1, K, st));
   }
   return RFN_OK;
@@ -264,6 +483,12 @@ struct DecWork {
   int32_t *top_idx, *tok, *src, *any, *st_idx;
   uint8_t* unfinished;
   BeamState bs;
+  // engine modes 4 / 5: activation-split scratch and the decoder's weights split once per decode loop
+  H3Ws h3;
+  void* wsplit[3];          // h_2_att_h | i2h,h2h,z2h (joint row scale) | logit
+  size_t wsplit_cap[3];
+  H3Operand w_att[1], w_gates[3], w_logit[1];
+  bool h3_ready;
 };
 static size_t carve_dec(const rfn_dims& d, int rowsA, int rows, int beam, int n_logit_bufs, Bump& b, DecWork& w) {
   const int R = d.rnn_size, A = d.att_hid_size, E = d.input_encoding_size, S1 = d.num_review_steps, V = d.vocab_plus1;
@@ -292,6 +517,19 @@ static size_t carve_dec(const rfn_dims& d, int rowsA, int rows, int beam, int n_
   w.src = b.take<int32_t>(rows);
   w.any = b.take<int32_t>(L + 2);
   w.unfinished = b.take<uint8_t>(rows);
+  w.h3 = H3Ws{};
+  w.h3_ready = false;
+  for (int i = 0; i < 3; ++i) { w.wsplit[i] = nullptr; w.wsplit_cap[i] = 0; }
+  if (h3_mode()) {
+    w.h3.xcap = std::max({split3(rows, E, R, R), split1(rows, R), split1(rowsA * S1, R)});
+    w.h3.x = b.take<char>(w.h3.xcap);
+    w.h3.wcap = split1(A, R);
+    w.h3.w = b.take<char>(w.h3.wcap);
+    w.wsplit_cap[0] = split1(A, R);
+    w.wsplit_cap[1] = split3(4 * R, E, R, R);
+    w.wsplit_cap[2] = split1(V, R);
+    for (int i = 0; i < 3; ++i) w.wsplit[i] = b.take<char>(w.wsplit_cap[i]);
+  }
   if (beam > 0) {
     const int images = rowsA;
     const size_t cap = (size_t)beam * L;
@@ -310,10 +548,41 @@ static size_t carve_dec(const rfn_dims& d, int rowsA, int rows, int beam, int n_
 
 // hoisted loop invariant: P_dec = att_2_att_h(TVc)   (the reference recomputes it every step,
 // misc/LSTMSoftAttentionCore.py:64-66)
-static int decoder_prepare(const rfn_dims& d, const float* const* prm, const float* TVc, int rowsA, float* Pdec, cudaStream_t st) {
+static int decoder_prepare(const rfn_dims& d, const float* const* prm, const float* TVc, int rowsA, float* Pdec, cudaStream_t st,
+                           DecWork* w = nullptr, int rows = 0) {
   const PIdx ix(d);
-  const int R = d.rnn_size, A = d.att_hid_size, S1 = d.num_review_steps;
-  return gemm(gemm1(TVc, R, prm[ix.dec(6)], prm[ix.dec(7)], R, Pdec, A, rowsA * S1, A), st);
+  const int R = d.rnn_size, A = d.att_hid_size, S1 = d.num_review_steps, E = d.input_encoding_size, V = d.vocab_plus1;
+  const H3Ws* sc = (w && h3_mode() && w->h3.x) ? &w->h3 : nullptr;
+  WCache wc(d, h3_bf16());
+  if (sc) wc.base = (const char*)prm[rfn_num_params(&d)];
+  H3Operand wu[1];
+  RFN_TRY(path_gemm(gemm1(TVc, R, prm[ix.dec(6)], prm[ix.dec(7)], R, Pdec, A, rowsA * S1, A), sc, nullptr, wc.get(wc.i_dec(0), wu), st));
+  if (sc && rows >= 256 && wc.base) {
+    wc.get(wc.i_dec(1), w->w_att);
+    wc.get(wc.i_dec(2), w->w_gates);
+    wc.get(wc.i_dec(3), w->w_logit);
+    w->h3_ready = true;
+  } else if (sc && rows >= 256) {
+    // the decoder's weights are shared by all L + 1 steps: split them once (misc/LSTMSoftAttentionCore.py:13-58, logit :156)
+    const bool bf = h3_bf16();
+    {
+      const float* ws[1] = {prm[ix.dec(8)]};
+      const int ld[1] = {R}, K[1] = {R};
+      RFN_TRY(h3_split(ws, ld, K, 1, A, bf, w->wsplit[0], w->w_att, st));
+    }
+    {
+      const float* ws[3] = {prm[ix.dec(0)], prm[ix.dec(2)], prm[ix.dec(4)]};
+      const int ld[3] = {E, R, R}, K[3] = {E, R, R};
+      RFN_TRY(h3_split(ws, ld, K, 3, 4 * R, bf, w->wsplit[1], w->w_gates, st));
+    }
+    {
+      const float* ws[1] = {prm[ix.logit(0)]};
+      const int ld[1] = {R}, K[1] = {R};
+      RFN_TRY(h3_split(ws, ld, K, 1, V, bf, w->wsplit[2], w->w_logit, st));
+    }
+    w->h3_ready = true;
+  }
+  return RFN_OK;
 }
 
 // one LSTMSoftAttentionCore step + vocab projection  (misc/LSTMSoftAttentionCore.py:60-102, logit :349)
@@ -324,7 +593,8 @@ static int decoder_step(const rfn_dims& d, const float* const* prm, const float*
                         DecWork& w, int rows, cudaStream_t st, int fuse_topk = 0, int* fused = nullptr) {
   const PIdx ix(d);
   const int R = d.rnn_size, A = d.att_hid_size, E = d.input_encoding_size, S1 = d.num_review_steps, V = d.vocab_plus1;
-  RFN_TRY(gemm(gemm1(hin, R, prm[ix.dec(8)], prm[ix.dec(9)], R, w.g, A, rows, A), st));
+  const H3Ws* sc = w.h3_ready ? &w.h3 : nullptr;
+  RFN_TRY(path_gemm(gemm1(hin, R, prm[ix.dec(8)], prm[ix.dec(9)], R, w.g, A, rows, A), sc, nullptr, w.w_att, st));
   RFN_TRY(attention_step(TVc, Pdec, w.g, prm[ix.dec(10)], prm[ix.dec(11)], w.z, R, nullptr, rows, S1, R, A, div, st));
   GemmArgs ga{};
   ga.src[0] = GemmSrc{x, prm[ix.dec(0)], prm[ix.dec(1)], E, E, E};
@@ -333,13 +603,26 @@ static int decoder_step(const rfn_dims& d, const float* const* prm, const float*
   ga.nsrc = 3; ga.y = w.G; ga.ldy = 4 * R; ga.M = rows; ga.N = 4 * R;
   {
     TagScope ts(TAG_GEMM_GATES);
-    RFN_TRY(gemm(ga, st));
+    RFN_TRY(path_gemm(ga, sc, nullptr, w.w_gates, st));
   }
   RFN_TRY(lstm_cell(w.G, cin, hout, cout, nullptr, 0, nullptr, 0, rows, R, st));
   if (fused) *fused = 0;
   if (logits) {
     GemmArgs la = gemm1(hout, R, prm[ix.logit(0)], prm[ix.logit(1)], R, logits, V, rows, V);
-    if (fuse_topk > 0 && gemm_mode() >= 1 && rows >= 128 && gemm_tc_supported(la)) {
+    if (sc && h3_take(la)) {
+      H3Gemm hg;
+      RFN_TRY(h3_prepare(la, *sc, nullptr, w.w_logit, hg, st));
+      if (fuse_topk > 0) {   // logits never reach HBM: per-slice max / sum-exp / top-k, merged below
+        hg.epi = 2; hg.st_max = w.st_max; hg.st_sum = w.st_sum; hg.st_val = w.st_val; hg.st_idx = w.st_idx; hg.ktop = fuse_topk;
+        RFN_TRY(gemm_h3(hg, st));
+        RFN_TRY(vocab_merge(w.st_max, w.st_sum, w.st_val, w.st_idx, tc_score_slices(V), rows, fuse_topk, w.rowmax, w.logsum,
+                            w.top_val, w.top_idx, st));
+        if (fused) *fused = 1;
+      } else {
+        TagScope ts(TAG_GEMM_LOGIT);
+        RFN_TRY(gemm_h3(hg, st));
+      }
+    } else if (fuse_topk > 0 && gemm_mode() >= 1 && rows >= 128 && gemm_tc_supported(la)) {
       RFN_TRY(gemm_tc_vocab(la, tc_passes(gemm_mode()), w.st_max, w.st_sum, w.st_val, w.st_idx, fuse_topk, st));
       RFN_TRY(vocab_merge(w.st_max, w.st_sum, w.st_val, w.st_idx, tc_score_slices(V), rows, fuse_topk, w.rowmax, w.logsum,
                           w.top_val, w.top_idx, st));
@@ -365,6 +648,32 @@ extern "C" {
 
 int rfn_set_concurrency(int on) {
   g_concurrency.store(on ? 1 : 0);
+  return RFN_OK;
+}
+
+int rfn_num_param_slots(const rfn_dims* dims) { return dims ? rfn_num_params(dims) + 1 : RFN_ERR_INVALID; }
+
+size_t rfn_wcache_bytes(const rfn_dims* dims, int bf16) {
+  if (check_dims(dims) != RFN_OK) return 0;
+  return WCache(*dims, bf16 != 0).bytes + 256;
+}
+
+int rfn_wcache_build(const rfn_dims* dims, const float* const* params, int bf16, void* wcache, size_t wcache_bytes,
+                     rfn_stream_t stream) {
+  RFN_TRY(check_dims(dims));
+  RFN_CHECK_ARG(params && wcache, "rfn_wcache_build: null pointer");
+  WCache wc(*dims, bf16 != 0);
+  if (wc.bytes > wcache_bytes) {
+    set_error("rfn_wcache_build: buffer %zu < %zu bytes", wcache_bytes, wc.bytes);
+    return RFN_ERR_WORKSPACE;
+  }
+  for (const WGroupDesc& g : wc.g) {
+    const float* ws[3];
+    int ld[3];
+    for (int s = 0; s < g.nsrc; ++s) { ws[s] = params[g.pidx[s]]; ld[s] = g.K[s]; }
+    H3Operand out[3];
+    RFN_TRY(h3_split(ws, ld, g.K, g.nsrc, g.n_rows, bf16 != 0, (char*)wcache + g.off, out, (cudaStream_t)stream));
+  }
   return RFN_OK;
 }
 
@@ -436,7 +745,7 @@ int rfn_decode_teacher_forced(const rfn_dims* dims, const float* const* params, 
   Bump b(workspace);
   DecWork w{};
   if (carve_dec(d, rows, rows, 0, 1, b, w) > workspace_bytes) return ws_fail("rfn_decode_teacher_forced", workspace_bytes, b.off);
-  RFN_TRY(decoder_prepare(d, params, TVc, rows, w.Pdec, st));
+  RFN_TRY(decoder_prepare(d, params, TVc, rows, w.Pdec, st, &w, rows));
   RFN_CUDA(cudaMemcpyAsync(w.hA, h0, (size_t)rows * R * sizeof(float), cudaMemcpyDeviceToDevice, st));
   RFN_CUDA(cudaMemcpyAsync(w.cA, c0, (size_t)rows * R * sizeof(float), cudaMemcpyDeviceToDevice, st));
   float* hb[2] = {w.hA, w.hB};
@@ -462,7 +771,7 @@ int rfn_decode_sample(const rfn_dims* dims, const float* const* params, const fl
   Bump b(workspace);
   DecWork w{};
   if (carve_dec(d, rows, rows, 0, 1, b, w) > workspace_bytes) return ws_fail("rfn_decode_sample", workspace_bytes, b.off);
-  RFN_TRY(decoder_prepare(d, params, TVc, rows, w.Pdec, st));
+  RFN_TRY(decoder_prepare(d, params, TVc, rows, w.Pdec, st, &w, rows));
   RFN_CUDA(cudaMemcpyAsync(w.hA, h0, (size_t)rows * R * sizeof(float), cudaMemcpyDeviceToDevice, st));
   RFN_CUDA(cudaMemcpyAsync(w.cA, c0, (size_t)rows * R * sizeof(float), cudaMemcpyDeviceToDevice, st));
   RFN_CUDA(cudaMemsetAsync(w.tok, 0, (size_t)rows * sizeof(int32_t), st));                       // t == 0: BOS (:617-618)
@@ -507,7 +816,7 @@ int rfn_decode_beam(const rfn_dims* dims, const float* const* params, const floa
   Bump b(workspace);
   DecWork w{};
   if (carve_dec(d, images, rows, beam, 1, b, w) > workspace_bytes) return ws_fail("rfn_decode_beam", workspace_bytes, b.off);
-  RFN_TRY(decoder_prepare(d, params, TVc, images, w.Pdec, st));
+  RFN_TRY(decoder_prepare(d, params, TVc, images, w.Pdec, st, &w, rows));
   RFN_TRY(beam_init(w, images, beam, L, st));
   // expand each image's stage-2 state to `beam` identical rows (:376-394)
   RFN_TRY(gather_rows(h0, nullptr, beam, w.hB, rows, R, st));

@@ -339,6 +339,9 @@ class RecurrentFusionModel(nn.Module):
     #: training only: set to seq_per_img (5) when the batch holds that many consecutive replicas of every image
     #: (dataloader.py:251-252) and stage-1/2 dropout is 0; stages 1-2 then run once per image
     dedup_rows = 1
+    #: training only, with dedup_rows = g > 1: the feature tensors passed in hold ONE row per image (what
+    #: ingest.FeatureIngest ships over PCIe) while labels hold g consecutive rows per image
+    unique_feature_rows = False
 
     def __init__(self, opt):
         super().__init__()
@@ -400,10 +403,19 @@ class RecurrentFusionModel(nn.Module):
             self.fc2h[i].weight.data.uniform_(-_INIT, _INIT)
 
     # ---- plumbing ------------------------------------------------------------------------------
+    #: keep a split copy of the weights for the fp16x3 / bf16 engines (modes 4 / 5) between inference calls; rebuilt
+    #: whenever a parameter's storage or version changes.  Costs about the size of the fp32 model in HBM.
+    weight_cache = True
+
     def _params(self):
-        """HOST array of device pointers in state_dict order (cached until storage moves)."""
+        """HOST array of device pointers in state_dict order plus the trailing weight-cache slot (rfn_num_param_slots);
+        cached until a parameter's storage moves, the engine mode changes, or -- for the weight cache -- a parameter is
+        modified (its autograd version counter changes)."""
         ps = list(self.parameters())
-        key = tuple(p.data_ptr() for p in ps)
+        mode = lib().rfn_get_gemm_mode()
+        use_cache = bool(self.weight_cache) and mode >= 4 and not torch.is_grad_enabled()
+        key = (tuple(p.data_ptr() for p in ps), mode, use_cache,
+               (tuple(p._version for p in ps), _capi.WEIGHTS_EPOCH[0]) if use_cache else None)
         if self._pcache is None or self._pcache[0] != key:
             n = lib().rfn_num_params(C.byref(self._dims))
             if n != len(ps):
@@ -412,7 +424,19 @@ class RecurrentFusionModel(nn.Module):
                 _require_cuda(p)
                 if p.dtype != torch.float32 or not p.is_contiguous():
                     raise _capi.RfnError("parameters must be contiguous fp32")
-            self._pcache = (key, ptr_array(ps))
+            arr = ptr_array(ps + [None])
+            wcache = None
+            if use_cache:
+                bf16 = 1 if mode == 5 else 0
+                nbytes = lib().rfn_wcache_bytes(C.byref(self._dims), bf16)
+                wcache = getattr(self, "_wcache", None)
+                if wcache is None or wcache.numel() < nbytes or wcache.device != ps[0].device:
+                    wcache = torch.empty(nbytes, dtype=torch.uint8, device=ps[0].device)
+                check(lib().rfn_wcache_build(C.byref(self._dims), arr, bf16, ptr(wcache), wcache.numel(), stream()),
+                      "rfn_wcache_build")
+                arr[len(ps)] = ptr(wcache)
+            self._wcache = wcache
+            self._pcache = (key, arr)
         return self._pcache[1]
 
     def _dropout_active(self, p):

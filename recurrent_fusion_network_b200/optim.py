@@ -13,6 +13,7 @@ import ctypes as C
 
 import torch
 
+from . import _capi
 from ._capi import check, lib, ptr, ptr_array, stream
 
 
@@ -101,4 +102,5 @@ class FusedAdam(torch.optim.Optimizer):
                                           float(group.get("grad_clip", 0.0)), float(group.get("grad_scale", 1.0)), int(step),
                                           ptr(hyper), stream()),
                   "rfn_adam_step_f32")
+        _capi.WEIGHTS_EPOCH[0] += 1   # the kernel wrote the parameters through raw pointers: invalidate derived weight caches
         return loss

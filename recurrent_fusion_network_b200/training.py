@@ -38,10 +38,15 @@ def _stages(model, fc, att):
     g = int(getattr(model, "dedup_rows", 1) or 1)
     rows = fc[0].shape[0]
     AG.clear_transposed_cache()
-    if g > 1 and rows % g == 0 and not (model._dropout_active(model.drop_prob_fusion) or
-                                        model._dropout_active(model.drop_prob_reason)):
-        fcu = [f[::g].contiguous() for f in fc]
-        attu = [a[::g].contiguous() for a in att]
+    unique = bool(getattr(model, "unique_feature_rows", False)) and g > 1
+    if unique and (model._dropout_active(model.drop_prob_fusion) or model._dropout_active(model.drop_prob_reason)):
+        raise RuntimeError("unique_feature_rows needs drop_prob_fusion = drop_prob_reason = 0 in training mode (each replica "
+                           "would draw its own dropout mask in the reference); pass FeatureBatch.expanded() instead")
+    if unique or (g > 1 and rows % g == 0 and not (model._dropout_active(model.drop_prob_fusion) or
+                                                   model._dropout_active(model.drop_prob_reason))):
+        # unique: the caller ships one feature row per image (ingest.FeatureBatch.fc / .att) and g label rows per image
+        fcu = fc if unique else [f[::g].contiguous() for f in fc]
+        attu = att if unique else [a[::g].contiguous() for a in att]
         TVc, reason_pred, (h, c) = thought_vectors(model, attu, model.get_init_state(fcu))
         ex = lambda t: AG.ExpandRowsFn.apply(t, g)
         return ex(TVc), [ex(r) for r in reason_pred], (ex(h.squeeze(0)).unsqueeze(0), ex(c.squeeze(0)).unsqueeze(0))
@@ -61,7 +66,11 @@ def forward_xe(model, fc_feats, att_feats, seq, col_any=None):
     columns hold a non-zero token) may be supplied by a caller that already knows it on the host, so that the
     call contains no device->host synchronisation (CUDA-graph capture)."""
     fc, att, rows = model._check_feats(fc_feats, att_feats)
+    if getattr(model, "unique_feature_rows", False) and int(getattr(model, "dedup_rows", 1) or 1) > 1:
+        rows *= int(model.dedup_rows)
     seq = seq.to(device=fc[0].device, dtype=torch.int64)
+    if seq.shape[0] != rows:
+        raise RuntimeError(f"labels have {seq.shape[0]} rows, the features describe {rows}")
     TVc, reason_pred, state = _stages(model, fc, att)
     outputs = []
     if col_any is None:
@@ -93,6 +102,8 @@ def sample_with_grad(model, fc_feats, att_feats, opt):
     sample_max = opt.get("sample_max", 1)
     temperature = opt.get("temperature", 1.0)
     fc, att, rows = model._check_feats(fc_feats, att_feats)
+    if getattr(model, "unique_feature_rows", False) and int(getattr(model, "dedup_rows", 1) or 1) > 1:
+        rows *= int(model.dedup_rows)
     dev = fc[0].device
     L = model.seq_length
     uniforms = None
@@ -212,4 +223,6 @@ class GraphedXEStep:
         if self.between is not None:
             self.between()
         self.g_opt.replay()
+        from . import _capi
+        _capi.WEIGHTS_EPOCH[0] += 1   # the replayed optimizer kernel rewrote the parameters
         return self.loss

@@ -111,9 +111,10 @@ def test_review_net_core_alias():
 
 
 # ---- path level vs the REAL reference's outputs (golden fixtures) -----------------------------------
-@pytest.fixture(params=[1, 3, 0], ids=["tc3xtf32", "tc_tf32_bf16x", "simt"])
+@pytest.fixture(params=[4, 1, 3, 0], ids=["tc_fp16x3", "tc3xtf32", "tc_tf32_bf16x", "simt"])
 def gemm_mode(request):
-    """Run under the fp32-grade engines: tcgen05 3xTF32 (default), tcgen05 TF32 + BF16 cross terms (mode 3) and fp32 SIMT."""
+    """Run under the fp32-grade engines: tcgen05 split-fp16 (mode 4, the default), 3xTF32, TF32 + BF16 cross terms (mode 3)
+    and fp32 SIMT."""
     from recurrent_fusion_network_b200 import _capi
     prev = _capi.lib().rfn_get_gemm_mode()
     _capi.check(_capi.lib().rfn_set_gemm_mode(request.param))

@@ -245,3 +245,100 @@ def test_graphed_xe_step_matches_eager_steps():
         worst[k] = maxdiff(pa, pb)
     bad = {k: v for k, v in worst.items() if v > 2e-5}
     assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:5]
+
+
+def _config2_batch(imgs=16, spi=5, seed=3):
+    """BASELINE.json configs[1] as the loader builds it (dataloader.py:251-252): `imgs` images x seq_per_img replicas."""
+    cfg = O.RFNConfig()
+    fc, att = O.make_inputs(cfg, imgs, seed=seed)
+    fc = [f.repeat_interleave(spi, 0) for f in fc]
+    att = [a.repeat_interleave(spi, 0) for a in att]
+    labels, masks, top = O.make_labels(cfg, imgs * spi, seed=seed + 1)
+    return cfg, fc, att, labels, masks, top
+
+
+def _oracle_xe_grads(cfg, sd, fc, att, labels, masks, top):
+    def oracle_loss(p):
+        lp, rp = O.forward_xe(p, cfg, fc, att, labels)
+        return O.xe_loss(lp, labels[:, 1:], masks[:, 1:], rp, top, 10.0, 0.1)
+    torch.set_num_threads(max(16, torch.get_num_threads()))
+    return _oracle_grads(sd, oracle_loss)
+
+
+@pytest.mark.parametrize("dedup", [1, 5], ids=["as_written", "deduplicated"])
+def test_xe_gradients_config2_size(dedup):
+    """The training step bench.py times (full five-encoder model, 80 rows = 16 images x 5 replicas, label smoothing): all 773
+    parameter gradients against autograd through the oracle.  At this size the step runs the split-K 1-CTA tensor kernel
+    (forward, < 128 rows), the MN-major dX route and the split-K 2-CTA dU kernel -- none of which the tiny cases reach."""
+    cfg, fc, att, labels, masks, top = _config2_batch()
+    sd = O.make_state_dict(cfg, seed=1234)
+    want_loss, want = _oracle_xe_grads(cfg, sd, fc, att, labels, masks, top)
+    from recurrent_fusion_network_b200.criteria import ReviewNetEnsembleCriterion
+    m = build_model(cfg, sd).train()
+    m.dedup_rows = dedup
+    crit = ReviewNetEnsembleCriterion(SimpleNamespace(use_label_smoothing=1, label_smoothing_epsilon=0.1, use_cuda=1))
+    lp, rp = m(cuda_list(fc), cuda_list(att), labels.cuda())
+    loss = crit(lp, labels[:, 1:].cuda(), masks[:, 1:].cuda(), rp, top.cuda(), 10.0)
+    loss.backward()
+    assert abs(float(loss) - want_loss) <= 1e-4 * max(1.0, abs(want_loss))
+    assert len(want) == 773
+    _compare_grads(m, want, rel=5e-4)
+
+
+def test_rl_gradients_config4_size():
+    """BASELINE.json configs[3] shapes: full model, 50 rows (10 images x 5), greedy tokens replayed through the taped sample
+    path, self-critical criterion; all gradients against oracle autograd."""
+    cfg = O.RFNConfig()
+    sd = O.make_state_dict(cfg, seed=1234, sharpen=True)
+    imgs, spi = 10, 5
+    rows = imgs * spi
+    fc, att = O.make_inputs(cfg, imgs, seed=8)
+    fc = [f.repeat_interleave(spi, 0) for f in fc]
+    att = [a.repeat_interleave(spi, 0) for a in att]
+    _, _, top = O.make_labels(cfg, rows, seed=3)
+    g = torch.Generator().manual_seed(5)
+    torch.set_num_threads(max(16, torch.get_num_threads()))
+    with torch.no_grad():
+        s0, *_ = O.sample(sd, cfg, fc, att, sample_max=1)
+    reward = torch.randn(rows, 1, generator=g).expand(rows, s0.shape[1]).contiguous()
+
+    def oracle_loss(p):
+        s, sl, la, rp = O.sample(p, cfg, fc, att, sample_max=1)
+        return O.rl_loss(sl, s, reward, la, 0.01, rp, top, 10.0)
+
+    want_loss, want = _oracle_grads(sd, oracle_loss)
+    from recurrent_fusion_network_b200.criteria import ReviewNetRewardCriterion
+    m = build_model(cfg, sd).train()
+    rl = ReviewNetRewardCriterion(SimpleNamespace(use_label_smoothing=0, label_smoothing_epsilon=0.1))
+    s, sl, la, rp = m.sample(cuda_list(fc), cuda_list(att), {"sample_max": 1})
+    if not torch.equal(s.cpu(), s0):
+        pytest.skip("greedy tokens differ on a near-tie at this size; the gradient comparison needs identical tokens")
+    loss = rl(sl, s, reward.cuda(), la, 0.01, rp, top.cuda(), 10.0, None, SimpleNamespace(use_ppo=0))
+    loss.backward()
+    assert abs(float(loss) - want_loss) <= 1e-4 * max(1.0, abs(want_loss))
+    _compare_grads(m, want, rel=5e-4)
+
+
+def test_unique_feature_rows_equal_replicated_rows():
+    """ingest.FeatureBatch ships one feature row per image; model.unique_feature_rows consumes them directly and gives the
+    loss and gradients of the reference's replicated batch (dataloader.py:246-247)."""
+    cfg = O.tiny_config(2)
+    sd = O.make_state_dict(cfg, seed=77, init_range=0.5, logit_scale=3.0)
+    g, imgs = 5, 3
+    fcu, attu = O.make_inputs(cfg, imgs, seed=4)
+    labels, masks, top = O.make_labels(cfg, imgs * g, seed=6)
+    from recurrent_fusion_network_b200.criteria import ReviewNetEnsembleCriterion
+    crit = ReviewNetEnsembleCriterion(SimpleNamespace(use_label_smoothing=1, label_smoothing_epsilon=0.1, use_cuda=1))
+    out = {}
+    for unique in (False, True):
+        m = build_model(cfg, sd).train()
+        m.dedup_rows, m.unique_feature_rows = g, unique
+        fc = cuda_list(fcu) if unique else [f.repeat_interleave(g, 0).cuda() for f in fcu]
+        att = cuda_list(attu) if unique else [a.repeat_interleave(g, 0).cuda() for a in attu]
+        lp, rp = m(fc, att, labels.cuda())
+        loss = crit(lp, labels[:, 1:].cuda(), masks[:, 1:].cuda(), rp, top.cuda(), 10.0)
+        loss.backward()
+        out[unique] = (float(loss), {k: p.grad.clone() for k, p in m.named_parameters()})
+    assert abs(out[True][0] - out[False][0]) <= 1e-6 * max(1.0, abs(out[False][0]))
+    for k in out[True][1]:
+        assert maxdiff(out[True][1][k], out[False][1][k]) <= 1e-6 * (float(out[False][1][k].abs().max()) + 1e-6) + 1e-8, k
