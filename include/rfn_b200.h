@@ -38,7 +38,7 @@ enum rfn_status {
 };
 
 #define RFN_MAX_ENCODERS 8
-#define RFN_MAX_BEAM 8
+#define RFN_MAX_BEAM 16   /* the reference's default beam_size is 10 (misc/RecurrentFusionModel.py:353) */
 
 /* The `opt` fields RecurrentFusionModel reads (misc/RecurrentFusionModel.py:120-151). */
 typedef struct rfn_dims {
@@ -237,6 +237,16 @@ int rfn_ensemble_decode_beam(const rfn_dims* dims, int n_models, const float* co
                              float* seq_logprobs, int32_t* done_seq, float* done_logps,
                              float* done_p, int32_t* n_done, void* workspace,
                              size_t workspace_bytes, rfn_stream_t stream);
+
+/* Ensemble greedy decode (eval_utils.py:729-975, the loop eval_ensemble.sh runs with --beam_size 1): `rows` images advance
+ * together, per step argmax of log_softmax(mean_m logit_m); every model embeds the UNMASKED argmax, finished rows write 0.
+ * seq (rows,L) int64, seq_logprobs (rows,L); *d_T = number of valid columns (the reference's early break, :889-891).
+ * Workspace: rfn_ensemble_workspace_bytes(dims, n_models, rows, 1). */
+int rfn_ensemble_decode_greedy(const rfn_dims* dims, int n_models, const float* const* const* params_m,
+                               const float* const* TVc_m, const float* const* h0_m,
+                               const float* const* c0_m, int rows, int64_t* seq, float* seq_logprobs,
+                               int32_t* d_T, void* workspace, size_t workspace_bytes,
+                               rfn_stream_t stream);
 
 /* ReviewNetEnsembleCriterion's sequence term (misc/utils.py:161-184), fused over the vocab:
  * out[0] = -(1/rows) sum_{b,t} mask[b,t] ((1-eps) lp[b,t,y] + eps/V1 sum_v lp[b,t,v]).

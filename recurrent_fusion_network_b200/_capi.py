@@ -14,7 +14,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "librfn_b200.so")
 
 MAX_ENCODERS = 8
-MAX_BEAM = 8
+MAX_BEAM = 16
 
 
 class RfnDims(C.Structure):
@@ -82,6 +82,7 @@ _SIGNATURES = {
     "rfn_decode_beam": (_i, [_dims, _pp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "rfn_ensemble_decode_beam": (_i, [_dims, _i, C.POINTER(_pp), _pp, _pp, _pp, _i, _i, _vp, _vp, _vp, _vp, _vp,
                                       _vp, _vp, _sz, _vp]),
+    "rfn_ensemble_decode_greedy": (_i, [_dims, _i, C.POINTER(_pp), _pp, _pp, _pp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "rfn_xe_loss_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
     "rfn_multilabel_margin_f32": (_i, [_vp, _vp, _i, _i, _f, _i, _vp, _vp]),
     "rfn_mean_log_softmax_f32": (_i, [_i, _pp, _i, _i, _vp, _vp, _vp]),

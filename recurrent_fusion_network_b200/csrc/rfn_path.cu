@@ -696,7 +696,8 @@ size_t rfn_ensemble_workspace_bytes(const rfn_dims* dims, int n_models, int imag
   carve_dec(*dims, images, images * beam, beam, n_models + 1, b, dw);
   const int R = dims->rnn_size, A = dims->att_hid_size, S1 = dims->num_review_steps;
   const size_t rows = (size_t)images * beam;
-  const size_t per_model = (4 * rows * R + (size_t)images * S1 * A) * sizeof(float) + 5 * 256;
+  // beam: 4 state buffers of rows x R + images x S1 x A; greedy (beam 1, rfn_ensemble_decode_greedy): 3 + rows x S1 x A
+  const size_t per_model = (4 * rows * R + rows * S1 * A) * sizeof(float) + 5 * 256;
   return b.off + per_model * n_models + 1024;
 }
 
@@ -888,6 +889,58 @@ int rfn_ensemble_decode_beam(const rfn_dims* dims, int n_models, const float* co
     RFN_TRY(vocab_stats_topk(mean, V, rows, V, beam, w.rowmax, w.logsum, w.top_val, w.top_idx, st));
   }
   return beam_finalize(w.bs, seq, seq_logprobs, done_seq, done_logps, done_p, n_done, st);
+}
+
+int rfn_ensemble_decode_greedy(const rfn_dims* dims, int n_models, const float* const* const* params_m,
+                               const float* const* TVc_m, const float* const* h0_m, const float* const* c0_m, int rows,
+                               int64_t* seq, float* seq_logprobs, int32_t* d_T, void* workspace, size_t workspace_bytes,
+                               rfn_stream_t stream) {
+  // eval_utils.py:729-975 (what eval_ensemble.sh runs, --beam_size 1): all images of the batch advance together; per step
+  // every model embeds the UNMASKED argmax (:880-883 before :893), the logits are averaged (:282-287) and the argmax of the
+  // log-softmax is taken; the loop ends when no row is unfinished (:889-891, read back by the caller through d_T)
+  RFN_TRY(check_dims(dims));
+  RFN_CHECK_ARG(params_m && TVc_m && h0_m && c0_m && seq && seq_logprobs && d_T && workspace, "rfn_ensemble_decode_greedy: null pointer");
+  RFN_CHECK_ARG(n_models >= 1 && n_models <= 8 && rows >= 1, "rfn_ensemble_decode_greedy: n_models=%d rows=%d", n_models, rows);
+  cudaStream_t st = (cudaStream_t)stream;
+  const rfn_dims& d = *dims;
+  const PIdx ix(d);
+  const int R = d.rnn_size, V = d.vocab_plus1, E = d.input_encoding_size, L = d.seq_length, A = d.att_hid_size;
+  const int S1 = d.num_review_steps;
+  Bump b(workspace);
+  DecWork w{};
+  carve_dec(d, rows, rows, 0, n_models + 1, b, w);
+  float *hA[8], *hB[8], *cS[8], *Pd[8];
+  for (int m = 0; m < n_models; ++m) {
+    hA[m] = b.take<float>((size_t)rows * R); hB[m] = b.take<float>((size_t)rows * R);
+    cS[m] = b.take<float>((size_t)rows * R);
+    Pd[m] = b.take<float>((size_t)rows * S1 * A);
+  }
+  if (b.off > workspace_bytes) return ws_fail("rfn_ensemble_decode_greedy", workspace_bytes, b.off);
+  float* mean = w.logits + (size_t)n_models * rows * V;
+  for (int m = 0; m < n_models; ++m) {
+    RFN_TRY(decoder_prepare(d, params_m[m], TVc_m[m], rows, Pd[m], st));
+    RFN_CUDA(cudaMemcpyAsync(hA[m], h0_m[m], (size_t)rows * R * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    RFN_CUDA(cudaMemcpyAsync(cS[m], c0_m[m], (size_t)rows * R * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  RFN_CUDA(cudaMemsetAsync(w.tok, 0, (size_t)rows * sizeof(int32_t), st));
+  RFN_CUDA(cudaMemsetAsync(w.any, 0, (size_t)(L + 2) * sizeof(int32_t), st));
+  RFN_CUDA(cudaMemsetAsync(w.unfinished, 0, (size_t)rows, st));
+  PtrList8 pl{};
+  for (int m = 0; m < n_models; ++m) pl.p[m] = w.logits + (size_t)m * rows * V;
+  for (int t = 0; t <= L; ++t) {
+    if (t >= 1)
+      RFN_TRY(sample_select(mean, V, V, w.rowmax, w.logsum, w.top_val, w.top_idx, nullptr, L, 1.f, t, L, w.tok, w.unfinished, w.any,
+                            seq, seq_logprobs, rows, st));
+    for (int m = 0; m < n_models; ++m) {
+      float* hin = (t & 1) ? hB[m] : hA[m];
+      float* hout = (t & 1) ? hA[m] : hB[m];
+      RFN_TRY(embed_gather_i32(w.tok, params_m[m][ix.embed()], w.x, rows, E, V, st));
+      RFN_TRY(decoder_step(d, params_m[m], TVc_m[m], Pd[m], 1, w.x, hin, cS[m], hout, cS[m], w.logits + (size_t)m * rows * V, w, rows, st));
+    }
+    RFN_TRY(mean_logits8(pl, n_models, mean, (size_t)rows * V, st));
+    RFN_TRY(vocab_stats_topk(mean, V, rows, V, 1, w.rowmax, w.logsum, w.top_val, w.top_idx, st));
+  }
+  return sample_finalize(w.any, L, d_T, st);
 }
 
 }  // extern "C"

@@ -119,8 +119,10 @@ int vocab_stats_topk(const float* logits, int ld, int rows, int V, int k, float*
     vocab_stats_topk_kernel<1><<<rows, VT, 0, st>>>(logits, ld, V, k, rowmax, logsum, top_val, top_idx);
   else if (k <= 4)
     vocab_stats_topk_kernel<4><<<rows, VT, 0, st>>>(logits, ld, V, k, rowmax, logsum, top_val, top_idx);
-  else
+  else if (k <= 8)
     vocab_stats_topk_kernel<8><<<rows, VT, 0, st>>>(logits, ld, V, k, rowmax, logsum, top_val, top_idx);
+  else
+    vocab_stats_topk_kernel<16><<<rows, VT, 0, st>>>(logits, ld, V, k, rowmax, logsum, top_val, top_idx);
   RFN_LAUNCH_CHECK();
   return RFN_OK;
 }

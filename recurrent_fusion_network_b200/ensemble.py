@@ -65,3 +65,34 @@ def ensemble_sample_beam(models, fc_feats, att_feats, opt={}):
         top_seq = [ds[k, :nl[k]] for k in range(rows)]
         top_prob = [dp[k][:nl[k]] for k in range(rows)]
         return seq, slp, top_seq, top_prob
+
+
+def ensemble_sample_greedy(models, fc_feats, att_feats, opt={}):
+    """Greedy decode of the logit-mean ensemble (eval_utils.py:729-975): all images of the batch advance together.
+    Returns (seq (B,T) int64, seqLogprobs (B,T)) with T <= seq_length as the reference's early break leaves it."""
+    m0 = models[0]
+    M = len(models)
+    if M > 8:
+        raise _capi.RfnError("at most 8 ensemble members are supported")
+    with torch.no_grad():
+        fc, att, rows = m0._check_feats(fc_feats, att_feats)
+        dev = fc[0].device
+        L = m0.seq_length
+        seq = torch.zeros(rows, L, dtype=torch.int64, device=dev)
+        slp = torch.zeros(rows, L, dtype=torch.float32, device=dev)
+        dT = torch.zeros(1, dtype=torch.int32, device=dev)
+        tv, hs, cs = [], [], []
+        for model in models:
+            TVc, _, h, c = model._thought_vectors(fc, att, rows, want_reason=False)
+            tv.append(TVc); hs.append(h); cs.append(c)
+        nbytes = lib().rfn_ensemble_workspace_bytes(C.byref(m0._dims), M, rows, 1)
+        ws = _WS.get(nbytes, dev)
+        pm = (C.POINTER(C.c_void_p) * M)(*[C.cast(model._params(), C.POINTER(C.c_void_p)) for model in models])
+        check(lib().rfn_ensemble_decode_greedy(C.byref(m0._dims), M, pm, ptr_array(tv), ptr_array(hs), ptr_array(cs), rows,
+                                               ptr(seq), ptr(slp), ptr(dT), ptr(ws), ws.numel(), stream()),
+              "rfn_ensemble_decode_greedy")
+        T = int(dT.item())
+        if T == 0:
+            raise RuntimeError("ensemble greedy: every row emitted <eos> at t=1; the reference fails here too "
+                               "(torch.cat of an empty list, eval_utils.py:947)")
+        return seq[:, :T], slp[:, :T]

@@ -17,7 +17,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from .ensemble import ensemble_sample_beam
+from .ensemble import ensemble_sample_beam, ensemble_sample_greedy
 
 
 def decode_sequence(ix_to_word, seq):
@@ -114,8 +114,15 @@ def eval_split(model, crit, loader, eval_kwargs={}):
     return loss_sum / max(loss_evals, 1), predictions, lang_stats
 
 
+def eval_ensemble_greedy(model_list, loader, eval_kwargs={}):
+    """eval_utils.py:729-975 -- what the reference's shipped eval_ensemble.sh runs (--beam_size 1)."""
+    return eval_ensemble(model_list, loader, dict(eval_kwargs, beam_size=1))
+
+
 def eval_ensemble(model_list, loader, eval_kwargs={}):
-    """Beam search over the logit-mean ensemble, one device call per loader batch; predictions carry 'log_prob'."""
+    """Beam search (eval_utils.py:387-719) or, with beam_size 1, greedy search (:729-975; the reference dispatches on
+    beam_size in eval_ensemble.py:179-186) over the logit-mean ensemble, one device call per loader batch; predictions
+    carry 'log_prob'."""
     num_images = eval_kwargs.get("num_images", -1)
     split = eval_kwargs.get("eval_split", "test")
     lang_eval = eval_kwargs.get("language_eval", 0)
@@ -123,7 +130,7 @@ def eval_ensemble(model_list, loader, eval_kwargs={}):
     beam_size = eval_kwargs.get("beam_size", 3)
     batch_size = eval_kwargs.get("batch_size", 1)
     verbose = eval_kwargs.get("verbose", True)
-    if beam_size <= 1:
+    if beam_size < 1:
         raise AssertionError("beam_size not correct")
     for m in model_list:
         m.eval()
@@ -138,7 +145,10 @@ def eval_ensemble(model_list, loader, eval_kwargs={}):
             pick = np.arange(loader.batch_size) * loader.seq_per_img
             fc = [_to(a[pick], dev) for a in data["fc_feats_array"]]
             att = [_to(a[pick], dev) for a in data["att_feats_array"]]
-            seq, seq_lp = ensemble_sample_beam(model_list, fc, att, {"beam_size": beam_size})[:2]
+            if beam_size == 1:
+                seq, seq_lp = ensemble_sample_greedy(model_list, fc, att)
+            else:
+                seq, seq_lp = ensemble_sample_beam(model_list, fc, att, {"beam_size": beam_size})[:2]
             log_probs = (seq_lp * (seq > 0).float()).sum(1).cpu().tolist()
             for k, sent in enumerate(decode_sequence(loader.get_vocab(), seq)):
                 entry = {"image_id": data["infos"][k]["id"], "caption": sent, "log_prob": log_probs[k]}

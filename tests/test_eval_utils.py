@@ -100,3 +100,64 @@ def test_eval_ensemble_matches_ensemble_beam():
     assert [p["caption"] for p in preds] == EU.decode_sequence(loader.vocab, seq)
     want_lp = (slp * (seq > 0).float()).sum(1).cpu()
     assert max(abs(p["log_prob"] - float(w)) for p, w in zip(preds, want_lp)) <= 1e-4
+
+
+# ---- against the restated oracle of the reference's drivers (oracle/eval_oracle.py) ---------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("beam_size,val_images_use,n_images,batch", [(3, 7, 7, 3), (1, 4, 7, 3), (3, -1, 5, 2), (1, 100, 5, 2)])
+def test_eval_split_matches_reference_driver_oracle(beam_size, val_images_use, n_images, batch):
+    """Mean loss, the prediction list (ids, captions, what gets popped) and both break conditions of eval_utils.py:66-265,
+    incl. the quirk that val_images_use = -1 stops after the first batch (`n >= -1`)."""
+    from oracle import eval_oracle as EO
+    from recurrent_fusion_network_b200 import eval_utils as EU
+    from recurrent_fusion_network_b200.criteria import ReviewNetEnsembleCriterion
+    from tests._gpu_util import build_model
+    cfg = O.tiny_config(2)
+    sd = O.make_state_dict(cfg, seed=1250, init_range=0.5, logit_scale=3.0, eos_bias=0.8)
+    m = build_model(cfg, sd)
+    crit = ReviewNetEnsembleCriterion(SimpleNamespace(use_label_smoothing=0, label_smoothing_epsilon=0.1, use_cuda=1))
+    kw = {"eval_split": "val", "val_images_use": val_images_use, "beam_size": beam_size, "language_eval": 0, "verbose": False,
+          "feature_type": "feat_array", "reason_weight": 10, "sample_max": 1}
+    loss, preds, _ = EU.eval_split(m, crit, FakeLoader(cfg, n_images, batch, 2, seed=3), kw)
+    want_loss, want_preds = EO.eval_split(sd, cfg, FakeLoader(cfg, n_images, batch, 2, seed=3), kw)
+    assert preds == want_preds
+    assert abs(loss - want_loss) <= 1e-4 * max(1.0, abs(want_loss))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("beam_size,num_images,n_images,batch", [(3, 5, 5, 2), (1, 5, 5, 2), (1, -1, 6, 3), (3, 2, 6, 3)])
+def test_eval_ensemble_beam_and_greedy_match_reference_driver_oracle(beam_size, num_images, n_images, batch):
+    """eval_ensemble (beam, eval_utils.py:387-719) and eval_ensemble_greedy (:729-975, what eval_ensemble.sh runs)."""
+    from oracle import eval_oracle as EO
+    from recurrent_fusion_network_b200 import eval_utils as EU
+    from tests._gpu_util import build_model
+    cfg = O.tiny_config(2)
+    sds = [O.make_state_dict(cfg, seed=s, init_range=0.5, logit_scale=3.0, eos_bias=0.8) for s in (1250, 1251, 1252)]
+    models = [build_model(cfg, sd) for sd in sds]
+    kw = {"eval_split": "test", "num_images": num_images, "beam_size": beam_size, "batch_size": batch, "verbose": False,
+          "language_eval": 0}
+    _, preds, _ = EU.eval_ensemble(models, FakeLoader(cfg, n_images, batch, 2, seed=5), kw)
+    want = EO.eval_ensemble(sds, cfg, FakeLoader(cfg, n_images, batch, 2, seed=5), kw)
+    assert [(p["image_id"], p["caption"]) for p in preds] == [(p["image_id"], p["caption"]) for p in want]
+    assert max(abs(p["log_prob"] - q["log_prob"]) for p, q in zip(preds, want)) <= 2e-4
+    if beam_size == 1:
+        _, preds_g, _ = EU.eval_ensemble_greedy(models, FakeLoader(cfg, n_images, batch, 2, seed=5), dict(kw, beam_size=7))
+        assert [p["caption"] for p in preds_g] == [p["caption"] for p in want]
+
+
+@pytest.mark.gpu
+def test_ensemble_greedy_full_size_two_models():
+    """Greedy logit-mean ensemble at reference sizes (two five-encoder models), tokens and log-probs vs the oracle."""
+    from oracle import eval_oracle as EO
+    from recurrent_fusion_network_b200.ensemble import ensemble_sample_greedy
+    from tests._gpu_util import LP_TOL, assert_tokens_match_with_tie_policy, build_model, cuda_list, maxdiff
+    cfg = O.RFNConfig()
+    sds = [O.make_state_dict(cfg, seed=1235 + i, sharpen=True) for i in range(2)]
+    fc, att = O.make_inputs(cfg, 4, seed=12)
+    models = [build_model(cfg, sd) for sd in sds]
+    torch.set_num_threads(16)
+    seq, slp = ensemble_sample_greedy(models, cuda_list(fc), cuda_list(att))
+    with torch.no_grad():
+        oseq, oslp = EO.ensemble_sample_greedy(sds, cfg, fc, att)
+    assert seq.shape == oseq.shape and torch.equal(seq.cpu(), oseq)
+    assert maxdiff(slp, oslp) <= LP_TOL

@@ -134,3 +134,37 @@ def test_weight_cache_equals_on_the_fly_split_and_tracks_weight_updates():
     m.weight_cache = False
     d_ref = decode()
     assert torch.equal(d[0], d_ref[0]) and torch.equal(d[1], d_ref[1]) and not torch.equal(d[1], c[1])
+
+
+@pytest.mark.parametrize("make_cfg,rows", [(lambda: O.config1(196), 256), (lambda: O.RFNConfig(), 256)], ids=["config1_n196", "full_j5"])
+def test_bf16_mode_logprobs_within_north_star_tolerance(make_cfg, rows):
+    """Engine mode 5 (north star: 'per-step log-probs within 2e-2 in bf16'): every large GEMM of the path as ONE bf16 MMA per
+    product on bf16 copies of the features / activations / weights.  Teacher-forced log-probs of 256 rows (reference-style
+    init) against the fp32 oracle, and the bf16 engine must actually have run."""
+    from recurrent_fusion_network_b200 import _capi
+    prev = _capi.lib().rfn_get_gemm_mode()
+    cfg = make_cfg()
+    sd = O.make_state_dict(cfg, seed=1234)
+    fc, att = O.make_inputs(cfg, rows, seed=41)
+    labels, masks, top = O.make_labels(cfg, rows, seed=42)
+    m = build_model(cfg, sd)
+    torch.set_num_threads(max(16, torch.get_num_threads()))
+    try:
+        _capi.check(_capi.lib().rfn_set_gemm_mode(5))
+        before = _capi.engine_launch_counts()
+        with torch.no_grad():
+            lp, rp = m(cuda_list(fc), cuda_list(att), labels.cuda())
+            torch.cuda.synchronize()
+        ran = {k: v - before[k] for k, v in _capi.engine_launch_counts().items()}
+        assert ran["tcgen05_2cta_persistent_bf16"] >= (cfg.num_review_steps_0 + cfg.num_review_steps) * cfg.J and \
+            ran["tcgen05_2cta_persistent_fp16x3"] == 0, ran
+        with torch.no_grad():
+            lp_o, rp_o = O.forward_xe(sd, cfg, fc, att, labels)
+        err = maxdiff(lp, lp_o)
+        assert err <= 2e-2, err
+        assert err > 1e-6          # it is a reduced-precision mode: bit-level agreement would mean the fp32 engine ran
+        tgt = lp.gather(2, labels[:, 1:lp.shape[1] + 1].cuda().unsqueeze(2)).squeeze(2)
+        tgt_o = lp_o.gather(2, labels[:, 1:lp.shape[1] + 1].unsqueeze(2)).squeeze(2)
+        assert maxdiff(tgt, tgt_o) <= 2e-2
+    finally:
+        _capi.check(_capi.lib().rfn_set_gemm_mode(prev))

@@ -217,7 +217,7 @@ def test_beam_batching_is_chunk_invariant():
         assert torch.equal(x, y)
 
 
-@pytest.mark.parametrize("beam", [1, 2, 5])
+@pytest.mark.parametrize("beam", [1, 2, 5, 10])
 def test_other_beam_widths(beam):
     cfg = O.tiny_config(2)
     sd = O.make_state_dict(cfg, seed=1247, init_range=0.5, logit_scale=3.0, eos_bias=0.8)
@@ -331,12 +331,17 @@ def test_max_beam_width_and_bad_arguments():
     fc, att = O.make_inputs(cfg, 3, seed=8)
     m = build_model(cfg, sd)
     with torch.no_grad():
-        seq, slp, ts, tp, _ = m.sample_beam(cuda_list(fc), cuda_list(att), {"beam_size": 8})
-        o = O.sample_beam(sd, cfg, fc, att, beam_size=8)
+        for beam in (8, 16):
+            seq, slp, ts, tp, _ = m.sample_beam(cuda_list(fc), cuda_list(att), {"beam_size": beam})
+            o = O.sample_beam(sd, cfg, fc, att, beam_size=beam)
+            assert torch.equal(seq.cpu(), o[0]) and maxdiff(slp, o[1]) <= LP_TOL
+            assert [t.shape for t in ts] == [t.shape for t in o[2]]
+        # the reference's DEFAULT beam width (sample_beam's opt.get('beam_size', 10), :353)
+        seq, slp, ts, tp, _ = m.sample_beam(cuda_list(fc), cuda_list(att), {})
+        o = O.sample_beam(sd, cfg, fc, att, beam_size=10)
         assert torch.equal(seq.cpu(), o[0]) and maxdiff(slp, o[1]) <= LP_TOL
-        assert [t.shape for t in ts] == [t.shape for t in o[2]]
         with pytest.raises(_capi.RfnError):
-            m.sample_beam(cuda_list(fc), cuda_list(att), {"beam_size": 9})
+            m.sample_beam(cuda_list(fc), cuda_list(att), {"beam_size": 17})
         with pytest.raises(_capi.RfnError):
             m.sample(cuda_list(fc)[:1], cuda_list(att), {})                      # wrong encoder count
         with pytest.raises(_capi.RfnError):
