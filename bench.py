@@ -164,9 +164,22 @@ def run_ours(args):
         dist.all_gather_into_tensor(out_l, pad_l)
         return out_s[:args.images], out_l[:args.images]
 
-    def step_resident():
+    def step_eager():
         seq, slp, *_ = model.beam_search(fc, att, BEAM, want_reason=True)
         return gather(seq, slp)
+
+    graphed = None
+    if args.graph:
+        # the same call captured once as a CUDA graph and replayed (graphs.GraphedBeamSearch): one launch per chunk instead of
+        # ~700 from the library's launch loop; the features stay where they are (the graph reads these very buffers)
+        from recurrent_fusion_network_b200.graphs import GraphedBeamSearch
+        graphed = GraphedBeamSearch(model, fc, att, BEAM, want_reason=True, warmup=1)
+
+    def step_resident():
+        if graphed is None:
+            return step_eager()
+        out = graphed()
+        return gather(out[0], out[1])
 
     def barrier():
         if world > 1:
@@ -196,6 +209,12 @@ def run_ours(args):
         sampler.start()
     ms_step, launches, out = timed(step_resident, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
+    eager = None
+    if graphed is not None:
+        launches = graphed.kernels_per_replay * args.steps * world   # kernels replayed inside the timed region
+        ms_eager, launches_eager, out_eager = timed(step_eager, max(1, min(2, args.steps)), 1)
+        eager = dict(ms_per_step=round(ms_eager, 3), value=round(args.images / (ms_eager / 1e3), 2),
+                     same_captions=bool(torch.equal(out_eager[0], out[0])))
     value = args.images / (ms_step / 1e3)
     seq_checksum = int(out[0].sum().item())
 
@@ -203,7 +222,7 @@ def run_ours(args):
     # (kernels timed one at a time: the encoder side streams are serialised for this pass only)
     _capi.check(_capi.lib().rfn_set_concurrency(0))
     _capi.profile_enable(True)
-    step_resident()
+    step_eager()
     torch.cuda.synchronize()
     prof = _capi.profile_read()
     _capi.profile_enable(False)
@@ -217,7 +236,8 @@ def run_ours(args):
     flops_att = 2.0 * A * sum(n * d for n, d, _ in ENC) * S0 * n_local
     #   with the tensor engine the scores are reduced in the GEMM epilogue, so the step reads A only (3.15 MB)
     uaa = sum(n * A for n, _, _ in ENC) if args.gemm_mode == 0 else sum(n * 4 for n, _, _ in ENC)
-    bytes_attn = (sum(n * d for n, d, _ in ENC) + uaa) * 4.0 * S0 * n_local
+    feat_bytes = 2.0 if args.gemm_mode == 5 else 4.0   # mode 5 streams the bf16 copy of the features
+    bytes_attn = (sum(n * d for n, d, _ in ENC) * feat_bytes + uaa * 4.0) * S0 * n_local
     g_ms, g_n = prof["gemm_att2att_stage1"]
     a_ms, a_n = prof["attention_step_stage1"]
     tf = flops_att / (g_ms / 1e3) / 1e12 if g_ms else 0.0
@@ -242,8 +262,8 @@ def run_ours(args):
                      peak_source=peaks["source"] + ", dense bf16 sustained; this engine computes in " + args_dtype(args))
     roof_attn = dict(kernel="attention_step_stage1", bound="hbm", achieved=round(gbs, 1), peak=peaks["hbm"], unit="GB/s",
                      frac=round(gbs / peaks["hbm"], 4), traffic=1.657e9,
-                     traffic_note="ncu capture of one launch (resnet encoder, 1024 images): 1.647 GB read + 0.009 GB written "
-                                  "vs 1.644 GB algorithmic (A read once)", launches=a_n,
+                     traffic_note="ncu capture of one launch (resnet encoder, 1024 images): 1.648 GB read + 0.011 GB written "
+                                  "vs 1.644 GB algorithmic (A read once); profiles/r2_attention_step_ncu.txt", launches=a_n,
                      avg_launch_ms=round(a_ms / max(1, a_n), 4), share_of_step=shares.get("attention_step_stage1"),
                      peak_source=peaks["source"])
     dominant = roof_gemm if g_ms >= a_ms else roof_attn
@@ -252,6 +272,7 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         del fc, att
+        graphed = None      # releases the graph's private pool (workspace + outputs) and its references to the features
         torch.cuda.empty_cache()
         hfc, hatt = make_features(n_local, device, seed=7 + rank, pinned_host=True)
         h2d = sum(t.numel() * 4 for t in hfc + hatt)
@@ -300,6 +321,11 @@ def run_ours(args):
         if world == 1:
             ens = ensemble_bench(model, device, timed)
 
+    # ---- BASELINE.json configs[0] on the GPU: latency of the small-batch greedy decode (eager vs CUDA graph) ----
+    cfg1 = None
+    if rank == 0 and world == 1 and args.train_steps > 0:
+        cfg1 = config1_bench(device, cpu=not args.no_cpu_baseline)
+
     # ---- next-row component: CIDEr-D self-critical reward, device vs the oracle port on the host ----
     ciderd = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -317,14 +343,14 @@ def run_ours(args):
                     config=dict(workload="BASELINE.json configs[2]: full 5-encoder RFNet, beam 3, "
                                          f"{args.images} synthetic images sharded over {world} GPU(s)",
                                 images=args.images, images_per_gpu=n_local, beam=BEAM, seq_length=L, vocab=9487,
-                                chunk_images=args.chunk, gemm_mode=args.gemm_mode,
+                                chunk_images=args.chunk, gemm_mode=args.gemm_mode, cuda_graph=bool(args.graph), eager=eager,
                                 tc_cluster=int(_capi.lib().rfn_get_tc_cluster()), cpu_affinity=str(numa),
                                 weights="reference-style random init, seed 1234",
                                 l2="per-step inputs (3.15 MB/image fp32 features) exceed the 126 MB L2",
                                 parity="fp32 mode; tests/test_gpu_parity.py vs the reference fixtures"),
                     clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=dominant,
                     roofline_attention=roof_attn, roofline_gemm=roof_gemm, kernel_time_shares=shares,
-                    cpu_baseline=cpu, xe_train=xe, rl_train=rl, ensemble=ens, ciderd_reward=ciderd,
+                    cpu_baseline=cpu, xe_train=xe, rl_train=rl, ensemble=ens, ciderd_reward=ciderd, config1_latency=cfg1,
                     seq_checksum=seq_checksum)
         emit(line)
     if world > 1:
@@ -516,6 +542,66 @@ def ensemble_bench(model, device, timed):
     return res
 
 
+def config1_bench(device, cpu=True):
+    """BASELINE.json configs[0]: single encoder (7x7x2048 attention map), greedy decode, batch 16, max_len 16 -- the
+    latency-bound corner of the path ('pure latency chain').  Reports the latency of one batch through
+    model.sample (eager: ~330 kernels launched from the library's C++ loop + one 4-byte read of T), the same call replayed
+    from a CUDA graph (graphs.GraphedSample) and, beside it, the oracle port on the host cores."""
+    from oracle import rfnet_oracle as O
+    from recurrent_fusion_network_b200 import _capi
+    from recurrent_fusion_network_b200.graphs import GraphedSample
+    from tests._gpu_util import build_model as build_from_sd
+    cfg = O.config1(49)
+    sd = O.make_state_dict(cfg, seed=1234, sharpen=True)
+    m = build_from_sd(cfg, sd)
+    fc, att = O.make_inputs(cfg, 16, seed=7)
+    fcg, attg = [t.to(device) for t in fc], [t.to(device) for t in att]
+    opt = {"sample_max": 1, "return_logprobs_all": False}
+
+    def lat(fn, reps):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    n0 = _capi.lib().rfn_launch_count()
+    with torch.no_grad():
+        seq = m.sample(fcg, attg, opt)[0]
+    kernels = int(_capi.lib().rfn_launch_count() - n0)
+    ms_eager = lat(lambda: m.sample(fcg, attg, opt), 50)
+    g = GraphedSample(m, fcg, attg, opt)
+    ms_graph = lat(lambda: g(), 200)
+    gseq, _, _, _, dT = g()
+    same = bool(torch.equal(gseq[:, :int(dT.item())], seq))
+    out = dict(workload="BASELINE.json configs[0]: J=1, 7x7x2048, greedy, batch 16, seq_length 16", kernels_per_batch=kernels,
+               eager_ms_per_batch=round(ms_eager, 4), graph_ms_per_batch=round(ms_graph, 4),
+               eager_captions_per_sec=round(16e3 / ms_eager, 1), graph_captions_per_sec=round(16e3 / ms_graph, 1),
+               us_per_kernel_eager=round(1e3 * ms_eager / kernels, 2), us_per_kernel_graph=round(1e3 * ms_graph / kernels, 2),
+               graph_equals_eager=same,
+               floor_note="weights streamed once per batch: 89.0 M parameters x 4 B = 356 MB -> 0.054 ms at the measured HBM peak; "
+                          "everything above that is the dependent chain of small kernels")
+    if cpu:
+        torch.set_num_threads(os.cpu_count() or 1)
+        with torch.no_grad():
+            O.sample(sd, cfg, fc, att)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                o = O.sample(sd, cfg, fc, att)
+            dt = (time.perf_counter() - t0) / 3
+        out["cpu_oracle_ms_per_batch"] = round(dt * 1e3, 1)
+        out["cpu_cores"] = os.cpu_count()
+        out["tokens_equal_oracle"] = bool(torch.equal(seq.cpu()[:, :o[0].shape[1]], o[0]))
+    del g, m
+    torch.cuda.empty_cache()
+    return out
+
+
 def ciderd_bench(device):
     """Self-critical reward of one RL step at config-4 size (250 rows = 50 images x 5, sample + greedy hypotheses, 5
     references per image, corpus document frequencies): device kernel vs the oracle port (= the reference scorer)."""
@@ -568,6 +654,9 @@ def args_dtype(args):
 # dram__bytes_read + write of ONE launch of the stage-1 projection GEMM from the committed `ncu --set full` captures (resnet
 # encoder, 1024 images), per engine mode
 GEMM_TRAFFIC = {
+    4: (1.725e9, "ncu capture of one launch of the split-fp16 kernel (gemm_h3_kernel<1,3>, resnet encoder, 1024 images): 1.718 GB read "
+                 "+ 0.007 GB written vs 1.648 GB algorithmic (the two fp16 pieces of A once + W once): 1.05x; tensor pipe 91.1 % active "
+                 "(profiles/r2_h3_score_ncu.txt)"),
     1: (1.718e9, "ncu capture of one launch (resnet encoder, 1024 images, persistent 2-CTA 3xTF32 kernel): 1.711 GB read + 0.007 GB "
                  "written vs 1.648 GB algorithmic (A once + W once); tensor pipe 97.7 % active (profiles/r1_gemm_tc2p_score_ncu.txt)"),
     3: (1.743e9, "ncu capture of the round-1 headline kernel as shipped (512 threads): 1.735 GB read + 0.008 GB written vs 1.648 GB "
@@ -652,6 +741,7 @@ def main():
     ap.add_argument("--train-steps", type=int, default=3, help="XE training steps timed for the secondary metric (0 = skip)")
     ap.add_argument("--cpu-images", type=int, default=24)
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--graph", type=int, default=1, help="1: the resident-feature step is replayed from a CUDA graph of the decode call")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -8,8 +8,16 @@
  *
  * Conventions
  *   - every pointer named d_* / every `const float*` tensor argument is a DEVICE pointer owned
- *     by the caller; the library never allocates or frees device memory and keeps no global
- *     mutable state besides the thread-local error string;
+ *     by the caller.  The path-level and operator-level entry points never allocate device memory
+ *     (all scratch comes from the caller's workspace).  Two exceptions, both outside the default
+ *     path: rfn_linear_f32_engine with engines 3 / 4 / 5 (an engine-test entry) takes its operand
+ *     scratch from the stream-ordered pool (cudaMallocAsync / cudaFreeAsync on `stream`);
+ *   - process-wide state the library DOES keep (all of it configuration or lazily created handles,
+ *     none of it data): the engine selection (rfn_set_gemm_mode, rfn_set_tc_cluster,
+ *     rfn_set_concurrency), per-device side streams + events for the encoder fork / join, the
+ *     kernels' one-time cudaFuncSetAttribute flags, the launch / engine counters and the optional
+ *     profile records; the error string is thread-local.  Calls on different streams from different
+ *     host threads are safe as long as they do not share a workspace; the engine selection is global;
  *   - `params` is a HOST array of device pointers to the model's fp32 tensors in the reference's
  *     state_dict registration order (misc/RecurrentFusionModel.py:153-184; 773 entries for the
  *     five-encoder model), Linear weights (out,in) row-major exactly as torch stores them;

@@ -4,6 +4,8 @@
 // A is streamed exactly once per CTA slice with 128-bit coalesced loads; reductions are
 // warp-shuffle based; no intermediate (rows,N,Ah) tensor is ever written (the reference
 // materialises three).
+#include <cuda_bf16.h>
+
 #include "rfn_internal.cuh"
 
 namespace rfn {
@@ -21,12 +23,15 @@ __device__ __forceinline__ float warp_max(float v) {
 
 constexpr int ATT_THREADS = 256;
 
+// A16 != nullptr (engine mode 5): the feature map is read as the bf16 copy the GEMM engine already made (row pitch lda16
+// elements), half the bytes of the fp32 map; everything else (scores, softmax, accumulation) stays fp32
 __global__ void __launch_bounds__(ATT_THREADS)
 attention_step_kernel(const float* __restrict__ A, const float* __restrict__ P,
                       const float* __restrict__ g, const float* __restrict__ w,
                       const float* __restrict__ d_wb, float* __restrict__ z, int ldz,
                       float* __restrict__ alpha, int N, int D, int Ah, int div,
-                      const float* __restrict__ scores, int nslices, size_t slice_stride) {
+                      const float* __restrict__ scores, int nslices, size_t slice_stride,
+                      const __nv_bfloat16* __restrict__ A16 = nullptr, int lda16 = 0) {
   extern __shared__ __align__(16) float smem[];
   float* s_g = smem;            // Ah
   float* s_w = smem + Ah;       // Ah
@@ -116,6 +121,24 @@ attention_step_kernel(const float* __restrict__ A, const float* __restrict__ P,
   const int per = (nvec + gridDim.y - 1) / gridDim.y;
   const int v0 = blockIdx.y * per;
   const int v1 = min(nvec, v0 + per);
+  if (A16) {
+    const uint2* Ar16 = reinterpret_cast<const uint2*>(A16 + (size_t)ra * N * lda16);
+    const int pitch = lda16 >> 2;   // uint2 (4 bf16) per feature row
+    for (int v = v0 + tid; v < v1; v += ATT_THREADS) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+      for (int n = 0; n < N; ++n) {
+        const uint2 q = __ldg(Ar16 + (size_t)n * pitch + v);
+        const float a0 = s_e[n];
+        acc.x = fmaf(a0, __uint_as_float(q.x << 16), acc.x);
+        acc.y = fmaf(a0, __uint_as_float(q.x & 0xffff0000u), acc.y);
+        acc.z = fmaf(a0, __uint_as_float(q.y << 16), acc.z);
+        acc.w = fmaf(a0, __uint_as_float(q.y & 0xffff0000u), acc.w);
+      }
+      *reinterpret_cast<float4*>(z + (size_t)r * ldz + v * 4) = acc;
+    }
+    return;
+  }
   const float4* Ar = reinterpret_cast<const float4*>(A + (size_t)ra * N * D);
   for (int v = v0 + tid; v < v1; v += ATT_THREADS) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -161,9 +184,10 @@ int attention_step(const float* A, const float* P, const float* g, const float* 
 }
 
 int attention_from_scores(const float* A, const float* scores, int nslices, const float* d_wb, float* z, int ldz,
-                          float* alpha, int rows, int N, int D, int div, cudaStream_t st) {
+                          float* alpha, int rows, int N, int D, int div, cudaStream_t st, const void* A_bf16, int lda_bf16) {
   ProfScope prof__(TAG_ATTN_SMALL, st);
-  RFN_CHECK_ARG(A && scores && d_wb && z, "attention_from_scores: null pointer");
+  RFN_CHECK_ARG((A || A_bf16) && scores && d_wb && z, "attention_from_scores: null pointer");
+  RFN_CHECK_ARG(!A_bf16 || (lda_bf16 % 4 == 0 && lda_bf16 >= D), "attention_from_scores: bf16 feature pitch %d", lda_bf16);
   RFN_CHECK_ARG(rows >= 0 && N > 0 && div >= 1 && D % 4 == 0 && ldz % 4 == 0, "attention_from_scores: bad shape");
   if (rows == 0) return RFN_OK;
   int dsplit = 1;
@@ -173,7 +197,8 @@ int attention_from_scores(const float* A, const float* scores, int nslices, cons
   if (smem > 48 * 1024)
     RFN_CUDA(cudaFuncSetAttribute(attention_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   attention_step_kernel<<<dim3(rows, dsplit), ATT_THREADS, smem, st>>>(A, nullptr, nullptr, nullptr, d_wb, z, ldz, alpha, N, D, 0,
-                                                                       div, scores, nslices, (size_t)rows * N);
+                                                                       div, scores, nslices, (size_t)rows * N,
+                                                                       (const __nv_bfloat16*)A_bf16, lda_bf16);
   RFN_LAUNCH_CHECK();
   return RFN_OK;
 }

@@ -130,8 +130,10 @@ int attention_step(const float* A, const float* P, const float* g, const float* 
                    float* z, int ldz, float* alpha, int rows, int N, int D, int Ah, int div,
                    cudaStream_t st);
 // same, from pre-reduced scores e[r,n] (without the att_h_2_out bias) produced by the fused GEMM epilogue
+// A_bf16 != nullptr: the context sum reads this bf16 copy of A (row pitch lda_bf16 elements) instead of the fp32 map
 int attention_from_scores(const float* A, const float* scores, int nslices, const float* d_wb, float* z, int ldz,
-                          float* alpha, int rows, int N, int D, int div, cudaStream_t st);
+                          float* alpha, int rows, int N, int D, int div, cudaStream_t st, const void* A_bf16 = nullptr,
+                          int lda_bf16 = 0);
 int lstm_cell(const float* G, const float* c_prev, float* h_out, float* c_out, float* h_out2,
               int ldh2, float* h_out3, int ldh3, int rows, int R, cudaStream_t st);
 int embed_gather_i64(const int64_t* tok, int ld_tok, const float* embed, float* x, int rows, int E,

@@ -317,7 +317,10 @@ static int attention_module(const rfn_dims& d, const float* h, int ldh, const fl
       RFN_TRY(gemm_h3(hg, st));
     }
     TagScope ts(tag_attn);
-    return attention_from_scores(Afeat, P, tc_score_slices(A), v_b, z, ldz, nullptr, rows, N, D, 1, st);
+    // engine mode 5: the weighted sum streams the bf16 copy of the features the GEMM just used (half the bytes)
+    const bool a16 = h3_bf16() && feat_split != nullptr;
+    return attention_from_scores(Afeat, P, tc_score_slices(A), v_b, z, ldz, nullptr, rows, N, D, 1, st,
+                                 a16 ? feat_split->p0 : nullptr, a16 ? feat_split->ld : 0);
   }
   if (gemm_mode() >= 1 && rows * N >= 128 && gemm_tc_supported(pa)) {
     {

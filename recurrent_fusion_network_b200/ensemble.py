@@ -8,7 +8,6 @@ import torch
 
 from . import _capi
 from ._capi import check, lib, ptr, ptr_array, stream
-from .model import _WS
 
 
 def model_ensemble_feat_array_one_step(model_list, xt_list, state_list, thought_vector_list):
@@ -53,7 +52,7 @@ def ensemble_sample_beam(models, fc_feats, att_feats, opt={}):
                 TVc, _, h, c = model._thought_vectors([f[k0:k1] for f in fc], [a[k0:k1] for a in att], n, want_reason=False)
                 tv.append(TVc); hs.append(h); cs.append(c)
             nbytes = lib().rfn_ensemble_workspace_bytes(C.byref(m0._dims), M, n, beam)
-            ws = _WS.get(nbytes, dev)
+            ws = m0._wsobj.get(nbytes, dev)   # after the last _thought_vectors call above: the same buffer may be handed out
             pm = (C.POINTER(C.c_void_p) * M)(*[C.cast(model._params(), C.POINTER(C.c_void_p)) for model in models])
             check(lib().rfn_ensemble_decode_beam(C.byref(m0._dims), M, pm, ptr_array(tv), ptr_array(hs), ptr_array(cs), n,
                                                  beam, ptr(seq[k0:k1]), ptr(slp[k0:k1]), ptr(done_seq[k0:k1]),
@@ -86,7 +85,7 @@ def ensemble_sample_greedy(models, fc_feats, att_feats, opt={}):
             TVc, _, h, c = model._thought_vectors(fc, att, rows, want_reason=False)
             tv.append(TVc); hs.append(h); cs.append(c)
         nbytes = lib().rfn_ensemble_workspace_bytes(C.byref(m0._dims), M, rows, 1)
-        ws = _WS.get(nbytes, dev)
+        ws = m0._wsobj.get(nbytes, dev)
         pm = (C.POINTER(C.c_void_p) * M)(*[C.cast(model._params(), C.POINTER(C.c_void_p)) for model in models])
         check(lib().rfn_ensemble_decode_greedy(C.byref(m0._dims), M, pm, ptr_array(tv), ptr_array(hs), ptr_array(cs), rows,
                                                ptr(seq), ptr(slp), ptr(dT), ptr(ws), ws.numel(), stream()),

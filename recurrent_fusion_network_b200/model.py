@@ -70,7 +70,7 @@ class _Workspace:
         return self.buf
 
 
-_WS = _Workspace()
+_WS = _Workspace()   # operator-level wrappers only (AttentionModelCore used on its own); every model owns its workspace
 
 
 # --------------------------------------------------------------------------------------------------
@@ -392,6 +392,7 @@ class RecurrentFusionModel(nn.Module):
                                      self.top_words_count, self.num_review_steps_0, self.num_review_steps,
                                      self.seq_length)
         self._pcache = None
+        self._wsobj = _Workspace()   # this model's scratch for the C ABI (grow-only; swapped by graphs.GraphedBeamSearch)
 
     def init_weights(self):  # :188-196
         self.embed.weight.data.uniform_(-_INIT, _INIT)
@@ -470,7 +471,7 @@ class RecurrentFusionModel(nn.Module):
         n = lib().rfn_workspace_bytes(C.byref(self._dims), rows, dec_rows)
         if n == 0:
             raise _capi.RfnError("rfn_workspace_bytes: " + lib().rfn_last_error().decode())
-        return _WS.get(n, device)
+        return self._wsobj.get(n, device)
 
     def _thought_vectors(self, fc, att, rows, init_state=None, want_reason=True, dec_rows=None, want_tv=False):
         """Stages 1-2 on `rows` feature rows -> TVc (rows,S1,R), reason (J+1,rows,K) or None, h, c (rows,R)."""
@@ -567,30 +568,41 @@ class RecurrentFusionModel(nn.Module):
             from . import training
             return training.sample_with_grad(self, fc_feats, att_feats, opt)
         self._inference_guard("sample")
-        fc, att, rows = self._check_feats(fc_feats, att_feats)
-        dev = fc[0].device
-        L, V1 = self.seq_length, self.vocab_size + 1
-        uniforms = None
-        if not sample_max:
-            uniforms = opt.get("uniforms")
-            if uniforms is None:   # the reference draws on the CPU RNG (:624-631); we take torch's CUDA generator
-                uniforms = torch.rand(rows, L, device=dev, dtype=torch.float32)
-            uniforms = _f32c(uniforms.to(dev))
-        seq = torch.empty(rows, L, dtype=torch.int64, device=dev)
-        slp = torch.empty(rows, L, dtype=torch.float32, device=dev)
-        want_all = opt.get("return_logprobs_all", True)
-        lp_all = torch.empty(rows, L + 1, V1, dtype=torch.float32, device=dev) if want_all else None
-        dT = torch.zeros(1, dtype=torch.int32, device=dev)
-        TVc, reason, h, c = self._thought_vectors(fc, att, rows)
-        ws = self._ws(rows, rows, dev)
-        check(lib().rfn_decode_sample(C.byref(self._dims), self._params(), ptr(TVc), ptr(h), ptr(c), rows,
-                                      ptr(uniforms), float(temperature), ptr(seq), ptr(slp), ptr(lp_all), ptr(dT),
-                                      ptr(ws), ws.numel(), stream()), "rfn_decode_sample")
+        seq, slp, lp_all, reason, dT = self.sample_device(fc_feats, att_feats, opt)
+        want_all = lp_all is not None
         T = int(dT.item())   # the reference's early break (:645) -- one 4-byte read per call
         if T == 0:
             raise RuntimeError("sample(): every row emitted <eos> at t=1; the reference fails here too "
                                "(torch.cat of an empty list, misc/RecurrentFusionModel.py:655)")
         return seq[:, :T], slp[:, :T], (lp_all[:, :T + 1] if want_all else None), self._reason_list(reason)
+
+    def sample_device(self, fc_feats, att_feats, opt={}):
+        """The device part of sample() (greedy / multinomial), free of host synchronisation and therefore capturable in a
+        CUDA graph: full-width (rows, L) tokens / log-probs, (rows, L + 1, V1) log-prob table (or None), reason_pred
+        (J+1, rows, K) and a device int32 T = number of valid columns (the reference's early break, :645)."""
+        sample_max = opt.get("sample_max", 1)
+        temperature = opt.get("temperature", 1.0)
+        with torch.no_grad():
+            fc, att, rows = self._check_feats(fc_feats, att_feats)
+            dev = fc[0].device
+            L, V1 = self.seq_length, self.vocab_size + 1
+            uniforms = None
+            if not sample_max:
+                uniforms = opt.get("uniforms")
+                if uniforms is None:   # the reference draws on the CPU RNG (:624-631); we take torch's CUDA generator
+                    uniforms = torch.rand(rows, L, device=dev, dtype=torch.float32)
+                uniforms = _f32c(uniforms.to(dev))
+            seq = torch.empty(rows, L, dtype=torch.int64, device=dev)
+            slp = torch.empty(rows, L, dtype=torch.float32, device=dev)
+            want_all = opt.get("return_logprobs_all", True)
+            lp_all = torch.empty(rows, L + 1, V1, dtype=torch.float32, device=dev) if want_all else None
+            dT = torch.zeros(1, dtype=torch.int32, device=dev)
+            TVc, reason, h, c = self._thought_vectors(fc, att, rows)
+            ws = self._ws(rows, rows, dev)
+            check(lib().rfn_decode_sample(C.byref(self._dims), self._params(), ptr(TVc), ptr(h), ptr(c), rows,
+                                          ptr(uniforms), float(temperature), ptr(seq), ptr(slp), ptr(lp_all), ptr(dT),
+                                          ptr(ws), ws.numel(), stream()), "rfn_decode_sample")
+        return seq, slp, lp_all, reason, dT
 
     def _device(self):
         return next(self.parameters()).device

@@ -168,3 +168,34 @@ def test_bf16_mode_logprobs_within_north_star_tolerance(make_cfg, rows):
         assert maxdiff(tgt, tgt_o) <= 2e-2
     finally:
         _capi.check(_capi.lib().rfn_set_gemm_mode(prev))
+
+
+def test_graphed_decode_equals_eager_decode():
+    """graphs.GraphedBeamSearch / GraphedSample: one CUDA-graph replay == the eager call (same kernels, same bits), also after
+    new inputs are loaded into the static buffers, and the model's own workspace is left untouched."""
+    from recurrent_fusion_network_b200 import _capi
+    from recurrent_fusion_network_b200.graphs import GraphedBeamSearch, GraphedSample
+    _capi.check(_capi.lib().rfn_set_gemm_mode(4))
+    cfg = O.config1(49)
+    sd = O.make_state_dict(cfg, seed=1234, sharpen=True)
+    m = build_model(cfg, sd)
+    fa, aa = [cuda_list(t) for t in O.make_inputs(cfg, 90, seed=51)]
+    fb, ab = [cuda_list(t) for t in O.make_inputs(cfg, 90, seed=52)]
+    with torch.no_grad():
+        ea = [t.clone() for t in m._beam_tensors(fa, aa, 90, 3)[:2]]
+        eb = [t.clone() for t in m._beam_tensors(fb, ab, 90, 3)[:2]]
+    g = GraphedBeamSearch(m, [t.clone() for t in fa], [t.clone() for t in aa], beam_size=3)
+    n0 = _capi.lib().rfn_launch_count()
+    ga = [t.clone() for t in g()[:2]]
+    gb = [t.clone() for t in g(fb, ab)[:2]]
+    assert _capi.lib().rfn_launch_count() == n0          # replays issue no launches from the library
+    assert torch.equal(ga[0], ea[0]) and torch.equal(ga[1], ea[1])
+    assert torch.equal(gb[0], eb[0]) and torch.equal(gb[1], eb[1])
+    # config 1 as BASELINE.json states it: greedy, batch 16
+    f16, a16 = [t[:16].contiguous() for t in fa], [t[:16].contiguous() for t in aa]
+    with torch.no_grad():
+        s, sl, la, _ = m.sample(f16, a16, {"sample_max": 1})
+    gs = GraphedSample(m, f16, a16, {"sample_max": 1, "return_logprobs_all": False})
+    seq, slp, _, _, dT = gs()
+    T = int(dT.item())
+    assert T == s.shape[1] and torch.equal(seq[:, :T], s) and torch.equal(slp[:, :T], sl)
