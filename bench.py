@@ -509,14 +509,42 @@ def rl_train_bench(model, device, world, rank, steps, timed):
         return box[0], box[0]
 
     ms, launches, _ = timed(step, steps, 3)
+    # the same iteration without host round trips, replayed from CUDA graphs (training.GraphedRLStep): stages 1-2 once, no-tape
+    # device decodes for the sampled and the baseline tokens, CIDEr-D on the device, teacher-forced taped decoder, backward | Adam
+    from recurrent_fusion_network_b200 import training as TR
+    graphed = {}
+    u = torch.rand(rows, L, device=device)
+    model.train()
+    for name, dd in (("as_written", 1), ("deduplicated", spi)):
+        model.dedup_rows = dd
+        opt_g = FusedAdam(params, lr=5e-5, weight_decay=1e-5, grad_clip=1.0, capturable=True, grad_scale=1.0 / world)
+        gs = TR.GraphedRLStep(model, crit, opt_g, fc, att, u, top, gts, table, ropt, spi, 10.0, entropy_reg=0.0, warmup=2,
+                              grad_sync=D.OverlappedGradSync(params) if world > 1 else None)
+
+        def gstep(gs=gs):
+            u.uniform_()                      # fresh uniforms every iteration, drawn on the device
+            l = gs(uniforms=u)
+            return l, l
+        ms_g, _, _ = timed(gstep, steps, 2)
+        graphed[name] = dict(value=round(rows * world / (ms_g / 1e3), 1), ms_per_step=round(ms_g, 2), loss=round(float(gs.loss), 4),
+                             mean_reward=round(float(gs.reward[:, 0].mean()), 4))
+        del gs, opt_g
+        torch.cuda.empty_cache()
+    model.dedup_rows = 1
     model.eval()
     for p in params:
         p.grad = None
-    return dict(metric="rl_train_samples_per_sec", value=round(rows * world / (ms / 1e3), 1), unit="sampled captions/s",
-                ms_per_step=round(ms, 2), rows_per_gpu=rows, sampled_length=box[1], loss=round(float(box[0]), 4),
-                gpu_launches_per_step=launches // max(1, steps),
-                note="BASELINE.json configs[3]; eager per-op autograd (the sampling loop reads one flag per step back to the "
-                     "host as the reference's early break does); reward scored on the device")
+    ga = graphed["as_written"]
+    return dict(metric="rl_train_samples_per_sec", value=ga["value"], unit="sampled captions/s", ms_per_step=ga["ms_per_step"],
+                api="training.GraphedRLStep: sample + greedy baseline + CIDEr-D reward + criterion + backward (gradient all-reduce "
+                    "overlapped inside) | mean + clamp + Adam, replayed from CUDA graphs",
+                deduplicated=graphed["deduplicated"], graph_loss=ga["loss"], mean_reward=ga["mean_reward"],
+                eager=dict(value=round(rows * world / (ms / 1e3), 1), ms_per_step=round(ms, 2), sampled_length=box[1],
+                           loss=round(float(box[0]), 4), gpu_launches_per_step=launches // max(1, steps),
+                           note="the reference-shaped iteration issued op by op (model.sample with the tape on reads one flag per "
+                                "step back to the host as the reference's early break does)"),
+                rows_per_gpu=rows,
+                note="BASELINE.json configs[3]: 50 images x 5 multinomial samples + greedy baseline per GPU; reward scored on the device")
 
 
 def ensemble_bench(model, device, timed):

@@ -168,6 +168,35 @@ def compute_reward(gen_result: torch.Tensor, greedy_res: torch.Tensor, gts, tabl
             for ng in seen:
                 df[ng] += 1
         table = DocumentFrequency(df, 2 * rows, dev)
+    return compute_reward_packed(gen_result, greedy_res, refs, n_refs, table, opt, seq_per_img)
+
+
+def pack_references_static(gts, n_images: int, max_refs: int, max_len: int):
+    """Host side of compute_reward for a CUDA-graph replay: references packed into FIXED-shape numpy arrays
+    (n_images, max_refs, max_len) / (n_images,), to be copied into the graph's static device buffers."""
+    if len(gts) != n_images:
+        raise ValueError(f"expected references for {n_images} images, got {len(gts)}")
+    refs = np.zeros((n_images, max_refs, max_len), dtype=np.int32)
+    n_refs = np.zeros(n_images, dtype=np.int32)
+    for i, g in enumerate(gts):
+        if len(g) > max_refs:
+            raise ValueError(f"image {i} has {len(g)} references, the graph was captured for at most {max_refs}")
+        n_refs[i] = len(g)
+        for j, r in enumerate(g):
+            r = _first_zero(list(map(int, r)))
+            if len(r) >= max_len and r[-1] != 0:
+                raise ValueError(f"reference longer than {max_len - 1} tokens")
+            refs[i, j, :min(len(r), max_len)] = r[:max_len]
+    return refs, n_refs
+
+
+def compute_reward_packed(gen_result, greedy_res, refs, n_refs, table: DocumentFrequency, opt, seq_per_img):
+    """The device part of compute_reward (no host work, no synchronisation: capturable in a CUDA graph): references already
+    packed on the device (pack_references), a fixed document-frequency table."""
+    rows, T = gen_result.shape
+    dev = gen_result.device
+    hyp = torch.cat([gen_result, greedy_res], 0).to(torch.int32).contiguous()
+    hyp_img = ((torch.arange(2 * rows, device=dev) % rows) // seq_per_img).to(torch.int32)
     scores = ciderd_scores(hyp, hyp_img, refs, n_refs, table)
     reward = torch.empty(rows, T, dtype=torch.float32, device=dev)
     check(lib().rfn_ciderd_reward_f32(ptr(scores), rows, T, float(getattr(opt, "cider_weight", 1.0)),

@@ -154,6 +154,150 @@ def rl_criterion(crit, input, seq, reward, logprobs_all, entropy_reg, top_pred, 
 
 
 
+def _decode_tokens(model, TVc, h, c, uniforms, temperature):
+    """Tokens of a greedy (uniforms None) or multinomial decode from given stage-2 outputs, all on the device and without
+    gradients (rfn_decode_sample): seq (rows, L) int64 with finished rows zeroed (:647), T on the device."""
+    import ctypes as C
+    from ._capi import check, lib, ptr, stream
+    rows, dev, L = h.shape[0], h.device, model.seq_length
+    seq = torch.empty(rows, L, dtype=torch.int64, device=dev)
+    slp = torch.empty(rows, L, dtype=torch.float32, device=dev)
+    dT = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = model._ws(rows, rows, dev)
+    check(lib().rfn_decode_sample(C.byref(model._dims), model._params(), ptr(TVc), ptr(h), ptr(c), rows, ptr(uniforms),
+                                  float(temperature), ptr(seq), ptr(slp), None, ptr(dT), ptr(ws), ws.numel(), stream()),
+          "rfn_decode_sample")
+    return seq, dT
+
+
+def rl_forward_loss(model, crit, fc_feats, att_feats, uniforms, reward_fn, top_true, reason_weight, entropy_reg=0.0,
+                    temperature=1.0):
+    """One self-critical iteration's forward (train_rl.py:150-169) without any host round trip:
+
+      stages 1-2 with the tape on, ONCE                      (the reference runs them again for the greedy baseline,
+                                                              get_rewards.py:119-124, on the same rows)
+      multinomial decode + greedy baseline decode, no tape   (rfn_decode_sample on the detached thought vectors; the sampled
+                                                              tokens are what :622-635 draws, given `uniforms`)
+      reward = reward_fn(sampled, greedy) on the device      (reward.compute_reward_packed)
+      teacher-forced taped decoder over the SAMPLED tokens   -> the log-probs the reference's sample() carries with grad
+      ReviewNetRewardCriterion                               (misc/utils.py:50-84)
+
+    Feeding the masked tokens (0 after <eos>) instead of the raw ones (:637 vs :647) changes only positions the criterion
+    masks out (mask0 = seq > 0 for the entropy term, its right shift for the sampled-token term), so the loss and every
+    gradient equal those of the reference-shaped step (tests/test_gpu_training.py).  Fixed length L: capturable.
+    Needs drop_prob_lm inactive (a no-tape decode cannot replay the taped pass's dropout masks).
+    Returns (loss, seq (rows, L), greedy (rows, L), reward (rows, L))."""
+    if model._dropout_active(model.drop_prob_lm):
+        raise RuntimeError("rl_forward_loss needs drop_prob_lm = 0 in training mode (the shipped RL scripts); use "
+                           "model.sample(..., {'sample_max': 0}) + the criterion for the general case")
+    fc, att, rows = model._check_feats(fc_feats, att_feats)
+    if getattr(model, "unique_feature_rows", False) and int(getattr(model, "dedup_rows", 1) or 1) > 1:
+        rows *= int(model.dedup_rows)
+    L = model.seq_length
+    TVc, reason_pred, state = _stages(model, fc, att)
+    with torch.no_grad():
+        TVd = TVc.detach().contiguous()
+        hd, cd = state[0].detach().squeeze(0).contiguous(), state[1].detach().squeeze(0).contiguous()
+        seq, _ = _decode_tokens(model, TVd, hd, cd, uniforms.to(TVd.device).float().contiguous(), temperature)
+        greedy, _ = _decode_tokens(model, TVd, hd, cd, None, 1.0)
+        reward = reward_fn(seq, greedy)
+        tokens = torch.cat([torch.zeros(rows, 1, dtype=torch.int64, device=seq.device), seq[:, :L - 1]], 1)
+    xts = AG.EmbedFn.apply(tokens.t().reshape(-1), model.embed.weight).view(L, rows, -1).unbind(0)
+    lps, slps = [], []
+    for i in range(L):
+        lp, state = _step(model, None, TVc, state, xt=xts[i])
+        lps.append(lp)
+        slps.append(AG.GatherColsFn.apply(lp, seq[:, i].contiguous()))
+    lp_all = torch.stack(lps, 1).contiguous()
+    slp = torch.stack(slps, 1)
+    loss = rl_criterion(crit, slp, seq, reward, lp_all, entropy_reg, [r.squeeze() for r in reason_pred], top_true, reason_weight)
+    return loss, seq, greedy, reward
+
+
+class GraphedRLStep:
+    """One self-critical RL iteration (train_rl.py:150-191: sample with grad, greedy baseline, CIDEr-D reward, criterion,
+    backward, clip_gradient, Adam) replayed from CUDA graphs: rl_forward_loss + backward in one graph (with the bucketed
+    gradient all-reduce captured inside when grad_sync is given), the fused clamp + Adam in a second.  Per call the new
+    inputs -- features, uniforms, top-word targets and the references packed to a fixed (n_images, max_refs, max_ref_len)
+    shape on the host -- are copied into static buffers; nothing is read back."""
+
+    def __init__(self, model, crit, optimizer, fc, att, uniforms, top_true, gts, table, reward_opt, seq_per_img, reason_weight,
+                 entropy_reg=0.0, temperature=1.0, max_refs=5, max_ref_len=None, warmup=2, grad_sync=None):
+        from . import reward as RW
+        if not all(g.get("capturable") for g in optimizer.param_groups):
+            raise RuntimeError("GraphedRLStep needs FusedAdam(capturable=True)")
+        self.model, self.crit, self.opt = model, crit, optimizer
+        self.reason_weight, self.entropy_reg, self.temperature = float(reason_weight), float(entropy_reg), float(temperature)
+        self.table, self.ropt, self.spi = table, reward_opt, int(seq_per_img)
+        self.fc = [f.clone() for f in fc]
+        self.att = [a.clone() for a in att]
+        self.uniforms, self.top = uniforms.clone().float(), top_true.clone()
+        self.n_images = len(gts)
+        self.max_refs = max(max_refs, max(len(g) for g in gts))
+        self.max_ref_len = max_ref_len or min(RW.MAXLEN, model.seq_length + 2)
+        dev = self.fc[0].device
+        r, n = RW.pack_references_static(gts, self.n_images, self.max_refs, self.max_ref_len)
+        self.refs, self.n_refs = torch.from_numpy(r).to(dev), torch.from_numpy(n).to(dev)
+        self.loss = self.seq = self.greedy = self.reward = None
+        from .model import _Workspace
+        self._ws = _Workspace()            # the no-tape decodes' scratch: private, the graph holds raw pointers into it
+        saved_ws, model._wsobj = model._wsobj, self._ws
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            optimizer.init_state()
+            with torch.cuda.stream(side):
+                for _ in range(max(1, warmup)):
+                    self._fwd_bwd()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self.g_fb = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_fb):
+                if grad_sync is not None:
+                    grad_sync.install()
+                self.loss, self.seq, self.greedy, self.reward = self._fwd_bwd()
+                if grad_sync is not None:
+                    grad_sync.finish()
+            if grad_sync is not None:
+                grad_sync.remove()
+            self.g_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_opt, pool=self.g_fb.pool()):
+                optimizer.step()
+        finally:
+            model._wsobj = saved_ws
+
+    def _reward(self, seq, greedy):
+        from . import reward as RW
+        return RW.compute_reward_packed(seq, greedy, self.refs, self.n_refs, self.table, self.ropt, self.spi)[0]
+
+    def _fwd_bwd(self):
+        self.opt.zero_grad(set_to_none=True)
+        loss, seq, greedy, reward = rl_forward_loss(self.model, self.crit, self.fc, self.att, self.uniforms, self._reward, self.top,
+                                                    self.reason_weight, self.entropy_reg, self.temperature)
+        loss.backward()
+        return loss.detach(), seq, greedy, reward
+
+    def __call__(self, fc=None, att=None, uniforms=None, top_true=None, gts=None):
+        """Replays the iteration on new data (same shapes); returns the loss tensor (device, overwritten by the next call);
+        .seq / .greedy / .reward hold the sampled tokens, the baseline tokens and the rewards of the replay."""
+        from . import _capi, reward as RW
+        if fc is not None:
+            for d, s in zip(self.fc + self.att, list(fc) + list(att)):
+                d.copy_(s, non_blocking=True)
+        if uniforms is not None:
+            self.uniforms.copy_(uniforms, non_blocking=True)
+        if top_true is not None:
+            self.top.copy_(top_true, non_blocking=True)
+        if gts is not None:
+            r, n = RW.pack_references_static(gts, self.n_images, self.max_refs, self.max_ref_len)
+            self.refs.copy_(torch.from_numpy(r), non_blocking=False)
+            self.n_refs.copy_(torch.from_numpy(n), non_blocking=False)
+        self.g_fb.replay()
+        self.g_opt.replay()
+        _capi.WEIGHTS_EPOCH[0] += 1
+        return self.loss
+
+
 class GraphedXEStep:
     """One XE training step (train.py:154-163: zero_grad, forward, criterion, backward, clip_gradient, Adam) captured as
     CUDA graphs and replayed: the eager step issues ~2,600 kernels from Python and is bound by the host, not the device.

@@ -342,3 +342,118 @@ def test_unique_feature_rows_equal_replicated_rows():
     assert abs(out[True][0] - out[False][0]) <= 1e-6 * max(1.0, abs(out[False][0]))
     for k in out[True][1]:
         assert maxdiff(out[True][1][k], out[False][1][k]) <= 1e-6 * (float(out[False][1][k].abs().max()) + 1e-6) + 1e-8, k
+
+
+def _pseudo_reward(L):
+    """A deterministic stand-in for the CIDEr-D reward: a function of the sampled / greedy tokens only."""
+    def fn(seq, greedy):
+        s = torch.nn.functional.pad(seq, (0, L - seq.shape[1])) if seq.shape[1] < L else seq
+        g = torch.nn.functional.pad(greedy, (0, L - greedy.shape[1])) if greedy.shape[1] < L else greedy
+        r = ((s.sum(1) % 7).float() - (g.sum(1) % 5).float()) * 0.25
+        return r.unsqueeze(1).expand(seq.shape[0], L).contiguous()
+    return fn
+
+
+def test_rl_forward_loss_equals_the_reference_shaped_step():
+    """training.rl_forward_loss (stages once, no-tape device decodes for the sampled and the greedy tokens, teacher-forced
+    taped decoder over the sampled tokens, fixed length) == the reference-shaped step (model.sample with the tape on and the
+    per-step early break, train_rl.py:160-169): same tokens, loss and gradients, with shared uniforms."""
+    from recurrent_fusion_network_b200 import training as T
+    from recurrent_fusion_network_b200.criteria import ReviewNetRewardCriterion
+    cfg = O.tiny_config(2)
+    sd = O.make_state_dict(cfg, seed=1250, init_range=0.5, logit_scale=3.0, eos_bias=0.8)
+    rows, L = 12, cfg.seq_length
+    fc, att = O.make_inputs(cfg, rows, seed=8)
+    _, _, top = O.make_labels(cfg, rows, seed=3)
+    u = torch.rand(rows, L, generator=torch.Generator().manual_seed(4)).cuda()
+    rl = ReviewNetRewardCriterion(SimpleNamespace(use_label_smoothing=0, label_smoothing_epsilon=0.1))
+    reward_fn = _pseudo_reward(L)
+    # (a) reference-shaped
+    ma = build_model(cfg, sd).train()
+    s, sl, la, rp = ma.sample(cuda_list(fc), cuda_list(att), {"sample_max": 0, "uniforms": u})
+    with torch.no_grad():
+        ma.eval()
+        greedy = ma.sample(cuda_list(fc), cuda_list(att), {"sample_max": 1})[0]
+        ma.train()
+        reward = reward_fn(s, greedy)[:, :s.shape[1]].contiguous()
+    loss_a = rl(sl, s, reward, la, 0.01, rp, top.cuda(), 10.0, None, SimpleNamespace(use_ppo=0))
+    loss_a.backward()
+    # (b) sync-free
+    mb = build_model(cfg, sd).train()
+    loss_b, seq_b, greedy_b, reward_b = T.rl_forward_loss(mb, rl, cuda_list(fc), cuda_list(att), u, reward_fn, top.cuda(), 10.0, 0.01)
+    loss_b.backward()
+    Ta = s.shape[1]
+    assert torch.equal(seq_b[:, :Ta], s) and int(seq_b[:, Ta:].abs().sum()) == 0
+    assert torch.equal(greedy_b[:, :greedy.shape[1]], greedy)
+    assert abs(float(loss_a) - float(loss_b)) <= 1e-5 * max(1.0, abs(float(loss_a)))
+    for (k, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+        ga = pa.grad if pa.grad is not None else torch.zeros_like(pa)
+        gb = pb.grad if pb.grad is not None else torch.zeros_like(pb)
+        assert maxdiff(ga, gb) <= 2e-5 * (float(ga.abs().max()) + 1e-6) + 1e-7, k
+
+
+def test_graphed_rl_step_matches_eager_steps():
+    """training.GraphedRLStep (sample + baseline + CIDEr-D reward + criterion + backward | clamp + Adam, two CUDA graphs) ==
+    the same iteration issued eagerly, over three iterations with fresh features / uniforms / references."""
+    from recurrent_fusion_network_b200 import reward as RW, training as T
+    from recurrent_fusion_network_b200.criteria import ReviewNetRewardCriterion
+    from recurrent_fusion_network_b200.optim import FusedAdam
+    cfg = O.tiny_config(2)
+    sd = O.make_state_dict(cfg, seed=1250, init_range=0.5, logit_scale=3.0, eos_bias=0.8)
+    imgs, spi, L = 4, 3, cfg.seq_length
+    rows = imgs * spi
+    rl = ReviewNetRewardCriterion(SimpleNamespace(use_label_smoothing=0, label_smoothing_epsilon=0.1))
+    ropt = SimpleNamespace(cider_weight=1.0, bleu4_weight=0, spice_weight=0, use_baseline=1, use_ppo=0)
+
+    def batch(seed):
+        g = torch.Generator().manual_seed(seed)
+        fc, att = O.make_inputs(cfg, imgs, seed=seed)
+        fc = [f.repeat_interleave(spi, 0).cuda() for f in fc]
+        att = [a.repeat_interleave(spi, 0).cuda() for a in att]
+        u = torch.rand(rows, L, generator=g).cuda()
+        _, _, top = O.make_labels(cfg, rows, seed=seed)
+        gts = [[torch.randint(1, cfg.V1, (int(torch.randint(2, L, (1,), generator=g)),), generator=g).tolist() + [0]
+                for _ in range(3)] for _ in range(imgs)]
+        return fc, att, u, top.cuda(), gts
+
+    df = {}
+    for s in (1, 2, 3):
+        for g in batch(s)[4]:
+            for r in g:
+                for k in range(1, 5):
+                    for j in range(len(r) - k + 1):
+                        df[tuple(r[j:j + k])] = df.get(tuple(r[j:j + k]), 0.0) + 1.0
+    table = RW.DocumentFrequency(df, 12, torch.device("cuda"))
+
+    def make():
+        m = build_model(cfg, sd).train()
+        return m, FusedAdam(m.parameters(), lr=1e-3, weight_decay=1e-5, grad_clip=1.0, capturable=True)
+
+    ma, oa = make()
+    losses_a = []
+    for s in (1, 2, 3):
+        fc, att, u, top, gts = batch(s)
+        refs, n_refs = RW.pack_references_static(gts, imgs, 3, L + 2)
+        refs, n_refs = torch.from_numpy(refs).cuda(), torch.from_numpy(n_refs).cuda()
+        oa.zero_grad(set_to_none=True)
+        loss, *_ = T.rl_forward_loss(ma, rl, fc, att, u, lambda a, b: RW.compute_reward_packed(a, b, refs, n_refs, table, ropt, spi)[0],
+                                     top, 10.0, 0.01)
+        loss.backward()
+        oa.step()
+        losses_a.append(float(loss))
+    mb, ob = make()
+    fc, att, u, top, gts = batch(1)
+    step = T.GraphedRLStep(mb, rl, ob, fc, att, u, top, gts, table, ropt, spi, 10.0, entropy_reg=0.01, max_refs=3, warmup=1)
+    losses_b = []
+    for s in (1, 2, 3):
+        fc, att, u, top, gts = batch(s)
+        losses_b.append(float(step(fc, att, u, top, gts)))
+    assert max(abs(a - b) for a, b in zip(losses_a, losses_b)) <= 1e-4 * max(1.0, abs(losses_a[0])), (losses_a, losses_b)
+    bad = {}
+    for (k, pa), (_, pb) in zip(ma.state_dict().items(), mb.state_dict().items()):
+        if k.endswith("att_h_2_out.bias"):
+            continue   # analytically zero gradient: Adam random-walks on rounding noise (see the XE graph test)
+        d = maxdiff(pa, pb)
+        if d > 2e-5:
+            bad[k] = d
+    assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:5]
