@@ -602,7 +602,11 @@ def config1_bench(device, cpu=True):
     with torch.no_grad():
         seq = m.sample(fcg, attg, opt)[0]
     kernels = int(_capi.lib().rfn_launch_count() - n0)
-    ms_eager = lat(lambda: m.sample(fcg, attg, opt), 50)
+
+    def eager():
+        with torch.no_grad():      # (with gradients enabled sample() takes the taped per-op path of training.py)
+            return m.sample(fcg, attg, opt)
+    ms_eager = lat(eager, 50)
     g = GraphedSample(m, fcg, attg, opt)
     ms_graph = lat(lambda: g(), 200)
     gseq, _, _, _, dT = g()

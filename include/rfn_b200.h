@@ -106,6 +106,12 @@ int rfn_get_tc_cluster(void);
  * (start, init done, first MMA, last MMA, last drain, epilogue done, exit); NULL switches it off. */
 int rfn_debug_set_timeline(long long* d_buf, int epilogue_kind /* -1 all, 0 store, 1 score, 2 vocab */);
 
+/* 1 (default): decodes with at most 64 decoder rows (greedy batches, beam x few images) run the whole timestep loop of the
+ * decoder LSTM as ONE cooperative launch (one CTA per SM, the gate weights of each CTA's hidden units resident in shared
+ * memory for all timesteps, five grid barriers per step); 0: always the per-step launch sequence. */
+int rfn_set_persistent_decoder(int on);
+int rfn_get_persistent_decoder(void);
+
 /* 1 (default): the J independent encoder cells of a fusion step run on internal side streams forked
  * from / joined into the caller's stream; 0: everything is serialised on the caller's stream. */
 int rfn_set_concurrency(int on);

@@ -60,6 +60,8 @@ _SIGNATURES = {
     "rfn_get_tc_cluster": (_i, []),
     "rfn_debug_set_timeline": (_i, [_vp, _i]),
     "rfn_set_concurrency": (_i, [_i]),
+    "rfn_set_persistent_decoder": (_i, [_i]),
+    "rfn_get_persistent_decoder": (_i, []),
     "rfn_profile_enable": (_i, [_i]),
     "rfn_profile_num_tags": (_i, []),
     "rfn_profile_tag_name": (C.c_char_p, [_i]),

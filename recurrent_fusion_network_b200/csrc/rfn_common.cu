@@ -69,7 +69,7 @@ const char* rfn_engine_name(int e) {
   static const char* names[rfn::ENG_COUNT] = {"simt_skinny", "simt_tiled", "tcgen05_1cta", "tcgen05_1cta_splitk", "tcgen05_2cta",
                                               "tcgen05_2cta_persistent_store", "tcgen05_2cta_persistent_score",
                                               "tcgen05_2cta_persistent_vocab", "tcgen05_2cta_persistent_fp16x3",
-                                              "tcgen05_2cta_persistent_bf16"};
+                                              "tcgen05_2cta_persistent_bf16", "persistent_decoder"};
   return (e >= 0 && e < rfn::ENG_COUNT) ? names[e] : "?";
 }
 int rfn_engine_launch_counts(uint64_t* out, int n) {

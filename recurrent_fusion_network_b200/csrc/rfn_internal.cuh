@@ -13,7 +13,8 @@ void count_launch(int n = 1);
 // per-engine launch accounting (rfn_engine_launch_counts): which GEMM kernel family actually ran
 enum Engine {
   ENG_SIMT_SKINNY = 0, ENG_SIMT_TILED = 1, ENG_TC1 = 2, ENG_TC1_SPLITK = 3, ENG_TC2 = 4, ENG_TC2P_STORE = 5,
-  ENG_TC2P_SCORE = 6, ENG_TC2P_VOCAB = 7, ENG_H3 = 8, ENG_BF16 = 9, ENG_COUNT = 10
+  ENG_TC2P_SCORE = 6, ENG_TC2P_VOCAB = 7, ENG_H3 = 8, ENG_BF16 = 9, ENG_PERSIST_DECODER = 10,
+  ENG_COUNT = 11
 };
 void count_engine(int engine);
 int gemm_mode();

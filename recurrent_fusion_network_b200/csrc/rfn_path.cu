@@ -7,6 +7,7 @@
 #include <mutex>
 #include <vector>
 
+#include "rfn_decoder_persist.cuh"
 #include "rfn_h3.cuh"
 #include "rfn_internal.cuh"
 #include "rfn_vocab.cuh"
@@ -492,6 +493,7 @@ struct DecWork {
   size_t wsplit_cap[3];
   H3Operand w_att[1], w_gates[3], w_logit[1];
   bool h3_ready;
+  float* pd_part;           // persistent decoder (rows <= PD_MAX_ROWS): per-slice vocabulary statistics
 };
 static size_t carve_dec(const rfn_dims& d, int rowsA, int rows, int beam, int n_logit_bufs, Bump& b, DecWork& w) {
   const int R = d.rnn_size, A = d.att_hid_size, E = d.input_encoding_size, S1 = d.num_review_steps, V = d.vocab_plus1;
@@ -522,6 +524,7 @@ static size_t carve_dec(const rfn_dims& d, int rowsA, int rows, int beam, int n_
   w.unfinished = b.take<uint8_t>(rows);
   w.h3 = H3Ws{};
   w.h3_ready = false;
+  w.pd_part = (rows >= 1 && rows <= PD_MAX_ROWS) ? b.take<float>(pd_part_floats(d, rows, k)) : nullptr;
   for (int i = 0; i < 3; ++i) { w.wsplit[i] = nullptr; w.wsplit_cap[i] = 0; }
   if (h3_mode()) {
     w.h3.xcap = std::max({split3(rows, E, R, R), split1(rows, R), split1(rowsA * S1, R)});
@@ -636,6 +639,30 @@ static int decoder_step(const rfn_dims& d, const float* const* prm, const float*
     }
   }
   return RFN_OK;
+}
+
+// the decoder loop as ONE cooperative launch (rfn_decoder_persist.cu); the caller has prepared Pdec, the initial state in
+// w.hA / w.cA, tok = 0 and (greedy) the unfinished / any flags or (beam) the beam state
+static int decoder_persistent(const rfn_dims& d, const float* const* prm, const float* TVc, DecWork& w, int rows, int div, int beam,
+                              int64_t* seq, float* seq_lp, float* lp_all, cudaStream_t st) {
+  const PIdx ix(d);
+  PDArgs a{};
+  a.i2h_w = prm[ix.dec(0)]; a.i2h_b = prm[ix.dec(1)]; a.h2h_w = prm[ix.dec(2)]; a.h2h_b = prm[ix.dec(3)];
+  a.z2h_w = prm[ix.dec(4)]; a.z2h_b = prm[ix.dec(5)];
+  a.hatt_w = prm[ix.dec(8)]; a.hatt_b = prm[ix.dec(9)]; a.out_w = prm[ix.dec(10)]; a.out_b = prm[ix.dec(11)];
+  a.logit_w = prm[ix.logit(0)]; a.logit_b = prm[ix.logit(1)]; a.embed = prm[ix.embed()];
+  a.TVc = TVc; a.Pdec = w.Pdec;
+  a.rows = rows; a.div = div; a.R = d.rnn_size; a.A = d.att_hid_size; a.E = d.input_encoding_size; a.V = d.vocab_plus1;
+  a.S1 = d.num_review_steps; a.L = d.seq_length;
+  a.hbuf[0] = w.hA; a.hbuf[1] = w.hB; a.cbuf[0] = w.cA; a.cbuf[1] = w.cB;
+  a.g = w.g; a.z = w.z; a.logits = lp_all ? w.logits : nullptr; a.rowmax = w.rowmax; a.logsum = w.logsum;
+  a.tok = w.tok; a.src = w.src;
+  a.ktop = beam > 0 ? beam : 1;
+  a.steps = (beam > 0 || !lp_all) ? d.seq_length : d.seq_length + 1;
+  a.seq = seq; a.seq_lp = seq_lp; a.unfinished = w.unfinished; a.any_unfinished = w.any; a.lp_all = lp_all;
+  a.beam = beam; a.bs = w.bs;
+  pd_bind_parts(d, a, w.pd_part);
+  return pd_launch(d, a, st);
 }
 
 static int ws_fail(const char* who, size_t have, size_t need) {
@@ -781,6 +808,10 @@ int rfn_decode_sample(const rfn_dims* dims, const float* const* params, const fl
   RFN_CUDA(cudaMemsetAsync(w.tok, 0, (size_t)rows * sizeof(int32_t), st));                       // t == 0: BOS (:617-618)
   RFN_CUDA(cudaMemsetAsync(w.any, 0, (size_t)(L + 2) * sizeof(int32_t), st));
   RFN_CUDA(cudaMemsetAsync(w.unfinished, 0, (size_t)rows, st));
+  if (!uniforms && w.pd_part && pd_supported(d, rows)) {   // greedy, small batch: the whole loop in one cooperative launch
+    RFN_TRY(decoder_persistent(d, params, TVc, w, rows, 1, 0, seq, seq_logprobs, lp_all, st));
+    return sample_finalize(w.any, L, d_T, st);
+  }
   float* hb[2] = {w.hA, w.hB};
   for (int t = 0; t <= L; ++t) {
     if (t >= 1)
@@ -822,6 +853,12 @@ int rfn_decode_beam(const rfn_dims* dims, const float* const* params, const floa
   if (carve_dec(d, images, rows, beam, 1, b, w) > workspace_bytes) return ws_fail("rfn_decode_beam", workspace_bytes, b.off);
   RFN_TRY(decoder_prepare(d, params, TVc, images, w.Pdec, st, &w, rows));
   RFN_TRY(beam_init(w, images, beam, L, st));
+  if (w.pd_part && pd_supported(d, rows)) {   // few images: the whole beam search in one cooperative launch
+    RFN_TRY(gather_rows(h0, nullptr, beam, w.hA, rows, R, st));
+    RFN_TRY(gather_rows(c0, nullptr, beam, w.cA, rows, R, st));
+    RFN_TRY(decoder_persistent(d, params, TVc, w, rows, beam, beam, nullptr, nullptr, nullptr, st));
+    return beam_finalize(w.bs, seq, seq_logprobs, done_seq, done_logps, done_p, n_done, st);
+  }
   // expand each image's stage-2 state to `beam` identical rows (:376-394)
   RFN_TRY(gather_rows(h0, nullptr, beam, w.hB, rows, R, st));
   RFN_TRY(gather_rows(c0, nullptr, beam, w.cB, rows, R, st));

@@ -412,7 +412,7 @@ class RecurrentFusionModel(nn.Module):
         """HOST array of device pointers in state_dict order plus the trailing weight-cache slot (rfn_num_param_slots);
         cached until a parameter's storage moves, the engine mode changes, or -- for the weight cache -- a parameter is
         modified (its autograd version counter changes)."""
-        ps = list(self.parameters())
+        ps = self._plist()
         mode = lib().rfn_get_gemm_mode()
         use_cache = bool(self.weight_cache) and mode >= 4 and not torch.is_grad_enabled()
         key = (tuple(p.data_ptr() for p in ps), mode, use_cache,
@@ -440,6 +440,26 @@ class RecurrentFusionModel(nn.Module):
             self._pcache = (key, arr)
         return self._pcache[1]
 
+    def _plist(self):
+        """The parameters in state_dict order.  Walking the module tree costs milliseconds for the 773-tensor model, which is
+        what a batch-16 decode takes on the device: the Parameter objects survive .cuda() / load_state_dict, so the list is
+        built once."""
+        pl = self.__dict__.get("_plist_cache")
+        if pl is None:
+            pl = list(self.parameters())
+            self.__dict__["_plist_cache"] = pl
+        return pl
+
+    def _apply(self, fn, *args, **kwargs):          # .cuda() / .to() / .float(): drop the derived caches
+        self.__dict__.pop("_plist_cache", None)
+        self._pcache = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):     # assign=True swaps the Parameter objects
+        self.__dict__.pop("_plist_cache", None)
+        self._pcache = None
+        return super().load_state_dict(*args, **kwargs)
+
     def _dropout_active(self, p):
         return self.training and p > 0
 
@@ -448,13 +468,13 @@ class RecurrentFusionModel(nn.Module):
         if self._dropout_active(self.drop_prob_fusion) or self._dropout_active(self.drop_prob_reason) or \
                 self._dropout_active(self.drop_prob_lm):
             return True
-        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self._plist())
 
     def _check_feats(self, fc_feats, att_feats, allow_host=False):
         J = self.num_feat_array
         if len(fc_feats) != J or len(att_feats) != J:
             raise _capi.RfnError(f"expected {J} fc / att feature tensors")
-        _require_cuda(next(self.parameters()))
+        _require_cuda(self._plist()[0])
         fc = [_f32c(t) for t in fc_feats]
         att = [_f32c(t) for t in att_feats]
         rows = fc[0].shape[0]
@@ -605,7 +625,7 @@ class RecurrentFusionModel(nn.Module):
         return seq, slp, lp_all, reason, dT
 
     def _device(self):
-        return next(self.parameters()).device
+        return self._plist()[0].device
 
     def _chunks(self, fc, att, rows, step):
         """Yields (k0, k1, fc_chunk, att_chunk) with the chunk resident on the device.  Host (pinned)

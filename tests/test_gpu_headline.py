@@ -199,3 +199,61 @@ def test_graphed_decode_equals_eager_decode():
     seq, slp, _, _, dT = gs()
     T = int(dT.item())
     assert T == s.shape[1] and torch.equal(seq[:, :T], s) and torch.equal(slp[:, :T], sl)
+
+
+@pytest.mark.parametrize("make_cfg,sharpen", [(lambda: O.tiny_config(2), None), (lambda: O.config1(49), True)], ids=["tiny_j2", "config1"])
+def test_persistent_decoder_matches_oracle_and_the_per_step_path(make_cfg, sharpen):
+    """The cooperative persistent decoder kernel (<= 64 decoder rows: the whole timestep loop in one launch, gate weights
+    resident in shared memory) against the oracle and against the per-step launch path: greedy with the full log-prob table,
+    greedy at 40 rows (three staged row groups), beam 3 x 20 images (60 rows) and beam 5."""
+    from recurrent_fusion_network_b200 import _capi
+    cfg = make_cfg()
+    if sharpen is None:
+        sd = O.make_state_dict(cfg, seed=1250, init_range=0.5, logit_scale=3.0, eos_bias=0.8)
+    else:
+        sd = O.make_state_dict(cfg, seed=1234, sharpen=True)
+    m = build_model(cfg, sd)
+    fc, att = O.make_inputs(cfg, 40, seed=61)
+    fcg, attg = cuda_list(fc), cuda_list(att)
+    torch.set_num_threads(max(16, torch.get_num_threads()))
+    from tests._gpu_util import assert_tokens_match_with_tie_policy
+
+    def run(on, fn):
+        _capi.check(_capi.lib().rfn_set_persistent_decoder(on))
+        before = _capi.engine_launch_counts()["persistent_decoder"]
+        with torch.no_grad():
+            out = fn()
+        torch.cuda.synchronize()
+        return out, _capi.engine_launch_counts()["persistent_decoder"] - before
+
+    try:
+        for n in (16, 40):
+            f, a = [t[:n] for t in fcg], [t[:n] for t in attg]
+            (s1, sl1, la1, _), used = run(1, lambda: m.sample(f, a, {"sample_max": 1}))
+            assert used == 1
+            (s0, sl0, la0, _), used0 = run(0, lambda: m.sample(f, a, {"sample_max": 1}))
+            assert used0 == 0
+            so, slo, lao, _ = O.sample(sd, cfg, [t[:n] for t in fc], [t[:n] for t in att])
+            T = min(s1.shape[1], so.shape[1])
+            ties = assert_tokens_match_with_tie_policy(s1[:, :T], so[:, :T], lao, f"persistent greedy {n} rows")
+            assert ties <= 1
+            same = (s1[:, :T].cpu() == so[:, :T]).all(dim=1)
+            assert maxdiff(sl1[:, :T][same.cuda()], slo[:, :T][same]) <= LP_TOL
+            assert maxdiff(la1[:, :T + 1][same.cuda()], lao[:, :T + 1][same]) <= 2 * LP_TOL
+            if s0.shape == s1.shape and torch.equal(s0, s1):
+                assert maxdiff(sl0, sl1) <= 2e-5
+        for beam, n in ((3, 20), (5, 7)):
+            f, a = [t[:n] for t in fcg], [t[:n] for t in attg]
+            (b1, used) = run(1, lambda: m.sample_beam(f, a, {"beam_size": beam}))
+            assert used == 1
+            margins = []
+            with torch.no_grad():
+                o = O.sample_beam(sd, cfg, [t[:n] for t in fc], [t[:n] for t in att], beam_size=beam, margins_out=margins)
+            ties = assert_beam_match_with_tie_policy(b1[0], b1[1], o[0], o[1], margins, f"persistent beam {beam}")
+            assert ties <= 1
+            if ties == 0:
+                assert [t.shape for t in b1[2]] == [t.shape for t in o[2]]
+                for x, y in zip(b1[2], o[2]):
+                    assert torch.equal(x, y)
+    finally:
+        _capi.check(_capi.lib().rfn_set_persistent_decoder(1))
