@@ -111,6 +111,9 @@ int rfn_debug_set_timeline(long long* d_buf, int epilogue_kind /* -1 all, 0 stor
  * memory for all timesteps, five grid barriers per step); 0: always the per-step launch sequence. */
 int rfn_set_persistent_decoder(int on);
 int rfn_get_persistent_decoder(void);
+/* Debugging aid: device buffer receiving 8 globaltimer stamps (ns) per decoder step from CTA 0 of the persistent decoder
+ * (step start, phase A done, after its barrier, B done, C done, D done, after its barrier, E done); NULL switches it off. */
+int rfn_debug_set_pd_timeline(long long* d_buf);
 
 /* 1 (default): the J independent encoder cells of a fusion step run on internal side streams forked
  * from / joined into the caller's stream; 0: everything is serialised on the caller's stream. */

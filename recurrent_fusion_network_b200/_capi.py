@@ -62,6 +62,7 @@ _SIGNATURES = {
     "rfn_set_concurrency": (_i, [_i]),
     "rfn_set_persistent_decoder": (_i, [_i]),
     "rfn_get_persistent_decoder": (_i, []),
+    "rfn_debug_set_pd_timeline": (_i, [_vp]),
     "rfn_profile_enable": (_i, [_i]),
     "rfn_profile_num_tags": (_i, []),
     "rfn_profile_tag_name": (C.c_char_p, [_i]),

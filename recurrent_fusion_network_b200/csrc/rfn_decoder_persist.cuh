@@ -35,6 +35,7 @@ struct PDArgs {
   // beam bookkeeping
   int beam;                                                     // 0 = greedy
   BeamState bs;
+  long long* dbg;                                               // optional per-step phase stamps (rfn_debug_set_pd_timeline)
 };
 
 

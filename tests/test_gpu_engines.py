@@ -146,6 +146,7 @@ def test_library_services_profile_concurrency_and_errors():
     fc, att = O.make_inputs(cfg, 5, seed=1)
     m = build_model(cfg, sd)
     outs = {}
+    _capi.check(lib().rfn_set_persistent_decoder(0))   # the per-step launch path is what carries the profile classes checked here
     for conc in (0, 1):
         _capi.check(lib().rfn_set_concurrency(conc))
         n0 = lib().rfn_launch_count()
@@ -159,6 +160,7 @@ def test_library_services_profile_concurrency_and_errors():
         assert lib().rfn_launch_count() - n0 >= n_prof > 50   # a profiled launcher may issue several kernels
         assert prof["beam_merge"][1] == cfg.seq_length + 1 and prof["lstm_cell"][0] > 0
     _capi.check(lib().rfn_set_concurrency(1))
+    _capi.check(lib().rfn_set_persistent_decoder(1))
     assert torch.equal(outs[0][0], outs[1][0]) and maxdiff(outs[0][1], outs[1][1]) == 0.0   # same kernels, same bits
     # workspace too small -> RFN_ERR_WORKSPACE with a message, nothing launched
     TVc = torch.empty(5, cfg.num_review_steps, cfg.rnn_size, device="cuda")
