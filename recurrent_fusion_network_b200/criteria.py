@@ -66,7 +66,11 @@ class ReviewNetRewardCriterion(nn.Module):
     def forward(self, input, seq, reward, logprobs_all, entropy_reg, top_pred, top_true, reason_weight,
                 sample_logprobs_old, opt):
         if getattr(opt, "use_ppo", 0):
-            raise NotImplementedError("use_ppo=1 is out of scope (SURVEY.md A.9)")
+            # the reference's own branch cannot execute for this model: it flattens `input` to (rows*T) but divides by the
+            # un-flattened (rows, T) sample_logprobs_old (misc/utils.py:53,63-65; called from train_rl.py:162-169), which
+            # raises a broadcasting error for every T != 1 -- probed in the build container with the imported reference
+            raise NotImplementedError("use_ppo=1: the reference's PPO branch of ReviewNetRewardCriterion raises a shape error "
+                                      "(misc/utils.py:65) and is not built; default 0 in every shipped script")
         tp = top_pred if isinstance(top_pred, list) else [top_pred]
         if _needs_grad(input, logprobs_all, *tp):
             from . import training

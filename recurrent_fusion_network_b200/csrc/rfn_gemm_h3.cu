@@ -573,7 +573,11 @@ static int launch_h3(const H3Args& t, int bf16, cudaStream_t st) {
   const int n_tiles = (t.N + H3_BN - 1) / H3_BN;
   const int n_pairs = (t.M + 2 * TC_BM - 1) / (2 * TC_BM);
   const int total = n_tiles * n_pairs;
-  const int clusters = total < n_sm / 2 ? total : n_sm / 2;
+  // as few clusters as finish in the same number of waves: a launch of 314 tiles takes 5 waves on 74 cluster slots and on 63,
+  // and the 22 SMs it then leaves alone run the other encoder streams' kernels meanwhile (matters for small shards)
+  const int slots = n_sm / 2;
+  const int waves = (total + slots - 1) / slots;
+  const int clusters = (total + waves - 1) / waves;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(2 * clusters), 1, 1);
   cfg.blockDim = dim3(H3_THREADS, 1, 1);

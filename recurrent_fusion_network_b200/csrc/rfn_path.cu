@@ -261,6 +261,8 @@ struct TVWork {
   H3Ws h3[RFN_MAX_ENCODERS];             // engine modes 4 / 5: split scratch of encoder j's stream
   void* fsplit[RFN_MAX_ENCODERS];        // pre-split features of encoder j (stage 1), then its thought vectors (stage 2)
   size_t fsplit_cap[RFN_MAX_ENCODERS];
+  void* hsplit;                          // stage 2: the review state h, split once per step for the J query projections
+  size_t hsplit_cap;
 };
 static size_t p_floats(const rfn_dims& d, int rows, int N) {
   // SIMT engine: P = att_2_att_h(A) is materialised (rows*N, A); tensor engine: partial scores only
@@ -293,6 +295,12 @@ static size_t carve_tv(const rfn_dims& d, int rows, bool need_tv, bool need_reas
       w.h3[j].w = b.take<char>(w.h3[j].wcap);
     }
   }
+  w.hsplit = nullptr;
+  w.hsplit_cap = 0;
+  if (h3_mode()) {
+    w.hsplit_cap = split1(rows, R);
+    w.hsplit = b.take<char>(w.hsplit_cap);
+  }
   w.TV = need_tv ? b.take<float>((size_t)J * rows * S0 * R) : nullptr;
   w.rs = need_reason ? b.take<float>((size_t)rows * std::max(S0, S1) * d.top_words_count) : nullptr;
   return b.off;
@@ -304,9 +312,9 @@ static int attention_module(const rfn_dims& d, const float* h, int ldh, const fl
                             const float* U_w, const float* U_b, const float* Wh_w, const float* Wh_b, const float* v_w,
                             const float* v_b, float* g, float* P, size_t p_cap, float* z, int ldz, int rows, int tag_gemm,
                             int tag_attn, const H3Ws* sc, const H3Operand* feat_split, const H3Operand* w_u, const H3Operand* w_h,
-                            cudaStream_t st) {
+                            cudaStream_t st, const H3Operand* h_split = nullptr) {
   const int R = d.rnn_size, A = d.att_hid_size;
-  RFN_TRY(path_gemm(gemm1(h, ldh, Wh_w, Wh_b, R, g, A, rows, A), sc, nullptr, w_h, st));      // :36
+  RFN_TRY(path_gemm(gemm1(h, ldh, Wh_w, Wh_b, R, g, A, rows, A), sc, h_split, w_h, st));      // :36
   GemmArgs pa = gemm1(Afeat, D, U_w, U_b, D, P, A, rows * N, A);                            // :32-34
   if (sc && h3_take(pa)) {
     // split engine with the fused tanh-score epilogue: the features arrive pre-split, U is split here
@@ -443,12 +451,17 @@ static int thought_vectors(const rfn_dims& d, const float* const* prm, const flo
   for (int s = 0; s < S1; ++s) {
     const float* hin = hb[(S1 + s) & 1];
     float* hout = hb[(S1 + s + 1) & 1];
+    // the J attention modules of a review step share the query h: split it once
+    H3Operand hop[1];
+    const bool have_h = h3 && h3_shape_ok(rows, d.att_hid_size);
+    if (have_h) RFN_TRY(h3_presplit(hin, R, R, rows, w.hsplit, w.hsplit_cap, hop, st));
     RFN_TRY(for_each_encoder(J, st, [&](int j, cudaStream_t sj) -> int {
       H3Operand wu[1], wh[1];
       return attention_module(d, hin, R, TV + j * tv_stride, S0, R, prm[ix.s2_att(s, j, 0)], prm[ix.s2_att(s, j, 1)],
                               prm[ix.s2_att(s, j, 2)], prm[ix.s2_att(s, j, 3)], prm[ix.s2_att(s, j, 4)], prm[ix.s2_att(s, j, 5)],
                               w.g[j], w.P[j], w.p_cap[j], w.z[j], R, rows, TAG_GEMM_OTHER, TAG_ATTN_SMALL, h3 ? &w.h3[j] : nullptr,
-                              have_tv ? &tvop[j] : nullptr, wc.get(wc.i_s2(s, 2 * j), wu), wc.get(wc.i_s2(s, 2 * j + 1), wh), sj);
+                              have_tv ? &tvop[j] : nullptr, wc.get(wc.i_s2(s, 2 * j), wu), wc.get(wc.i_s2(s, 2 * j + 1), wh), sj,
+                              have_h ? hop : nullptr);
     }));
     // G = h2h(h) + sum_j z_2_h[j](z_j)       (misc/LSTMSoftMultiAttentionFeatArrayNoInputCore.py:50-52)
     int jn = 0, grp = 0;
