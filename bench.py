@@ -768,7 +768,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images", type=int, default=5000)
     ap.add_argument("--chunk", type=int, default=5000, help="images per device call when the features are resident")
-    ap.add_argument("--e2e-chunk", type=int, default=500, help="images per device call when streaming host features")
+    ap.add_argument("--e2e-chunk", type=int, default=256,
+                    help="images per device call when streaming host features (>= 256 keeps every GEMM on the tensor engine; "
+                         "smaller chunks shorten the exposed decode of the last chunk)")
     ap.add_argument("--gemm-mode", type=int, default=int(os.environ.get("RFN_GEMM_MODE", "4")))
     ap.add_argument("--train-steps", type=int, default=3, help="XE training steps timed for the secondary metric (0 = skip)")
     ap.add_argument("--cpu-images", type=int, default=24)

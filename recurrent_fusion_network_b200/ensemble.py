@@ -58,12 +58,9 @@ def ensemble_sample_beam(models, fc_feats, att_feats, opt={}):
                                                  beam, ptr(seq[k0:k1]), ptr(slp[k0:k1]), ptr(done_seq[k0:k1]),
                                                  ptr(done_lp[k0:k1]), ptr(done_p[k0:k1]), ptr(n_done[k0:k1]), ptr(ws),
                                                  ws.numel(), stream()), "rfn_ensemble_decode_beam")
+        from .model import _TopList
         nl = n_done.cpu().tolist()
-        ds = done_seq.cpu().long()
-        dp = done_p.cpu().tolist()
-        top_seq = [ds[k, :nl[k]] for k in range(rows)]
-        top_prob = [dp[k][:nl[k]] for k in range(rows)]
-        return seq, slp, top_seq, top_prob
+        return seq, slp, _TopList(done_seq.cpu(), nl, "seq"), _TopList(done_p.cpu(), nl, "prob")
 
 
 def ensemble_sample_greedy(models, fc_feats, att_feats, opt={}):

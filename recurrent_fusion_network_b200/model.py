@@ -311,6 +311,28 @@ class _ReasonPredBatch(Sequence):
         return [self._r[j, k].unsqueeze(0).expand(self._beam, -1) for j in range(self._r.shape[0])]
 
 
+class _TopList(Sequence):
+    """top_seq / top_prob of sample_beam (:533-541): per image the finished beams sorted by -p, as a (n_done, L) int64
+    tensor (kind 'seq') or a list of floats (kind 'prob').  Lazy: building 5000 Python objects eagerly costs ~15 ms per
+    decode call, a twentieth of the whole end-to-end call."""
+
+    def __init__(self, data, n_done, kind):
+        self._d, self._n, self._kind = data, n_done, kind
+
+    def __len__(self):
+        return len(self._n)
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return [self[i] for i in range(*k.indices(len(self)))]
+        if k < 0:
+            k += len(self)
+        if not 0 <= k < len(self):
+            raise IndexError(k)
+        n = int(self._n[k])
+        return self._d[k, :n].long() if self._kind == "seq" else self._d[k, :n].tolist()
+
+
 class _DoneBeams(Sequence):
     """done_beams[k] -> list of {'seq','logps','p'} sorted by -p (misc/RecurrentFusionModel.py:529)."""
 
@@ -325,7 +347,7 @@ class _DoneBeams(Sequence):
             return [self[i] for i in range(*k.indices(len(self)))]
         if self._l.is_cuda:
             self._l = self._l.cpu()   # copied on first access only
-        return [{"seq": self._s[k, i], "logps": self._l[k, i], "p": float(self._p[k, i])} for i in range(int(self._n[k]))]
+        return [{"seq": self._s[k, i].long(), "logps": self._l[k, i], "p": float(self._p[k, i])} for i in range(int(self._n[k]))]
 
 
 # --------------------------------------------------------------------------------------------------
@@ -723,11 +745,8 @@ class RecurrentFusionModel(nn.Module):
             seq, slp, done_seq, done_lp, done_p, n_done, reason = self._beam_tensors(fc, att, rows, beam_size)
             # the caption gather: one D2H of the finished-beam lists
             n_cpu = n_done.cpu()
-            ds_cpu = done_seq.cpu().long()
+            ds_cpu = done_seq.cpu()
             dp_cpu = done_p.cpu()
             nl = n_cpu.tolist()
-            top_seq = [ds_cpu[k, :nl[k]] for k in range(rows)]
-            dpl = dp_cpu.tolist()
-            top_prob = [dpl[k][:nl[k]] for k in range(rows)]
             self.done_beams = _DoneBeams(ds_cpu, done_lp, dp_cpu, nl)
-            return seq, slp, top_seq, top_prob, _ReasonPredBatch(reason, beam_size)
+            return seq, slp, _TopList(ds_cpu, nl, "seq"), _TopList(dp_cpu, nl, "prob"), _ReasonPredBatch(reason, beam_size)
