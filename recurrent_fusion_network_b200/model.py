@@ -663,6 +663,10 @@ class RecurrentFusionModel(nn.Module):
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
         cs = self._copy_stream
+        # equal chunks (a short tail chunk would fall below the row counts the tensor engines take: < 128 rows run on the
+        # fp32 SIMT kernels, an order of magnitude slower per row)
+        n_chunks = (rows + step - 1) // step
+        step = (rows + n_chunks - 1) // n_chunks
         n_buf = min(step, rows)
         key = (n_buf, dev)
         if getattr(self, "_staging_key", None) != key:
