@@ -106,6 +106,13 @@ int rfn_get_tc_cluster(void);
  * (start, init done, first MMA, last MMA, last drain, epilogue done, exit); NULL switches it off. */
 int rfn_debug_set_timeline(long long* d_buf, int epilogue_kind /* -1 all, 0 store, 1 score, 2 vocab */);
 
+/* 1: the frequent kernels of the decode path are launched with programmatic dependent launch (their launch latency and
+ * prologue overlap the tail of the preceding kernel of the stream; each waits with griddepcontrol.wait before touching
+ * global memory); 0 (default): plain stream order.  Results are bit-identical; measured gain on B200: none within noise
+ * (20.34 vs 20.44 ms per 625-image step), the path is not bound by launch gaps once it is replayed from a CUDA graph. */
+int rfn_set_pdl(int on);
+int rfn_get_pdl(void);
+
 /* 1 (default): decodes with at most 64 decoder rows (greedy batches, beam x few images) run the whole timestep loop of the
  * decoder LSTM as ONE cooperative launch (one CTA per SM, the gate weights of each CTA's hidden units resident in shared
  * memory for all timesteps, five grid barriers per step); 0: always the per-step launch sequence. */

@@ -60,6 +60,8 @@ _SIGNATURES = {
     "rfn_get_tc_cluster": (_i, []),
     "rfn_debug_set_timeline": (_i, [_vp, _i]),
     "rfn_set_concurrency": (_i, [_i]),
+    "rfn_set_pdl": (_i, [_i]),
+    "rfn_get_pdl": (_i, []),
     "rfn_set_persistent_decoder": (_i, [_i]),
     "rfn_get_persistent_decoder": (_i, []),
     "rfn_debug_set_pd_timeline": (_i, [_vp]),
@@ -147,6 +149,9 @@ def lib() -> C.CDLL:
         mode = os.environ.get("RFN_GEMM_MODE")
         if mode is not None:
             check(_lib.rfn_set_gemm_mode(int(mode)), "rfn_set_gemm_mode")
+        pdl = os.environ.get("RFN_PDL")
+        if pdl is not None:
+            check(_lib.rfn_set_pdl(int(pdl)), "rfn_set_pdl")
         cl = os.environ.get("RFN_TC_CLUSTER")
         if cl is not None:
             check(_lib.rfn_set_tc_cluster(int(cl)), "rfn_set_tc_cluster")

@@ -43,6 +43,8 @@ attention_step_kernel(const float* __restrict__ A, const float* __restrict__ P,
   const int ra = r / div;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = ATT_THREADS / 32;
+  pdl_trigger();
+  pdl_wait();
 
   const float wb = __ldg(d_wb);
   if (scores) {
@@ -178,7 +180,8 @@ int attention_step(const float* A, const float* P, const float* g, const float* 
   RFN_CHECK_ARG(smem <= 200 * 1024, "attention_step: N=%d Ah=%d exceed shared memory", N, Ah);
   if (smem > 48 * 1024)
     RFN_CUDA(cudaFuncSetAttribute(attention_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  attention_step_kernel<<<dim3(rows, dsplit), ATT_THREADS, smem, st>>>(A, P, g, w, d_wb, z, ldz, alpha, N, D, Ah, div, nullptr, 0, 0);
+  RFN_CUDA(launch_pdl(attention_step_kernel, dim3(rows, dsplit), dim3(ATT_THREADS), smem, st, A, P, g, w, d_wb, z, ldz, alpha, N, D, Ah,
+                      div, (const float*)nullptr, 0, (size_t)0, (const __nv_bfloat16*)nullptr, 0));
   RFN_LAUNCH_CHECK();
   return RFN_OK;
 }
@@ -196,9 +199,9 @@ int attention_from_scores(const float* A, const float* scores, int nslices, cons
   RFN_CHECK_ARG(smem <= 200 * 1024, "attention_from_scores: N=%d exceeds shared memory", N);
   if (smem > 48 * 1024)
     RFN_CUDA(cudaFuncSetAttribute(attention_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  attention_step_kernel<<<dim3(rows, dsplit), ATT_THREADS, smem, st>>>(A, nullptr, nullptr, nullptr, d_wb, z, ldz, alpha, N, D, 0,
-                                                                       div, scores, nslices, (size_t)rows * N,
-                                                                       (const __nv_bfloat16*)A_bf16, lda_bf16);
+  RFN_CUDA(launch_pdl(attention_step_kernel, dim3(rows, dsplit), dim3(ATT_THREADS), smem, st, A, (const float*)nullptr,
+                      (const float*)nullptr, (const float*)nullptr, d_wb, z, ldz, alpha, N, D, 0, div, scores, nslices,
+                      (size_t)rows * N, (const __nv_bfloat16*)A_bf16, lda_bf16));
   RFN_LAUNCH_CHECK();
   return RFN_OK;
 }

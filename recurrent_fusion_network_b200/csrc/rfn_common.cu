@@ -23,6 +23,8 @@ void count_engine(int engine) {
   if (engine >= 0 && engine < ENG_COUNT) g_engine_launches[engine].fetch_add(1, std::memory_order_relaxed);
 }
 int gemm_mode() { return g_gemm_mode.load(std::memory_order_relaxed); }
+static std::atomic<int> g_pdl{0};   // measured: no gain at 625 or 5000 images (profiles/r2_pdl_625img.json), so off by default
+bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; }
 
 // ---- optional per-kernel-class timing with CUDA events on the launching stream -------------------
 static std::atomic<int> g_prof_on{0};
@@ -97,6 +99,11 @@ int rfn_set_gemm_mode(int mode) {
   return RFN_OK;
 }
 int rfn_get_gemm_mode(void) { return rfn::gemm_mode(); }
+int rfn_set_pdl(int on) {
+  rfn::g_pdl.store(on ? 1 : 0);
+  return RFN_OK;
+}
+int rfn_get_pdl(void) { return rfn::pdl_enabled() ? 1 : 0; }
 
 int rfn_profile_enable(int on) {
   rfn::g_prof_on.store(on ? 1 : 0);

@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(H3_THREADS, 1) gemm_h3_kernel(const __grid_con
   const bool leader = (rank == 0);
   const int cluster = blockIdx.x >> 1;
   const int n_clusters = gridDim.x >> 1;
+  pdl_trigger();
 
   int total_kb = 0;
   for (int s = 0; s < a.nsrc; ++s) total_kb += (a.K[s] + H3_BK - 1) / H3_BK;
@@ -139,6 +140,7 @@ __global__ void __launch_bounds__(H3_THREADS, 1) gemm_h3_kernel(const __grid_con
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above touched only shared memory, TMEM and the kernel parameters
 
   if (warp < 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -409,6 +411,8 @@ constexpr int SPLIT_WARPS = 8;
 __global__ void __launch_bounds__(SPLIT_WARPS * 32) split_rows_kernel(const SplitArgs a) {
   const int lane = threadIdx.x & 31;
   const long row = (long)blockIdx.x * SPLIT_WARPS + (threadIdx.x >> 5);
+  pdl_trigger();
+  pdl_wait();
   if (row >= a.rows) return;
   float scale = 1.f;
   if (!a.bf16) {
@@ -495,7 +499,7 @@ int h3_split(const float* const* x, const int* ldx, const int* K, int nsrc, int 
     out[s] = H3Operand{a.p0[s], a.p1[s], a.ldp[s], a.inv};
   }
   a.nsrc = nsrc; a.rows = rows; a.bf16 = bf16 ? 1 : 0;
-  split_rows_kernel<<<(unsigned)((rows + SPLIT_WARPS - 1) / SPLIT_WARPS), SPLIT_WARPS * 32, 0, st>>>(a);
+  RFN_CUDA(launch_pdl(split_rows_kernel, dim3((unsigned)((rows + SPLIT_WARPS - 1) / SPLIT_WARPS)), dim3(SPLIT_WARPS * 32), 0, st, a));
   RFN_LAUNCH_CHECK();
   return RFN_OK;
 }
@@ -583,13 +587,15 @@ static int launch_h3(const H3Args& t, int bf16, cudaStream_t st) {
   cfg.blockDim = dim3(H3_THREADS, 1, 1);
   cfg.dynamicSmemBytes = Cfg::SMEM;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   RFN_CUDA(cudaLaunchKernelEx(&cfg, gemm_h3_kernel<EPI, NPROD>, t, n_tiles, total, bf16));
   RFN_LAUNCH_CHECK();
   count_engine(bf16 ? ENG_BF16 : ENG_H3);

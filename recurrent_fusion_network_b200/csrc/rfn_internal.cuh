@@ -43,6 +43,31 @@ struct ProfScope {  // records start/stop events around one launcher call when p
   ~ProfScope();
 };
 
+// ---- programmatic dependent launch (PDL): a kernel launched with launch_pdl may be scheduled while its predecessor in the
+// stream is still running; it must execute pdl_wait() before its first global-memory access (then the predecessor has
+// completed and its writes are visible), and every kernel calls pdl_trigger() at its start so that a PDL successor can be
+// scheduled early.  What this hides is the launch latency and the prologue (barrier init, TMEM allocation, cluster sync) of
+// the ~700 dependent kernels of a decode call -- it matters for small shards.  rfn_set_pdl(0) turns it off.
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 #define RFN_CHECK_ARG(cond, ...)              \
   do {                                        \
     if (!(cond)) {                            \

@@ -12,6 +12,8 @@ __global__ void lstm_cell_kernel(const float* __restrict__ G, const float* c_pre
                                  float* __restrict__ h_out, float* c_out,
                                  float* __restrict__ h_out2, int ldh2, float* __restrict__ h_out3,
                                  int ldh3, int rows, int R) {
+  pdl_trigger();
+  pdl_wait();
   const size_t total = (size_t)rows * R;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / R), k = (int)(i % R);
@@ -36,7 +38,7 @@ int lstm_cell(const float* G, const float* c_prev, float* h_out, float* c_out, f
   if (rows == 0) return RFN_OK;
   const size_t total = (size_t)rows * R;
   const int blocks = (int)min((size_t)148 * 8, (total + 255) / 256);
-  lstm_cell_kernel<<<blocks, 256, 0, st>>>(G, c_prev, h_out, c_out, h_out2, ldh2, h_out3, ldh3, rows, R);
+  RFN_CUDA(launch_pdl(lstm_cell_kernel, dim3(blocks), dim3(256), 0, st, G, c_prev, h_out, c_out, h_out2, ldh2, h_out3, ldh3, rows, R));
   RFN_LAUNCH_CHECK();
   return RFN_OK;
 }
@@ -44,6 +46,8 @@ int lstm_cell(const float* G, const float* c_prev, float* h_out, float* c_out, f
 template <typename TokT>
 __global__ void embed_gather_kernel(const TokT* __restrict__ tok, int ld_tok, const float* __restrict__ embed,
                                     float* __restrict__ x, int rows, int E, int V1) {
+  pdl_trigger();
+  pdl_wait();
   const size_t total = (size_t)rows * E;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / E), k = (int)(i % E);
@@ -59,7 +63,7 @@ int embed_gather_i64(const int64_t* tok, int ld_tok, const float* embed, float* 
   if (rows == 0) return RFN_OK;
   const size_t total = (size_t)rows * E;
   const int blocks = (int)min((size_t)148 * 8, (total + 255) / 256);
-  embed_gather_kernel<int64_t><<<blocks, 256, 0, st>>>(tok, ld_tok, embed, x, rows, E, V1);
+  RFN_CUDA(launch_pdl(embed_gather_kernel<int64_t>, dim3(blocks), dim3(256), 0, st, tok, ld_tok, embed, x, rows, E, V1));
   RFN_LAUNCH_CHECK();
   return RFN_OK;
 }
@@ -68,13 +72,15 @@ int embed_gather_i32(const int32_t* tok, const float* embed, float* x, int rows,
   if (rows == 0) return RFN_OK;
   const size_t total = (size_t)rows * E;
   const int blocks = (int)min((size_t)148 * 8, (total + 255) / 256);
-  embed_gather_kernel<int32_t><<<blocks, 256, 0, st>>>(tok, 1, embed, x, rows, E, V1);
+  RFN_CUDA(launch_pdl(embed_gather_kernel<int32_t>, dim3(blocks), dim3(256), 0, st, tok, 1, embed, x, rows, E, V1));
   RFN_LAUNCH_CHECK();
   return RFN_OK;
 }
 
 __global__ void gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx, int div,
                                    float* __restrict__ dst, int rows, int R) {
+  pdl_trigger();
+  pdl_wait();
   const size_t total = (size_t)rows * R;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / R), k = (int)(i % R);
@@ -87,7 +93,7 @@ int gather_rows(const float* src, const int32_t* idx, int div, float* dst, int r
   if (rows == 0) return RFN_OK;
   const size_t total = (size_t)rows * R;
   const int blocks = (int)min((size_t)148 * 8, (total + 255) / 256);
-  gather_rows_kernel<<<blocks, 256, 0, st>>>(src, idx, div, dst, rows, R);
+  RFN_CUDA(launch_pdl(gather_rows_kernel, dim3(blocks), dim3(256), 0, st, src, idx, div, dst, rows, R));
   RFN_LAUNCH_CHECK();
   return RFN_OK;
 }

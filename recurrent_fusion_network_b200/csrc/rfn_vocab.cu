@@ -199,6 +199,8 @@ vocab_merge_kernel(const float* __restrict__ st_max, const float* __restrict__ s
                    float* __restrict__ logsum, float* __restrict__ top_val, int32_t* __restrict__ top_idx) {
   const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  pdl_trigger();
+  pdl_wait();
   if (r >= rows) return;
   float m = -INFINITY;
   for (int s = lane; s < slices; s += 32) m = fmaxf(m, st_max[(size_t)s * rows + r]);
@@ -243,7 +245,8 @@ int vocab_merge(const float* st_max, const float* st_sum, const float* st_val, c
                 int k, float* rowmax, float* logsum, float* top_val, int32_t* top_idx, cudaStream_t st) {
   ProfScope prof__(TAG_VOCAB, st);
   if (rows == 0) return RFN_OK;
-  vocab_merge_kernel<<<(rows + 3) / 4, 128, 0, st>>>(st_max, st_sum, st_val, st_idx, slices, rows, k, rowmax, logsum, top_val, top_idx);
+  RFN_CUDA(launch_pdl(vocab_merge_kernel, dim3((rows + 3) / 4), dim3(128), 0, st, st_max, st_sum, st_val, st_idx, slices, rows, k, rowmax,
+                      logsum, top_val, top_idx));
   RFN_LAUNCH_CHECK();
   return RFN_OK;
 }
@@ -347,6 +350,8 @@ __global__ void beam_merge_kernel(BeamState bs, int t, const float* __restrict__
                                   const int32_t* __restrict__ top_idx, int32_t* __restrict__ src_row,
                                   int32_t* __restrict__ next_tok) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_trigger();
+  pdl_wait();
   if (k >= bs.images) return;
   beam_merge_image(bs, k, t, top_val, top_idx, src_row, next_tok);
 }
@@ -387,7 +392,7 @@ int beam_merge(const BeamState& bs, int t, const float* top_val, const int32_t* 
                int32_t* next_tok, cudaStream_t st) {
   ProfScope prof__(TAG_BEAM, st);
   if (bs.images == 0) return RFN_OK;
-  beam_merge_kernel<<<(bs.images + 63) / 64, 64, 0, st>>>(bs, t, top_val, top_idx, src_row, next_tok);
+  RFN_CUDA(launch_pdl(beam_merge_kernel, dim3((bs.images + 63) / 64), dim3(64), 0, st, bs, t, top_val, top_idx, src_row, next_tok));
   RFN_LAUNCH_CHECK();
   return RFN_OK;
 }

@@ -257,3 +257,35 @@ def test_persistent_decoder_matches_oracle_and_the_per_step_path(make_cfg, sharp
                     assert torch.equal(x, y)
     finally:
         _capi.check(_capi.lib().rfn_set_persistent_decoder(1))
+
+
+def test_programmatic_dependent_launch_does_not_change_results():
+    """rfn_set_pdl: the decode path's kernels launched with programmatic stream serialization (their prologues overlap the
+    predecessor's tail, griddepcontrol.wait before the first global access) give bit-identical results to plain stream order,
+    eagerly and replayed from a CUDA graph."""
+    from recurrent_fusion_network_b200 import _capi
+    from recurrent_fusion_network_b200.graphs import GraphedBeamSearch
+    _capi.check(_capi.lib().rfn_set_gemm_mode(4))
+    cfg = O.config1(49)
+    sd = O.make_state_dict(cfg, seed=1234, sharpen=True)
+    m = build_model(cfg, sd)
+    fc, att = [cuda_list(t) for t in O.make_inputs(cfg, 130, seed=71)]
+    out = {}
+    try:
+        for on in (0, 1):
+            _capi.check(_capi.lib().rfn_set_pdl(on))
+            with torch.no_grad():
+                for _ in range(3):      # repeated: a missing dependency would show up as run-to-run differences
+                    r = m._beam_tensors(fc, att, 130, 3)
+                    key = (on, "eager")
+                    if key in out:
+                        assert torch.equal(out[key][0], r[0]) and torch.equal(out[key][1], r[1])
+                    out[key] = (r[0].clone(), r[1].clone())
+            g = GraphedBeamSearch(m, fc, att, beam_size=3)
+            r = g()
+            out[(on, "graph")] = (r[0].clone(), r[1].clone())
+    finally:
+        _capi.check(_capi.lib().rfn_set_pdl(0))
+    ref = out[(0, "eager")]
+    for k, v in out.items():
+        assert torch.equal(v[0], ref[0]) and torch.equal(v[1], ref[1]), k
