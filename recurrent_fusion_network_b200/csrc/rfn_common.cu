@@ -41,6 +41,10 @@ static cudaEvent_t prof_event() {
   return e;
 }
 bool prof_enabled() { return g_prof_on.load(std::memory_order_relaxed) != 0; }
+static thread_local int g_conc_hint = 1;
+int concurrency_hint() { return g_conc_hint; }
+ConcurrencyScope::ConcurrencyScope(int n) : prev(g_conc_hint) { g_conc_hint = n < 1 ? 1 : n; }
+ConcurrencyScope::~ConcurrencyScope() { g_conc_hint = prev; }
 TagScope::TagScope(int tag) : prev(g_tag_override) { g_tag_override = tag; }
 TagScope::~TagScope() { g_tag_override = prev; }
 ProfScope::ProfScope(int default_tag, cudaStream_t st, bool fixed_tag) : st_(st), idx_(-1) {

@@ -579,7 +579,10 @@ static int launch_h3(const H3Args& t, int bf16, cudaStream_t st) {
   const int total = n_tiles * n_pairs;
   // as few clusters as finish in the same number of waves: a launch of 314 tiles takes 5 waves on 74 cluster slots and on 63,
   // and the 22 SMs it then leaves alone run the other encoder streams' kernels meanwhile (matters for small shards)
-  const int slots = n_sm / 2;
+  int slots = n_sm / 2;
+  // short launches issued side by side with other encoder streams (concurrency_hint() > 1) take half of the cluster slots:
+  // 314 tiles are 5 waves on 74 slots but 9 on 37, i.e. 4.5 waves' worth of the machine, with a sibling launch in the other half
+  if (concurrency_hint() > 1 && total <= 6 * slots) slots = (slots + 1) / 2;
   const int waves = (total + slots - 1) / slots;
   const int clusters = (total + waves - 1) / waves;
   cudaLaunchConfig_t cfg{};

@@ -31,6 +31,15 @@ enum Tag {
   TAG_COUNT = 13
 };
 bool prof_enabled();
+// how many independent kernel chains the caller is issuing side by side (the J encoder streams of a fusion step): a GEMM
+// launch that would take only a few waves then sizes its grid for its share of the SMs, so that two such launches run
+// concurrently instead of one after the other with a partly empty last wave each
+int concurrency_hint();
+struct ConcurrencyScope {
+  int prev;
+  explicit ConcurrencyScope(int n);
+  ~ConcurrencyScope();
+};
 struct TagScope {  // call-site override of a launcher's default class
   int prev;
   explicit TagScope(int tag);

@@ -97,6 +97,7 @@ static int for_each_encoder(int J, cudaStream_t st, F&& fn) {
     return RFN_OK;
   }
   RFN_CUDA(cudaEventRecord(sp->fork, st));
+  ConcurrencyScope conc(J);
   for (int j = 0; j < J; ++j) {
     RFN_CUDA(cudaStreamWaitEvent(sp->s[j], sp->fork, 0));
     RFN_TRY(fn(j, sp->s[j]));
