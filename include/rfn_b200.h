@@ -191,6 +191,19 @@ int rfn_attention_core_f32(const float* h, const float* A, const float* U_w, con
 int rfn_lstm_cell_f32(const float* G, const float* c_prev, float* h_out, float* c_out,
                       float* h_out2, int ldh2, int rows, int R, rfn_stream_t stream);
 
+/* The same with nn.Dropout applied to h' (training, misc/LSTMSoftAttentionCore.py:98-100: the dropped h' is both the output
+ * and the carried state): h' = scale * mask * sig(o) tanh(c'), mask (rows,R) of 0/1 (NULL: no dropout). */
+int rfn_lstm_cell_drop_f32(const float* G, const float* c_prev, const float* mask, float scale, float* h_out,
+                           float* c_out, float* h_out2, int ldh2, float* h_out3, int ldh3, int rows, int R,
+                           rfn_stream_t stream);
+/* out[r,:] = alpha * sum_i x_i[r,:] over n <= 8 strided (rows, R) sources, and
+ * out[r,:] = (((0 + in_0[r,:]) + in_1[r,:]) + ...) / n with in_j = in + j*stride (the stage-1 -> stage-2 bridge,
+ * misc/RecurrentFusionModel.py:307-309, in Python's summation order). */
+int rfn_sum_strided_f32(int n, const float* const* x, const int* ldx, float alpha, float* out, int ldo, int rows, int R,
+                        rfn_stream_t stream);
+int rfn_mean_tensors_f32(const float* in, size_t stride, int n, float* out, int ld_out, int rows, int R, int ld_in,
+                         rfn_stream_t stream);
+
 /* lp[r,:] = log_softmax(logits[r,:]) (F.log_softmax, misc/RecurrentFusionModel.py:278). */
 int rfn_log_softmax_f32(const float* logits, int ld_in, float* lp, int ld_out, int rows, int V,
                         rfn_stream_t stream);
@@ -278,11 +291,20 @@ int rfn_ensemble_decode_greedy(const rfn_dims* dims, int n_models, const float* 
 int rfn_xe_loss_f32(const float* logprobs, const int64_t* target, const float* mask, int ld_t,
                     int rows, int T, int V, float eps, float* out, rfn_stream_t stream);
 
+/* The same with lp[b,t,:] at logprobs + b*ld_b + t*ld_s (floats): the time-major (T, rows, V) log-prob table of the fused
+ * training tape (tape.py) is read in place, ld_b = V, ld_s = rows*V. */
+int rfn_xe_loss_strided_f32(const float* logprobs, size_t ld_b, size_t ld_s, const int64_t* target, const float* mask,
+                            int ld_t, int rows, int T, int V, float eps, float* out, rfn_stream_t stream);
+
 /* ReviewNetRewardCriterion's sequence + entropy terms, non-PPO (misc/utils.py:50-72):
  * out[0] = -(1/rows) sum m l R + (entropy_reg/rows) sum_{b,t} m0 sum_v p log p. */
 int rfn_rl_loss_f32(const float* sample_logprobs, const int64_t* seq, const float* reward,
                     const float* logprobs_all, int ld_lp_rows, int rows, int T, int V,
                     float entropy_reg, float* out, rfn_stream_t stream);
+
+int rfn_rl_loss_strided_f32(const float* sample_logprobs, const int64_t* seq, const float* reward,
+                            const float* logprobs_all, size_t ld_b, size_t ld_s, int rows, int T, int V,
+                            float entropy_reg, float* out, rfn_stream_t stream);
 
 /* nn.MultiLabelMarginLoss (mean reduction) scaled by `weight`, the discriminative term of both
  * criteria (misc/utils.py:76-82, :186-190): out[0] (+)= weight * mean_rows(margin loss).
@@ -322,6 +344,17 @@ int rfn_attention_step_bwd_f32(const float* A, const float* P, const float* g, c
 /* backward of rfn_lstm_cell_f32: (dh, dc_next may be NULL) -> dG (rows,4R), dc_prev (rows,R) */
 int rfn_lstm_cell_bwd_f32(const float* G, const float* c_prev, const float* dh, const float* dc_next,
                           float* dG, float* dc_prev, int rows, int R, rfn_stream_t stream);
+/* The same with dh = sum of n_dh (<= 8) strided sources dh[i] (rows, R, leading dimension ld_dh[i]) and an optional dropout
+ * keep-mask on h (dh_raw = scale * mask * dh): the hand-scheduled backward of tape.py feeds the gradient pieces of h (the
+ * thought-vector slot, the slice of dH from the next fusion step, the next step's query gradient) without add kernels. */
+int rfn_lstm_cell_bwd_multi_f32(const float* G, const float* c_prev, int n_dh, const float* const* dh, const int* ld_dh,
+                                const float* mask, float scale, const float* dc_next, float* dG, float* dc_prev,
+                                int rows, int R, rfn_stream_t stream);
+/* dX[M,K] (+)= sum_i dY_i[M,N_i] . W_i[N_i,K], 1 <= n_src <= 3: the input gradient of y = sum_i x_i W_i^T (nn.Linear weights
+ * (out, in) are read as they lie, MN-major on the tensor engine), and with several dY_i the sum over the consumers of one
+ * input -- dH of a fusion step, misc/RecurrentFusionModel.py:53,102-107 -- in one launch. */
+int rfn_linear_bwd_x_f32(int n_src, const float* const* dY, const int* lddy, const float* const* W, const int* ldw,
+                         const int* Nc, float* dX, int lddx, int M, int K, int accumulate, rfn_stream_t stream);
 /* dx = dlp - exp(lp) * sum_v dlp */
 int rfn_log_softmax_bwd_f32(const float* lp, size_t ld_lp, const float* dlp, size_t ld_d, float* dx,
                             size_t ld_x, int rows, int V, rfn_stream_t stream);
@@ -359,6 +392,12 @@ int rfn_rl_loss_bwd_f32(const int64_t* seq, const float* reward, const float* lp
                         float* dlp_all, rfn_stream_t stream);
 int rfn_multilabel_margin_bwd_f32(const float* pred, const int64_t* target, int rows, int K, float weight,
                                   const float* gout, float* dx, rfn_stream_t stream);
+/* strided variants (dlp[b,t,:] at dlp + b*ld_b + t*ld_s; likewise lp_all / dlp_all), see rfn_xe_loss_strided_f32 */
+int rfn_xe_loss_bwd_strided_f32(const int64_t* target, const float* mask, int ld_t, int rows, int T, int V, float eps,
+                                const float* gout, float* dlp, size_t ld_b, size_t ld_s, rfn_stream_t stream);
+int rfn_rl_loss_bwd_strided_f32(const int64_t* seq, const float* reward, const float* lp_all, size_t ld_b, size_t ld_s,
+                                int rows, int T, int T1, int V, float entropy_reg, const float* gout, float* dslp,
+                                float* dlp_all, rfn_stream_t stream);
 
 /* Fused clip_gradient (element-wise clamp to +-grad_clip, misc/utils.py:292-296; <= 0 disables) + Adam step with
  * L2 weight decay (torch.optim.Adam semantics, train.py:56,160-163) over n_tensors parameter tensors; `step` is the

@@ -117,6 +117,15 @@ _SIGNATURES = {
     "rfn_transpose_f32": (_i, [_vp, _i, _i, _i, _vp, _i, _vp]),
     "rfn_adam_step_f32": (_i, [_i, _pp, _pp, _pp, _pp, C.POINTER(C.c_int64), _f, _f, _f, _f, _f, _f, _f, _i, _vp, _vp]),
     "rfn_rl_loss_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
+    "rfn_lstm_cell_drop_f32": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp]),
+    "rfn_sum_strided_f32": (_i, [_i, _pp, C.POINTER(_i), _f, _vp, _i, _i, _i, _vp]),
+    "rfn_mean_tensors_f32": (_i, [_vp, _sz, _i, _vp, _i, _i, _i, _i, _vp]),
+    "rfn_xe_loss_strided_f32": (_i, [_vp, _sz, _sz, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
+    "rfn_rl_loss_strided_f32": (_i, [_vp, _vp, _vp, _vp, _sz, _sz, _i, _i, _i, _f, _vp, _vp]),
+    "rfn_lstm_cell_bwd_multi_f32": (_i, [_vp, _vp, _i, _pp, C.POINTER(_i), _vp, _f, _vp, _vp, _vp, _i, _i, _vp]),
+    "rfn_linear_bwd_x_f32": (_i, [_i, _pp, C.POINTER(_i), _pp, C.POINTER(_i), C.POINTER(_i), _vp, _i, _i, _i, _i, _vp]),
+    "rfn_xe_loss_bwd_strided_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _sz, _sz, _vp]),
+    "rfn_rl_loss_bwd_strided_f32": (_i, [_vp, _vp, _vp, _sz, _sz, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

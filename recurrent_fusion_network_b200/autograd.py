@@ -19,6 +19,16 @@ def _c(t):
     return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
 
 
+def _dense3(t):
+    """A (rows, T, V) fp32 table as the criteria kernels address it: unit stride over V and either the contiguous layout or
+    its time-major transpose (what tape.DecoderFn produces); anything else is copied."""
+    if t.dtype == torch.float32 and t.dim() == 3 and t.stride(2) == 1:
+        rows, T, V = t.shape
+        if (t.stride(0), t.stride(1)) in ((T * V, V), (V, rows * V)):
+            return t
+    return t.float().contiguous()
+
+
 def _gemm_general(a_k, b_k, A, lda, B, ldb, Cm, ldc, M, N, K, accumulate=0):
     check(lib().rfn_gemm_general_f32(int(a_k), int(b_k), ptr(A), lda, ptr(B), ldb, ptr(Cm), ldc, M, N, K, int(accumulate),
                                      stream()), "rfn_gemm_general_f32")
@@ -324,9 +334,16 @@ class DropoutFn(Function):
         return dx, None, None
 
 
+#: test hook: a list of keep-masks consumed front to back instead of drawing them (tests/test_gpu_tape.py feeds the per-op
+#: tape and the fused tape the same masks)
+MASK_QUEUE = None
+
+
 def dropout(x, p, training, mask=None):
     if not training or p <= 0:
         return x
+    if mask is None and MASK_QUEUE:
+        mask = MASK_QUEUE.pop(0)
     if mask is None:
         mask = (torch.rand_like(x) >= p).float()
     return DropoutFn.apply(x, mask, 1.0 / (1.0 - p))
@@ -399,15 +416,16 @@ class XeLossFn(Function):
 
     @staticmethod
     def forward(ctx, lp, target, mask, eps):
-        lp = _c(lp)
+        lp = _dense3(lp)
         rows, T, V = lp.shape
-        target = target.to(torch.int64).contiguous()
-        mask = _c(mask)
+        target = target[:, :T].to(torch.int64).contiguous()
+        mask = _c(mask[:, :T])
         out = torch.zeros(1, dtype=torch.float32, device=lp.device)
-        check(lib().rfn_xe_loss_f32(ptr(lp), ptr(target), ptr(mask), target.stride(0), rows, T, V, float(eps), ptr(out),
-                                    stream()), "rfn_xe_loss_f32")
+        check(lib().rfn_xe_loss_strided_f32(ptr(lp), lp.stride(0), lp.stride(1), ptr(target), ptr(mask), target.stride(0), rows, T,
+                                            V, float(eps), ptr(out), stream()), "rfn_xe_loss_strided_f32")
         ctx.save_for_backward(target, mask)
         ctx.dims = (rows, T, V, float(eps))
+        ctx.strides = (lp.stride(0), lp.stride(1))
         return out
 
     @staticmethod
@@ -415,9 +433,10 @@ class XeLossFn(Function):
     def backward(ctx, gout):
         target, mask = ctx.saved_tensors
         rows, T, V, eps = ctx.dims
-        dlp = torch.empty(rows, T, V, dtype=torch.float32, device=gout.device)
-        check(lib().rfn_xe_loss_bwd_f32(ptr(target), ptr(mask), target.stride(0), rows, T, V, eps, ptr(_c(gout)), ptr(dlp),
-                                        stream()), "rfn_xe_loss_bwd_f32")
+        ld_b, ld_s = ctx.strides      # the gradient takes the layout of the log-prob table (time-major from tape.DecoderFn)
+        dlp = torch.empty_strided((rows, T, V), (ld_b, ld_s, 1), dtype=torch.float32, device=gout.device)
+        check(lib().rfn_xe_loss_bwd_strided_f32(ptr(target), ptr(mask), target.stride(0), rows, T, V, eps, ptr(_c(gout)), ptr(dlp),
+                                                ld_b, ld_s, stream()), "rfn_xe_loss_bwd_strided_f32")
         return dlp, None, None, None
 
 
@@ -426,13 +445,13 @@ class RlLossFn(Function):
 
     @staticmethod
     def forward(ctx, slp, seq, reward, lp_all, entropy_reg):
-        slp, reward, lp_all = _c(slp), _c(reward), _c(lp_all)
+        slp, reward, lp_all = _c(slp), _c(reward), _dense3(lp_all)
         seq = seq.to(torch.int64).contiguous()
         rows, T = slp.shape
         T1, V = lp_all.shape[1], lp_all.shape[2]
         out = torch.zeros(1, dtype=torch.float32, device=slp.device)
-        check(lib().rfn_rl_loss_f32(ptr(slp), ptr(seq), ptr(reward), ptr(lp_all), lp_all.stride(0), rows, T, V,
-                                    float(entropy_reg), ptr(out), stream()), "rfn_rl_loss_f32")
+        check(lib().rfn_rl_loss_strided_f32(ptr(slp), ptr(seq), ptr(reward), ptr(lp_all), lp_all.stride(0), lp_all.stride(1), rows,
+                                            T, V, float(entropy_reg), ptr(out), stream()), "rfn_rl_loss_strided_f32")
         ctx.save_for_backward(seq, reward, lp_all)
         ctx.dims = (rows, T, T1, V, float(entropy_reg))
         return out
@@ -443,9 +462,9 @@ class RlLossFn(Function):
         seq, reward, lp_all = ctx.saved_tensors
         rows, T, T1, V, ent = ctx.dims
         dslp = torch.empty(rows, T, dtype=torch.float32, device=gout.device)
-        dlp = torch.empty(rows, T1, V, dtype=torch.float32, device=gout.device)
-        check(lib().rfn_rl_loss_bwd_f32(ptr(seq), ptr(reward), ptr(lp_all), lp_all.stride(0), rows, T, T1, V, ent,
-                                        ptr(_c(gout)), ptr(dslp), ptr(dlp), stream()), "rfn_rl_loss_bwd_f32")
+        dlp = torch.empty_strided((rows, T1, V), (lp_all.stride(0), lp_all.stride(1), 1), dtype=torch.float32, device=gout.device)
+        check(lib().rfn_rl_loss_bwd_strided_f32(ptr(seq), ptr(reward), ptr(lp_all), lp_all.stride(0), lp_all.stride(1), rows, T, T1,
+                                                V, ent, ptr(_c(gout)), ptr(dslp), ptr(dlp), stream()), "rfn_rl_loss_bwd_strided_f32")
         return dslp, None, None, dlp, None
 
 

@@ -186,9 +186,33 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ d
     atomicAdd(db + n, t);
   }
 }
+// the same for M <= 256 (one row slab per column block): plain store / read-add-store, no memset and no atomics, so
+// the result does not depend on arrival order (every bias gradient of an 80-row training batch takes this route)
+__global__ void __launch_bounds__(256) colsum_small_kernel(const float* __restrict__ dY, int ld, int M, int N, float* db,
+                                                           int accumulate) {
+  __shared__ float s_p[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + tx;
+  float s = 0.f;
+  if (n < N)
+    for (int m = ty; m < M; m += 8) s += dY[(size_t)m * ld + n];
+  s_p[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += s_p[i][tx];
+    db[n] = accumulate ? db[n] + t : t;
+  }
+}
 int colsum(const float* dY, int ld, int M, int N, float* db, int accumulate, cudaStream_t st) {
   ProfScope prof__(TAG_MISC, st);
   if (N == 0) return RFN_OK;
+  if (M > 0 && M <= 256) {
+    colsum_small_kernel<<<(N + 31) / 32, 256, 0, st>>>(dY, ld, M, N, db, accumulate);
+    RFN_LAUNCH_CHECK();
+    return RFN_OK;
+  }
   if (!accumulate) RFN_CUDA(cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), st));
   if (M == 0) return RFN_OK;
   colsum_kernel<<<dim3((N + 31) / 32, (M + 255) / 256), 256, 0, st>>>(dY, ld, M, N, db);
@@ -336,6 +360,50 @@ int lstm_cell_bwd(const float* G, const float* c_prev, const float* dh, const fl
   if (rows == 0) return RFN_OK;
   const size_t total = (size_t)rows * R;
   lstm_cell_bwd_kernel<<<(int)min((size_t)148 * 8, (total + 255) / 256), 256, 0, st>>>(G, c_prev, dh, dc_next, dG, dc_prev, rows, R);
+  RFN_LAUNCH_CHECK();
+  return RFN_OK;
+}
+
+// The same with dh given as the SUM of up to 8 strided sources (the thought-vector slot's gradient, the slice of dH the
+// next fusion step returned, the query gradient of the next step's attention, ...), an optional dropout keep-mask on h
+// (h = mask * scale * o tanh(c), so dh_raw = mask * scale * dh) -- replaces the add / mul kernels between the steps of a
+// hand-scheduled backward pass (recurrent_fusion_network_b200/tape.py).
+struct CellBwdSrcs {
+  const float* p[8];
+  int ld[8];
+  int n;
+};
+__global__ void lstm_cell_bwd_multi_kernel(const float* __restrict__ G, const float* __restrict__ c_prev, CellBwdSrcs src,
+                                           const float* __restrict__ mask, float scale, const float* __restrict__ dc_next,
+                                           float* __restrict__ dG, float* __restrict__ dc_prev, int rows, int R) {
+  const size_t total = (size_t)rows * R;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / R), k = (int)(i % R);
+    const float* Gr = G + (size_t)r * 4 * R;
+    const float ig = sigm(Gr[k]), fg = sigm(Gr[R + k]), og = sigm(Gr[2 * R + k]), gg = tanhf(Gr[3 * R + k]);
+    const float cp = c_prev[i];
+    const float c2 = fg * cp + ig * gg;
+    const float tc = tanhf(c2);
+    float dhv = 0.f;
+    for (int s = 0; s < src.n; ++s) dhv += src.p[s][(size_t)r * src.ld[s] + k];
+    if (mask) dhv *= mask[i] * scale;
+    const float dc = (dc_next ? dc_next[i] : 0.f) + dhv * og * (1.f - tc * tc);
+    float* dGr = dG + (size_t)r * 4 * R;
+    dGr[k] = dc * gg * ig * (1.f - ig);
+    dGr[R + k] = dc * cp * fg * (1.f - fg);
+    dGr[2 * R + k] = dhv * tc * og * (1.f - og);
+    dGr[3 * R + k] = dc * ig * (1.f - gg * gg);
+    dc_prev[i] = dc * fg;
+  }
+}
+int lstm_cell_bwd_multi(const float* G, const float* c_prev, const CellBwdSrcs& src, const float* mask, float scale,
+                        const float* dc_next, float* dG, float* dc_prev, int rows, int R, cudaStream_t st) {
+  ProfScope prof__(TAG_CELL, st);
+  RFN_CHECK_ARG(G && c_prev && dG && dc_prev, "lstm_cell_bwd_multi: null pointer");
+  if (rows == 0) return RFN_OK;
+  const size_t total = (size_t)rows * R;
+  lstm_cell_bwd_multi_kernel<<<(int)min((size_t)148 * 8, (total + 255) / 256), 256, 0, st>>>(G, c_prev, src, mask, scale, dc_next,
+                                                                                          dG, dc_prev, rows, R);
   RFN_LAUNCH_CHECK();
   return RFN_OK;
 }
@@ -548,20 +616,20 @@ __global__ void group_sum_kernel(const float* __restrict__ x, float* __restrict_
 // XE (misc/utils.py:161-184): dL/dlp[b,t,v] = -gout * mask[b,t]/rows * ((1-eps) 1[v == y] + eps/V)
 __global__ void __launch_bounds__(256)
 xe_loss_bwd_kernel(const int64_t* __restrict__ target, const float* __restrict__ mask, int ld_t, int T, int V, float eps,
-                   float inv_rows, const float* __restrict__ gout, float* __restrict__ dlp) {
+                   float inv_rows, const float* __restrict__ gout, float* __restrict__ dlp, size_t ld_b, size_t ld_s) {
   const int b = blockIdx.x / T, t = blockIdx.x % T;
   const float mk = mask[(size_t)b * ld_t + t] * inv_rows * gout[0];
   long long y = target[(size_t)b * ld_t + t];
   y = y < 0 ? 0 : (y >= V ? V - 1 : y);
-  float* o = dlp + ((size_t)b * T + t) * V;
+  float* o = dlp + (size_t)b * ld_b + (size_t)t * ld_s;
   const float base = -mk * (eps / (float)V);
   for (int v = threadIdx.x; v < V; v += 256) o[v] = base + (v == (int)y ? -mk * (1.f - eps) : 0.f);
 }
 int xe_loss_bwd(const int64_t* target, const float* mask, int ld_t, int rows, int T, int V, float eps, const float* gout,
-                float* dlp, cudaStream_t st) {
+                float* dlp, size_t ld_b, size_t ld_s, cudaStream_t st) {
   ProfScope prof__(TAG_VOCAB, st);
   if (rows * T == 0) return RFN_OK;
-  xe_loss_bwd_kernel<<<rows * T, 256, 0, st>>>(target, mask, ld_t, T, V, eps, 1.f / (float)rows, gout, dlp);
+  xe_loss_bwd_kernel<<<rows * T, 256, 0, st>>>(target, mask, ld_t, T, V, eps, 1.f / (float)rows, gout, dlp, ld_b, ld_s);
   RFN_LAUNCH_CHECK();
   return RFN_OK;
 }
@@ -570,10 +638,10 @@ int xe_loss_bwd(const int64_t* target, const float* mask, int ld_t, int rows, in
 //   d/d lp_all[b,t,v] = gout * entropy_reg/rows * m0 * p (1 + lp)   for t < T, 0 for the extra last step
 __global__ void __launch_bounds__(256)
 rl_loss_bwd_kernel(const int64_t* __restrict__ seq, const float* __restrict__ reward, const float* __restrict__ lp_all,
-                   int ld_lp_rows, int T, int T1, int V, float entropy_reg, float inv_rows, const float* __restrict__ gout,
-                   float* __restrict__ dslp, float* __restrict__ dlp_all) {
+                   size_t ld_lp_rows, size_t ld_lp_s, int T, int T1, int V, float entropy_reg, float inv_rows,
+                   const float* __restrict__ gout, float* __restrict__ dslp, float* __restrict__ dlp_all) {
   const int b = blockIdx.x / T1, t = blockIdx.x % T1;
-  float* o = dlp_all + (size_t)b * ld_lp_rows + (size_t)t * V;
+  float* o = dlp_all + (size_t)b * ld_lp_rows + (size_t)t * ld_lp_s;
   if (t >= T) {
     for (int v = threadIdx.x; v < V; v += 256) o[v] = 0.f;
     return;
@@ -582,19 +650,19 @@ rl_loss_bwd_kernel(const int64_t* __restrict__ seq, const float* __restrict__ re
   const bool m = (t == 0) ? true : (seq[(size_t)b * T + t - 1] > 0);
   const float go = gout[0];
   if (threadIdx.x == 0) dslp[(size_t)b * T + t] = m ? -go * reward[(size_t)b * T + t] * inv_rows : 0.f;
-  const float* x = lp_all + (size_t)b * ld_lp_rows + (size_t)t * V;
+  const float* x = lp_all + (size_t)b * ld_lp_rows + (size_t)t * ld_lp_s;
   const float c = m0 ? go * entropy_reg * inv_rows : 0.f;
   for (int v = threadIdx.x; v < V; v += 256) {
     const float l = x[v];
     o[v] = c * expf(l) * (1.f + l);
   }
 }
-int rl_loss_bwd(const int64_t* seq, const float* reward, const float* lp_all, int ld_lp_rows, int rows, int T, int T1, int V,
-                float entropy_reg, const float* gout, float* dslp, float* dlp_all, cudaStream_t st) {
+int rl_loss_bwd(const int64_t* seq, const float* reward, const float* lp_all, size_t ld_lp_rows, size_t ld_lp_s, int rows, int T,
+                int T1, int V, float entropy_reg, const float* gout, float* dslp, float* dlp_all, cudaStream_t st) {
   ProfScope prof__(TAG_VOCAB, st);
   if (rows * T1 == 0) return RFN_OK;
-  rl_loss_bwd_kernel<<<rows * T1, 256, 0, st>>>(seq, reward, lp_all, ld_lp_rows, T, T1, V, entropy_reg, 1.f / (float)rows, gout,
-                                                dslp, dlp_all);
+  rl_loss_bwd_kernel<<<rows * T1, 256, 0, st>>>(seq, reward, lp_all, ld_lp_rows, ld_lp_s, T, T1, V, entropy_reg, 1.f / (float)rows,
+                                                gout, dslp, dlp_all);
   RFN_LAUNCH_CHECK();
   return RFN_OK;
 }
@@ -715,12 +783,61 @@ int rfn_axpby_f32(float alpha, const float* x, float beta, const float* y, float
 int rfn_xe_loss_bwd_f32(const int64_t* target, const float* mask, int ld_t, int rows, int T, int V, float eps,
                         const float* gout, float* dlp, rfn_stream_t stream) {
   RFN_CHECK_ARG(target && mask && gout && dlp, "rfn_xe_loss_bwd_f32: null pointer");
-  return xe_loss_bwd(target, mask, ld_t, rows, T, V, eps, gout, dlp, (cudaStream_t)stream);
+  return xe_loss_bwd(target, mask, ld_t, rows, T, V, eps, gout, dlp, (size_t)T * V, (size_t)V, (cudaStream_t)stream);
+}
+int rfn_xe_loss_bwd_strided_f32(const int64_t* target, const float* mask, int ld_t, int rows, int T, int V, float eps,
+                                const float* gout, float* dlp, size_t ld_b, size_t ld_s, rfn_stream_t stream) {
+  RFN_CHECK_ARG(target && mask && gout && dlp, "rfn_xe_loss_bwd_strided_f32: null pointer");
+  return xe_loss_bwd(target, mask, ld_t, rows, T, V, eps, gout, dlp, ld_b, ld_s, (cudaStream_t)stream);
 }
 int rfn_rl_loss_bwd_f32(const int64_t* seq, const float* reward, const float* lp_all, int ld_lp_rows, int rows, int T, int T1,
                         int V, float entropy_reg, const float* gout, float* dslp, float* dlp_all, rfn_stream_t stream) {
   RFN_CHECK_ARG(seq && reward && lp_all && gout && dslp && dlp_all, "rfn_rl_loss_bwd_f32: null pointer");
-  return rl_loss_bwd(seq, reward, lp_all, ld_lp_rows, rows, T, T1, V, entropy_reg, gout, dslp, dlp_all, (cudaStream_t)stream);
+  return rl_loss_bwd(seq, reward, lp_all, (size_t)ld_lp_rows, (size_t)V, rows, T, T1, V, entropy_reg, gout, dslp, dlp_all,
+                     (cudaStream_t)stream);
+}
+int rfn_rl_loss_bwd_strided_f32(const int64_t* seq, const float* reward, const float* lp_all, size_t ld_b, size_t ld_s, int rows,
+                                int T, int T1, int V, float entropy_reg, const float* gout, float* dslp, float* dlp_all,
+                                rfn_stream_t stream) {
+  RFN_CHECK_ARG(seq && reward && lp_all && gout && dslp && dlp_all, "rfn_rl_loss_bwd_strided_f32: null pointer");
+  return rl_loss_bwd(seq, reward, lp_all, ld_b, ld_s, rows, T, T1, V, entropy_reg, gout, dslp, dlp_all, (cudaStream_t)stream);
+}
+int rfn_lstm_cell_bwd_multi_f32(const float* G, const float* c_prev, int n_dh, const float* const* dh, const int* ld_dh,
+                                const float* mask, float scale, const float* dc_next, float* dG, float* dc_prev, int rows, int R,
+                                rfn_stream_t stream) {
+  RFN_CHECK_ARG(n_dh >= 0 && n_dh <= 8 && (n_dh == 0 || (dh && ld_dh)), "rfn_lstm_cell_bwd_multi_f32: 0..8 dh sources");
+  CellBwdSrcs src{};
+  src.n = n_dh;
+  for (int s = 0; s < n_dh; ++s) {
+    RFN_CHECK_ARG(dh[s] != nullptr, "rfn_lstm_cell_bwd_multi_f32: dh source %d is null", s);
+    src.p[s] = dh[s];
+    src.ld[s] = ld_dh[s];
+  }
+  return lstm_cell_bwd_multi(G, c_prev, src, mask, scale, dc_next, dG, dc_prev, rows, R, (cudaStream_t)stream);
+}
+/* dX[M,K] (+)= sum_i dY_i[M,N_i] . W_i[N_i,K]: the input gradient of y = sum_i x_i W_i^T, and with several dY_i the sum over
+ * the consumers of one input (dH of a fusion step = sum over the J encoders' gate GEMMs) in ONE launch. */
+int rfn_linear_bwd_x_f32(int n_src, const float* const* dY, const int* lddy, const float* const* W, const int* ldw,
+                         const int* Nc, float* dX, int lddx, int M, int K, int accumulate, rfn_stream_t stream) {
+  RFN_CHECK_ARG(n_src >= 1 && n_src <= 3 && dY && lddy && W && ldw && Nc && dX, "rfn_linear_bwd_x_f32: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  bool tc = gemm_mode() >= 1 && K >= 128;
+  long work = 0;
+  for (int s = 0; s < n_src; ++s) {
+    tc = tc && tc_general_ok(dY[s], lddy[s], W[s], ldw[s], dX, lddx, K, Nc[s]);
+    work += (long)M * K * Nc[s];
+  }
+  if (tc && work >= (1L << 25)) {
+    ProfScope prof__(TAG_GEMM_BWD, st);
+    GemmArgs g{};
+    for (int s = 0; s < n_src; ++s) g.src[s] = GemmSrc{dY[s], W[s], nullptr, lddy[s], ldw[s], Nc[s]};
+    g.nsrc = n_src;
+    g.y = dX; g.ldy = lddx; g.M = M; g.N = K; g.accumulate = accumulate ? 1 : 0; g.splitk_ok = 1;
+    return gemm_tc_splitk(g, true, tc_passes(gemm_mode()), st);
+  }
+  for (int s = 0; s < n_src; ++s)
+    RFN_TRY(gemm_general(true, false, dY[s], lddy[s], W[s], ldw[s], dX, lddx, M, K, Nc[s], (accumulate || s > 0) ? 1 : 0, st));
+  return RFN_OK;
 }
 int rfn_multilabel_margin_bwd_f32(const float* pred, const int64_t* target, int rows, int K, float weight, const float* gout,
                                   float* dx, rfn_stream_t stream) {

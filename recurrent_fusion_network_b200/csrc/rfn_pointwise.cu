@@ -11,7 +11,7 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 __global__ void lstm_cell_kernel(const float* __restrict__ G, const float* c_prev,
                                  float* __restrict__ h_out, float* c_out,
                                  float* __restrict__ h_out2, int ldh2, float* __restrict__ h_out3,
-                                 int ldh3, int rows, int R) {
+                                 int ldh3, int rows, int R, const float* __restrict__ mask, float scale) {
   pdl_trigger();
   pdl_wait();
   const size_t total = (size_t)rows * R;
@@ -23,7 +23,8 @@ __global__ void lstm_cell_kernel(const float* __restrict__ G, const float* c_pre
     const float og = sigmoidf_(Gr[2 * R + k]);
     const float gg = tanhf(Gr[3 * R + k]);
     const float c2 = fg * c_prev[i] + ig * gg;
-    const float h2 = og * tanhf(c2);
+    float h2 = og * tanhf(c2);
+    if (mask) h2 = scale * h2 * mask[i];   // nn.Dropout with an explicit keep-mask (training): the state carries the dropped h
     c_out[i] = c2;
     if (h_out) h_out[i] = h2;
     if (h_out2) h_out2[(size_t)r * ldh2 + k] = h2;
@@ -32,13 +33,13 @@ __global__ void lstm_cell_kernel(const float* __restrict__ G, const float* c_pre
 }
 
 int lstm_cell(const float* G, const float* c_prev, float* h_out, float* c_out, float* h_out2, int ldh2,
-              float* h_out3, int ldh3, int rows, int R, cudaStream_t st) {
+              float* h_out3, int ldh3, int rows, int R, cudaStream_t st, const float* mask, float scale) {
   ProfScope prof__(TAG_CELL, st);
   RFN_CHECK_ARG(G && c_prev && c_out, "lstm_cell: null pointer");
   if (rows == 0) return RFN_OK;
   const size_t total = (size_t)rows * R;
   const int blocks = (int)min((size_t)148 * 8, (total + 255) / 256);
-  RFN_CUDA(launch_pdl(lstm_cell_kernel, dim3(blocks), dim3(256), 0, st, G, c_prev, h_out, c_out, h_out2, ldh2, h_out3, ldh3, rows, R));
+  RFN_CUDA(launch_pdl(lstm_cell_kernel, dim3(blocks), dim3(256), 0, st, G, c_prev, h_out, c_out, h_out2, ldh2, h_out3, ldh3, rows, R, mask, scale));
   RFN_LAUNCH_CHECK();
   return RFN_OK;
 }
@@ -160,4 +161,50 @@ int mean_logits8(const PtrList8& ptrs, int n, float* out, size_t count, cudaStre
 extern "C" int rfn_lstm_cell_f32(const float* G, const float* c_prev, float* h_out, float* c_out, float* h_out2,
                                  int ldh2, int rows, int R, rfn_stream_t stream) {
   return rfn::lstm_cell(G, c_prev, h_out, c_out, h_out2, ldh2, nullptr, 0, rows, R, (cudaStream_t)stream);
+}
+
+extern "C" int rfn_lstm_cell_drop_f32(const float* G, const float* c_prev, const float* mask, float scale, float* h_out,
+                                      float* c_out, float* h_out2, int ldh2, float* h_out3, int ldh3, int rows, int R,
+                                      rfn_stream_t stream) {
+  return rfn::lstm_cell(G, c_prev, h_out, c_out, h_out2, ldh2, h_out3, ldh3, rows, R, (cudaStream_t)stream, mask, scale);
+}
+
+namespace rfn {
+struct SumSrcs {
+  const float* p[8];
+  int ld[8];
+  int n;
+};
+__global__ void sum_strided_kernel(SumSrcs src, float alpha, float* __restrict__ out, int ldo, int rows, int R) {
+  const size_t total = (size_t)rows * R;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / R), k = (int)(i % R);
+    float s = 0.f;
+    for (int j = 0; j < src.n; ++j) s += src.p[j][(size_t)r * src.ld[j] + k];
+    out[(size_t)r * ldo + k] = alpha * s;
+  }
+}
+}  // namespace rfn
+
+extern "C" int rfn_sum_strided_f32(int n, const float* const* x, const int* ldx, float alpha, float* out, int ldo, int rows, int R,
+                                   rfn_stream_t stream) {
+  RFN_CHECK_ARG(n >= 1 && n <= 8 && x && ldx && out, "rfn_sum_strided_f32: 1..8 sources");
+  if (rows == 0 || R == 0) return RFN_OK;
+  rfn::SumSrcs src{};
+  src.n = n;
+  for (int j = 0; j < n; ++j) {
+    RFN_CHECK_ARG(x[j] != nullptr, "rfn_sum_strided_f32: source %d is null", j);
+    src.p[j] = x[j];
+    src.ld[j] = ldx[j];
+  }
+  const size_t total = (size_t)rows * R;
+  rfn::sum_strided_kernel<<<(int)min((size_t)148 * 8, (total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, alpha, out, ldo, rows, R);
+  RFN_LAUNCH_CHECK();
+  return RFN_OK;
+}
+
+extern "C" int rfn_mean_tensors_f32(const float* in, size_t stride, int n, float* out, int ld_out, int rows, int R, int ld_in,
+                                    rfn_stream_t stream) {
+  RFN_CHECK_ARG(in && out && n >= 1, "rfn_mean_tensors_f32: bad arguments");
+  return rfn::mean_tensors(in, stride, n, out, ld_out, (size_t)rows * R, R, ld_in, (cudaStream_t)stream);
 }

@@ -408,13 +408,13 @@ int beam_finalize(const BeamState& bs, int64_t* seq, float* seq_lp, int32_t* don
 // ---- fused criteria reductions (misc/utils.py:161-184, :50-72) ---------------------------------
 // one CTA per (row, t): needs only lp[y] and sum_v lp_v (XE) or sum_v p log p (RL entropy)
 __global__ void __launch_bounds__(VT)
-xe_loss_kernel(const float* __restrict__ lp, const int64_t* __restrict__ target, const float* __restrict__ mask,
-               int ld_t, int T, int V, float eps, float inv_rows, float* __restrict__ out) {
+xe_loss_kernel(const float* __restrict__ lp, size_t ld_b, size_t ld_s, const int64_t* __restrict__ target,
+               const float* __restrict__ mask, int ld_t, int T, int V, float eps, float inv_rows, float* __restrict__ out) {
   __shared__ float s_red[VT / 32];
   const int b = blockIdx.x / T, t = blockIdx.x % T;
   const float mk = mask[(size_t)b * ld_t + t];
   if (mk == 0.f) return;
-  const float* x = lp + ((size_t)b * T + t) * V;
+  const float* x = lp + (size_t)b * ld_b + (size_t)t * ld_s;
   float sum = 0.f;
   if (eps > 0.f) {
     for (int v = threadIdx.x; v < V; v += VT) sum += x[v];
@@ -434,27 +434,27 @@ xe_loss_kernel(const float* __restrict__ lp, const int64_t* __restrict__ target,
   }
 }
 
-int xe_loss(const float* logprobs, const int64_t* target, const float* mask, int ld_t, int rows, int T, int V,
-            float eps, float* out, cudaStream_t st) {
+int xe_loss(const float* logprobs, size_t ld_b, size_t ld_s, const int64_t* target, const float* mask, int ld_t, int rows, int T,
+            int V, float eps, float* out, cudaStream_t st) {
   ProfScope prof__(TAG_VOCAB, st);
   RFN_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
   if (rows * T == 0) return RFN_OK;
-  xe_loss_kernel<<<rows * T, VT, 0, st>>>(logprobs, target, mask, ld_t, T, V, eps, 1.f / (float)rows, out);
+  xe_loss_kernel<<<rows * T, VT, 0, st>>>(logprobs, ld_b, ld_s, target, mask, ld_t, T, V, eps, 1.f / (float)rows, out);
   RFN_LAUNCH_CHECK();
   return RFN_OK;
 }
 
 __global__ void __launch_bounds__(VT)
 rl_loss_kernel(const float* __restrict__ slp, const int64_t* __restrict__ seq, const float* __restrict__ reward,
-               const float* __restrict__ lp_all, int ld_lp_rows, int T, int V, float entropy_reg, float inv_rows,
-               float* __restrict__ out) {
+               const float* __restrict__ lp_all, size_t ld_lp_rows, size_t ld_lp_s, int T, int V, float entropy_reg,
+               float inv_rows, float* __restrict__ out) {
   __shared__ float s_red[VT / 32];
   const int b = blockIdx.x / T, t = blockIdx.x % T;
   const bool m0 = seq[(size_t)b * T + t] > 0;
   const bool m = (t == 0) ? true : (seq[(size_t)b * T + t - 1] > 0);
   float ent = 0.f;
   if (m0 && entropy_reg != 0.f) {
-    const float* x = lp_all + (size_t)b * ld_lp_rows + (size_t)t * V;
+    const float* x = lp_all + (size_t)b * ld_lp_rows + (size_t)t * ld_lp_s;
     for (int v = threadIdx.x; v < V; v += VT) { const float l = x[v]; ent += l * expf(l); }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ent += __shfl_xor_sync(0xffffffffu, ent, o);
@@ -471,12 +471,12 @@ rl_loss_kernel(const float* __restrict__ slp, const int64_t* __restrict__ seq, c
   }
 }
 
-int rl_loss(const float* slp, const int64_t* seq, const float* reward, const float* lp_all, int ld_lp_rows, int rows,
-            int T, int V, float entropy_reg, float* out, cudaStream_t st) {
+int rl_loss(const float* slp, const int64_t* seq, const float* reward, const float* lp_all, size_t ld_lp_rows, size_t ld_lp_s,
+            int rows, int T, int V, float entropy_reg, float* out, cudaStream_t st) {
   ProfScope prof__(TAG_VOCAB, st);
   RFN_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
   if (rows * T == 0) return RFN_OK;
-  rl_loss_kernel<<<rows * T, VT, 0, st>>>(slp, seq, reward, lp_all, ld_lp_rows, T, V, entropy_reg, 1.f / (float)rows, out);
+  rl_loss_kernel<<<rows * T, VT, 0, st>>>(slp, seq, reward, lp_all, ld_lp_rows, ld_lp_s, T, V, entropy_reg, 1.f / (float)rows, out);
   RFN_LAUNCH_CHECK();
   return RFN_OK;
 }
@@ -544,14 +544,25 @@ extern "C" int rfn_log_softmax_f32(const float* logits, int ld_in, float* lp, in
 extern "C" int rfn_xe_loss_f32(const float* logprobs, const int64_t* target, const float* mask, int ld_t, int rows,
                                int T, int V, float eps, float* out, rfn_stream_t stream) {
   RFN_CHECK_ARG(logprobs && target && mask && out, "rfn_xe_loss_f32: null pointer");
-  return rfn::xe_loss(logprobs, target, mask, ld_t, rows, T, V, eps, out, (cudaStream_t)stream);
+  return rfn::xe_loss(logprobs, (size_t)T * V, (size_t)V, target, mask, ld_t, rows, T, V, eps, out, (cudaStream_t)stream);
+}
+extern "C" int rfn_xe_loss_strided_f32(const float* logprobs, size_t ld_b, size_t ld_s, const int64_t* target, const float* mask,
+                                       int ld_t, int rows, int T, int V, float eps, float* out, rfn_stream_t stream) {
+  RFN_CHECK_ARG(logprobs && target && mask && out, "rfn_xe_loss_strided_f32: null pointer");
+  return rfn::xe_loss(logprobs, ld_b, ld_s, target, mask, ld_t, rows, T, V, eps, out, (cudaStream_t)stream);
 }
 extern "C" int rfn_rl_loss_f32(const float* sample_logprobs, const int64_t* seq, const float* reward,
                                const float* logprobs_all, int ld_lp_rows, int rows, int T, int V, float entropy_reg,
                                float* out, rfn_stream_t stream) {
   RFN_CHECK_ARG(sample_logprobs && seq && reward && logprobs_all && out, "rfn_rl_loss_f32: null pointer");
-  return rfn::rl_loss(sample_logprobs, seq, reward, logprobs_all, ld_lp_rows, rows, T, V, entropy_reg, out,
+  return rfn::rl_loss(sample_logprobs, seq, reward, logprobs_all, (size_t)ld_lp_rows, (size_t)V, rows, T, V, entropy_reg, out,
                       (cudaStream_t)stream);
+}
+extern "C" int rfn_rl_loss_strided_f32(const float* sample_logprobs, const int64_t* seq, const float* reward,
+                                       const float* logprobs_all, size_t ld_b, size_t ld_s, int rows, int T, int V,
+                                       float entropy_reg, float* out, rfn_stream_t stream) {
+  RFN_CHECK_ARG(sample_logprobs && seq && reward && logprobs_all && out, "rfn_rl_loss_strided_f32: null pointer");
+  return rfn::rl_loss(sample_logprobs, seq, reward, logprobs_all, ld_b, ld_s, rows, T, V, entropy_reg, out, (cudaStream_t)stream);
 }
 
 extern "C" int rfn_multilabel_margin_f32(const float* pred, const int64_t* target, int rows, int K, float weight,

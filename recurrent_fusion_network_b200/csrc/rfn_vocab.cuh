@@ -104,10 +104,11 @@ int sample_select(const float* logits, int ld, int V, const float* rowmax, const
                   int rows, cudaStream_t st);
 int sample_finalize(const int32_t* any_unfinished, int L, int32_t* d_T, cudaStream_t st);
 int log_softmax_rows(const float* logits, int ld_in, float* lp, int ld_out, int rows, int V, cudaStream_t st);
-int xe_loss(const float* logprobs, const int64_t* target, const float* mask, int ld_t, int rows, int T, int V,
-            float eps, float* out, cudaStream_t st);
-int rl_loss(const float* slp, const int64_t* seq, const float* reward, const float* lp_all, int ld_lp_rows, int rows,
-            int T, int V, float entropy_reg, float* out, cudaStream_t st);
+// lp[b, t, :] at logprobs + b * ld_b + t * ld_s (contiguous (rows, T, V): ld_b = T * V, ld_s = V; time-major: ld_b = V, ld_s = rows * V)
+int xe_loss(const float* logprobs, size_t ld_b, size_t ld_s, const int64_t* target, const float* mask, int ld_t, int rows, int T,
+            int V, float eps, float* out, cudaStream_t st);
+int rl_loss(const float* slp, const int64_t* seq, const float* reward, const float* lp_all, size_t ld_lp_rows, size_t ld_lp_s,
+            int rows, int T, int V, float entropy_reg, float* out, cudaStream_t st);
 
 int multilabel_margin(const float* pred, const int64_t* target, int rows, int K, float weight, int accumulate,
                       float* out, cudaStream_t st);

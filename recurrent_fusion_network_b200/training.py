@@ -5,6 +5,7 @@ from __future__ import annotations
 import torch
 
 from . import autograd as AG
+from . import tape
 
 
 def thought_vectors(model, att, state_list):
@@ -47,9 +48,14 @@ def _stages(model, fc, att):
         # unique: the caller ships one feature row per image (ingest.FeatureBatch.fc / .att) and g label rows per image
         fcu = fc if unique else [f[::g].contiguous() for f in fc]
         attu = att if unique else [a[::g].contiguous() for a in att]
-        TVc, reason_pred, (h, c) = thought_vectors(model, attu, model.get_init_state(fcu))
+        if tape.usable(model):
+            TVc, reason_pred, (h, c) = tape.thought_vectors(model, fcu, attu)
+        else:
+            TVc, reason_pred, (h, c) = thought_vectors(model, attu, model.get_init_state(fcu))
         ex = lambda t: AG.ExpandRowsFn.apply(t, g)
         return ex(TVc), [ex(r) for r in reason_pred], (ex(h.squeeze(0)).unsqueeze(0), ex(c.squeeze(0)).unsqueeze(0))
+    if tape.usable(model):      # hand-scheduled multi-stream tape (tape.py); the per-op tape below is the general case
+        return tape.thought_vectors(model, fc, att)
     return thought_vectors(model, att, model.get_init_state(fc))
 
 
@@ -75,6 +81,15 @@ def forward_xe(model, fc_feats, att_feats, seq, col_any=None):
     outputs = []
     if col_any is None:
         col_any = (seq != 0).any(dim=0).cpu().tolist()
+    if model.ss_prob <= 0.0 and tape.usable(model):
+        # teacher forcing only: the whole decoder loop is one Function (T-batched weight gradients, hoisted invariants)
+        Tn = seq.size(1)
+        for i in range(1, seq.size(1)):
+            if not col_any[i]:                                          # :274-275
+                Tn = i
+                break
+        lp = tape.decode_teacher_forced(model, seq[:, :Tn], TVc, state)
+        return lp, [r.squeeze() for r in reason_pred]
     xts = None
     if model.ss_prob <= 0.0:
         # teacher forcing only: all input tokens are known, one embedding gather (and one dense dE in backward) for the
@@ -202,14 +217,19 @@ def rl_forward_loss(model, crit, fc_feats, att_feats, uniforms, reward_fn, top_t
         greedy, _ = _decode_tokens(model, TVd, hd, cd, None, 1.0)
         reward = reward_fn(seq, greedy)
         tokens = torch.cat([torch.zeros(rows, 1, dtype=torch.int64, device=seq.device), seq[:, :L - 1]], 1)
-    xts = AG.EmbedFn.apply(tokens.t().reshape(-1), model.embed.weight).view(L, rows, -1).unbind(0)
-    lps, slps = [], []
-    for i in range(L):
-        lp, state = _step(model, None, TVc, state, xt=xts[i])
-        lps.append(lp)
-        slps.append(AG.GatherColsFn.apply(lp, seq[:, i].contiguous()))
-    lp_all = torch.stack(lps, 1).contiguous()
-    slp = torch.stack(slps, 1)
+    if tape.usable(model):
+        lp_all = tape.decode_teacher_forced(model, tokens, TVc, state)            # (rows, L, V) view of a time-major table
+        lp_tm = lp_all.transpose(0, 1)                                            # (L, rows, V), contiguous again
+        slp = AG.GatherColsFn.apply(lp_tm.reshape(L * rows, -1), seq.t().reshape(-1)).view(L, rows).t()
+    else:
+        xts = AG.EmbedFn.apply(tokens.t().reshape(-1), model.embed.weight).view(L, rows, -1).unbind(0)
+        lps, slps = [], []
+        for i in range(L):
+            lp, state = _step(model, None, TVc, state, xt=xts[i])
+            lps.append(lp)
+            slps.append(AG.GatherColsFn.apply(lp, seq[:, i].contiguous()))
+        lp_all = torch.stack(lps, 1).contiguous()
+        slp = torch.stack(slps, 1)
     loss = rl_criterion(crit, slp, seq, reward, lp_all, entropy_reg, [r.squeeze() for r in reason_pred], top_true, reason_weight)
     return loss, seq, greedy, reward
 
