@@ -97,6 +97,12 @@ int rfn_engine_launch_counts(uint64_t* out, int n);
  * rows always use the SIMT kernel on the decode path. */
 int rfn_set_gemm_mode(int mode);
 int rfn_get_gemm_mode(void);
+/* 1: every GEMM of the following calls may take the split-K route (partial tiles summed with atomic adds: the summation
+ * order, hence the last bits of the result, vary from run to run).  Default 0: only the training operators ask for it
+ * (RFN_GEMM_SPLITK); training.rl_forward_loss turns it on around its two no-tape decodes of a few hundred rows, whose
+ * tokens are samples / a baseline, not outputs that must reproduce bit for bit. */
+int rfn_set_splitk(int on);
+int rfn_get_splitk(void);
 /* Tensor-engine GEMMs with >= 256 rows and columns: 0 = one CTA per 128 x 256 tile; 1 = 2-CTA clusters
  * (tcgen05 cta_group::2, 256 x 256 tiles, operands split across the pair), one tile per cluster;
  * 2 = persistent 2-CTA clusters looping over tiles with the epilogue overlapped (3xTF32 mode). */

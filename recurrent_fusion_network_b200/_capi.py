@@ -56,6 +56,8 @@ _SIGNATURES = {
     "rfn_engine_launch_counts": (_i, [C.POINTER(C.c_uint64), _i]),
     "rfn_set_gemm_mode": (_i, [_i]),
     "rfn_get_gemm_mode": (_i, []),
+    "rfn_set_splitk": (_i, [_i]),
+    "rfn_get_splitk": (_i, []),
     "rfn_set_tc_cluster": (_i, [_i]),
     "rfn_get_tc_cluster": (_i, []),
     "rfn_debug_set_timeline": (_i, [_vp, _i]),

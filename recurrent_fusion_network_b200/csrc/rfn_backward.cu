@@ -225,7 +225,7 @@ int colsum(const float* dY, int ld, int M, int N, float* db, int accumulate, cud
 // given dz: da[n] = dz.A[n,:] ; de = a * (da - sum_m a[m] da[m]) ; dwb += sum de ; dw[k] += sum_n de[n] t[n,k]
 //           du[n,k] = de[n] w[k] (1 - t^2) = dP[n,k] ; dg[k] = sum_n du[n,k] ; dA[n,:] += a[n] dz   (if requested)
 // one CTA per query row; dw / dwb are accumulated with atomics (one per CTA per element).
-constexpr int AB_THREADS = 256;
+constexpr int AB_THREADS = 512;
 __global__ void __launch_bounds__(AB_THREADS)
 attention_bwd_kernel(const float* __restrict__ A, const float* __restrict__ P, const float* __restrict__ g,
                      const float* __restrict__ w, const float* __restrict__ alpha, const float* __restrict__ dz, int lddz,

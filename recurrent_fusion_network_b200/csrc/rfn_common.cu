@@ -23,6 +23,8 @@ void count_engine(int engine) {
   if (engine >= 0 && engine < ENG_COUNT) g_engine_launches[engine].fetch_add(1, std::memory_order_relaxed);
 }
 int gemm_mode() { return g_gemm_mode.load(std::memory_order_relaxed); }
+static std::atomic<int> g_splitk_all{0};   // rfn_set_splitk: every GEMM may use the atomically summed split-K route
+bool splitk_all() { return g_splitk_all.load(std::memory_order_relaxed) != 0; }
 static std::atomic<int> g_pdl{0};   // measured: no gain at 625 or 5000 images (profiles/r2_pdl_625img.json), so off by default
 bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; }
 
@@ -103,6 +105,11 @@ int rfn_set_gemm_mode(int mode) {
   return RFN_OK;
 }
 int rfn_get_gemm_mode(void) { return rfn::gemm_mode(); }
+int rfn_set_splitk(int on) {
+  rfn::g_splitk_all.store(on ? 1 : 0);
+  return RFN_OK;
+}
+int rfn_get_splitk(void) { return rfn::splitk_all() ? 1 : 0; }
 int rfn_set_pdl(int on) {
   rfn::g_pdl.store(on ? 1 : 0);
   return RFN_OK;

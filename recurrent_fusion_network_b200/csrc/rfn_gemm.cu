@@ -30,8 +30,17 @@ int gemm(const GemmArgs& a, cudaStream_t st) {
   // (modes 4 / 5: the path code routes large GEMMs to the split-fp16 / bf16 engine with its workspace, rfn_path.cu; what
   // arrives here are the shapes that engine does not take: 3xTF32 / single-pass TF32 respectively)
   const int eng = (mode == 3 || mode == 4) ? 1 : (mode == 5 ? 2 : mode);
+  const bool splitk_ok = a.splitk_ok || splitk_all();
+  if (mode >= 1 && a.M >= 128 && splitk_ok && gemm_tc_supported(a)) {
+    // a few hundred rows (the 250 sampled captions of an RL iteration): the 128 x 128 output tiles alone cover a fraction of
+    // the SMs and each would walk the whole contraction; split it over CTAs when the caller accepts an atomic sum
+    long nkb = 0;
+    for (int s = 0; s < a.nsrc; ++s) nkb += (a.src[s].K + 31) / 32;
+    const long tiles = (long)((a.M + 127) / 128) * ((a.N + 127) / 128);
+    if (tiles * 2 <= 148 && nkb >= 8) return gemm_tc_splitk(a, false, tc_passes(mode), st);
+  }
   if (mode >= 1 && a.M >= 128 && gemm_tc_supported(a)) return gemm_engine(a, eng, st);
-  if (mode >= 1 && a.splitk_ok && gemm_tc_supported(a)) {   // training: few rows, the weights are streamed once
+  if (mode >= 1 && splitk_ok && gemm_tc_supported(a)) {   // training: few rows, the weights are streamed once
     long wk = 0;
     for (int s = 0; s < a.nsrc; ++s) wk += a.src[s].K;
     if (wk * a.N >= (a.M > 32 ? (1L << 17) : (1L << 20))) return gemm_tc_splitk(a, false, tc_passes(mode), st);

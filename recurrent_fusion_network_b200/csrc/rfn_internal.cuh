@@ -18,6 +18,7 @@ enum Engine {
 };
 void count_engine(int engine);
 int gemm_mode();
+bool splitk_all();
 // tensor-engine pass count of an engine mode: 1 -> 3 (3xTF32), 2 -> 1 (single-pass TF32), 3 -> 2 (TF32 hi.hi + two BF16 cross
 // terms in the persistent kernel; 3xTF32 wherever another kernel runs)
 // modes 4 (split fp16, rfn_h3.cuh) and 5 (single-pass bf16) have their own engine; GEMMs too small for it fall back to

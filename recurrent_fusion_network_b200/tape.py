@@ -121,13 +121,17 @@ def _bwd_x(dYs, Ws, dX, M, K, acc, st):
         done += len(grp)
 
 
-def _dw(dY, X, st, long_ok=True):
-    """dW[N,K] = dY[M,N]^T . X[M,K]; long contractions go to the tensor engine through K-major (transposed) copies."""
+def _dw(dY, X, st, long_ok=True, xt=None):
+    """dW[N,K] = dY[M,N]^T . X[M,K]; xt: X^T (K, ld) if the caller already holds it (shared by several gradients)."""
     M, N = dY.shape
     K = X.shape[1]
     dW = torch.empty(N, K, dtype=_f32, device=dY.device)
-    if long_ok and M >= 1024 and N >= 256 and K >= 256 and K % 4 == 0 and lib().rfn_get_gemm_mode() >= 1:
-        dYt, Xt = _transpose(dY, st), _transpose(X, st)
+    # tensor engine through K-major copies: long contractions, and short ones (an 80-row batch) when the output is large --
+    # the FFMA kernel needs 40 us for a 2048 x 4608 x 80 gate-weight gradient, transposes + tensor GEMM a third of that
+    big = (M >= 1024 and N >= 256 and K >= 256) or (M >= 32 and N >= 256 and K >= 256 and N * K >= (1 << 21))
+    if long_ok and big and K % 4 == 0 and lib().rfn_get_gemm_mode() >= 1:
+        dYt = _transpose(dY, st)
+        Xt = xt if xt is not None else _transpose(X, st)
         Kc = dYt.shape[1]
         ld = (C.c_int * 1)(Kc)
         ks = (C.c_int * 1)(Kc)
@@ -159,6 +163,27 @@ def _dw_pre(dY, Xt, K, st):
     check(lib().rfn_linear_f32(1, ptr_array([dYt]), ld, ptr_array([Xt]), ks, ptr_array([None]), ptr(dW), K, N, K, 2, st),
           "rfn_linear_f32")
     return dW
+
+
+def _split(x2d, st, bf16):
+    """fp32 rows -> the split engine's operand (power-of-two row scale + two fp16 pieces, or one bf16 piece; rfn_h3.cuh)."""
+    rows, K = x2d.shape
+    ks = (C.c_int * 1)(K)
+    nbytes = lib().rfn_split_bytes(rows, 1, ks, bf16)
+    out = torch.empty(int(nbytes), dtype=torch.uint8, device=x2d.device)
+    ld = (C.c_int * 1)(x2d.stride(0))
+    check(lib().rfn_split_rows_f32(1, ptr_array([x2d]), ld, ks, rows, bf16, ptr(out), out.numel(), st), "rfn_split_rows_f32")
+    _KEEP.append(out)
+    return out
+
+
+def _lin_split(xs, W, b, y, M, N, bf16, st):
+    """y = x W^T + b with x pre-split (`xs` from _split) and W split here: the stage-1 att_2_att_h projection, 89 % of the
+    step's FLOPs, on the split-fp16 tcgen05 engine (engine modes 4 / 5) instead of 3xTF32."""
+    K = W.shape[1]
+    ws = _split(W, st, bf16)
+    ks = (C.c_int * 1)(K)
+    check(lib().rfn_linear_split(bf16, 1, ptr(xs), ptr(ws), ks, ptr_array([b]), ptr(y), y.stride(0), M, N, 0, st), "rfn_linear_split")
 
 
 def _colsum(dY, st):
@@ -247,15 +272,23 @@ class Stage1Fn(Function):
         g = [bufs[i] for i in ig]
         G = [bufs[i] for i in iG]
         torch.cat(h0, 1, out=Hs[0])
+        mode = lib().rfn_get_gemm_mode()
+        bf16 = 1 if mode == 5 else 0
+        asplit = [None] * J
         for s in range(S0):
             for j in range(J):
                 e = pool.enc[j]
                 _after(e, main)
                 st = _sid(e)
+                if s == 0 and mode >= 4 and rows * N[j] >= 256 and A >= 256 and D[j] % 8 == 0:
+                    asplit[j] = _split(att[j].view(rows * N[j], D[j]), st, bf16)     # once for the S0 steps
                 U_w, U_b, Wh_w, Wh_b, v_w, v_b, H2h_w, H2h_b, z2h_w, z2h_b = P[s][j]
                 h_in = Hs[s][:, j * R:(j + 1) * R]
                 _lin([h_in], [Wh_w], [Wh_b], g[j][s], rows, A, True, st)
-                _lin([att[j].view(rows * N[j], D[j])], [U_w], [U_b], Pb[j][s], rows * N[j], A, False, st)
+                if asplit[j] is not None:
+                    _lin_split(asplit[j], U_w, U_b, Pb[j][s], rows * N[j], A, bf16, st)
+                else:
+                    _lin([att[j].view(rows * N[j], D[j])], [U_w], [U_b], Pb[j][s], rows * N[j], A, False, st)
                 _att_fwd(att[j], Pb[j][s], g[j][s], v_w, v_b, z[j][s], al[j][s], rows, N[j], D[j], A, st)
                 _lin([Hs[s], z[j][s]], [H2h_w, z2h_w], [H2h_b, z2h_b], G[j][s], rows, 4 * R, True, st)
                 c_prev = h0[j] if s == 0 else Cs[j][s - 1]
@@ -265,6 +298,7 @@ class Stage1Fn(Function):
         hbar = E(rows, R, dtype=_f32, device=dev)
         cbar = E(rows, R, dtype=_f32, device=dev)
         sm = _sid(main)
+        _KEEP.clear()
         check(lib().rfn_mean_tensors_f32(ptr(Hs[S0]), R, J, ptr(hbar), R, rows, R, J * R, sm), "rfn_mean_tensors_f32")
         check(lib().rfn_mean_tensors_f32(ptr(Cs[0][S0 - 1]), S0 * rows * R, J, ptr(cbar), R, rows, R, R, sm), "rfn_mean_tensors_f32")
         ctx.J, ctx.S0 = J, S0
@@ -327,7 +361,9 @@ class Stage1Fn(Function):
                 _after(pool.wg[j], main)
                 At[j] = _transpose(att[j].view(rows * N[j], D[j]), _sid(pool.wg[j]))
         grads = [[None] * J for _ in range(S0)]
+        big_dw = use_tc and rows >= 32 and 4 * R * J * R >= (1 << 21) and R % 4 == 0
         for s in range(S0 - 1, -1, -1):
+            Ht = _transpose(Hs[s], sm) if big_dw else None      # H^T of this step, shared by the J encoders' dH2h
             for j in range(J):
                 e, w = pool.enc[j], pool.wg[j]
                 _after(e, main)
@@ -345,7 +381,7 @@ class Stage1Fn(Function):
                 _after(w, e)
                 h_in = Hs[s][:, j * R:(j + 1) * R]
                 # weight gradients of the gate GEMM, off the dependent chain
-                dH2h_w = _dw(dG[j][s], Hs[s], sw)
+                dH2h_w = _dw(dG[j][s], Hs[s], sw, xt=Ht)
                 dz2h_w = _dw(dG[j][s], z[j][s], sw)
                 dH2h_b = _colsum(dG[j][s], sw)
                 dz2h_b = _colsum(dG[j][s], sw)
@@ -506,7 +542,7 @@ class Stage2Fn(Function):
                 gs[2 + 2 * j] = _dw(dG[s], z[j][s], sw)
                 gs[3 + 2 * j] = _colsum(dG[s], sw)
                 o = 2 + 2 * J + 6 * j
-                gs[o] = _dw(dP[j][s], TV[j].view(rows * S0, R), sw, long_ok=False)
+                gs[o] = _dw(dP[j][s], TV[j].view(rows * S0, R), sw)
                 check(lib().rfn_colsum_f32(ptr(dP[j][s]), A, rows * S0, A, ptr(dUb[j][s]), 1, sw), "rfn_colsum_f32")
                 gs[o + 1] = dUb[j][s]
                 gs[o + 2] = _dw(dg[j][s], hin, sw)
@@ -638,7 +674,7 @@ class DecoderFn(Function):
         dPs = E(rows * S1, A, dtype=_f32, device=dev)      # sum over the steps of dP_t (P is loop invariant)
         check(lib().rfn_colsum_f32(ptr(dP), rows * S1 * A, T, rows * S1 * A, ptr(dPs), 0, sw), "rfn_colsum_f32")
         _bwd_x([dPs], [U_w], dTVc.view(rows * S1, R), rows * S1, R, True, sw)
-        dU_w = _dw(dPs, TVc.view(rows * S1, R), sw, long_ok=False)
+        dU_w = _dw(dPs, TVc.view(rows * S1, R), sw)
         dU_b = _colsum(dPs, sw)
         Hprev = Hx[:T].view(T * rows, R)
         dWi = _dw(dG2, X, sw)

@@ -213,8 +213,14 @@ def rl_forward_loss(model, crit, fc_feats, att_feats, uniforms, reward_fn, top_t
     with torch.no_grad():
         TVd = TVc.detach().contiguous()
         hd, cd = state[0].detach().squeeze(0).contiguous(), state[1].detach().squeeze(0).contiguous()
-        seq, _ = _decode_tokens(model, TVd, hd, cd, uniforms.to(TVd.device).float().contiguous(), temperature)
-        greedy, _ = _decode_tokens(model, TVd, hd, cd, None, 1.0)
+        from ._capi import lib
+        prev = lib().rfn_get_splitk()
+        lib().rfn_set_splitk(1)      # a few hundred rows: split-K GEMMs fill the GPU (the tokens are samples and a baseline)
+        try:
+            seq, _ = _decode_tokens(model, TVd, hd, cd, uniforms.to(TVd.device).float().contiguous(), temperature)
+            greedy, _ = _decode_tokens(model, TVd, hd, cd, None, 1.0)
+        finally:
+            lib().rfn_set_splitk(prev)
         reward = reward_fn(seq, greedy)
         tokens = torch.cat([torch.zeros(rows, 1, dtype=torch.int64, device=seq.device), seq[:, :L - 1]], 1)
     if tape.usable(model):
