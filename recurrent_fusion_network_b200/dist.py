@@ -145,18 +145,49 @@ class OverlappedGradSync:
         self.side = torch.cuda.Stream()
         self.pending, self.pending_bytes, self.handles = [], 0, []
         self.buckets_launched = 0
+        self._early_done = set()
 
     def install(self):
         self.remove()
         for p in self.params:
             self.handles.append(p.register_post_accumulate_grad_hook(self._hook))
+        from . import tape
+        self._early_done = set()
+        tape.GRAD_SINK = self
 
     def remove(self):
         for h in self.handles:
             h.remove()
         self.handles = []
+        from . import tape
+        if tape.GRAD_SINK is self:
+            tape.GRAD_SINK = None
+
+    # tape.GRAD_SINK protocol: the hand-scheduled stage-1 backward (tape.Stage1Fn) hands over each fusion step's weight
+    # gradients as soon as they are issued, long before autograd sees them (it returns all 400 tensors at the very end)
+    def early(self, pairs, streams):
+        from torch.distributed.distributed_c10d import _coalescing_manager
+        grads = [g for _, g in pairs]
+        if not grads:
+            return
+        for st in streams:
+            self.side.wait_stream(st)
+        with torch.cuda.stream(self.side):
+            for i in range(0, len(grads), 256):
+                with _coalescing_manager(group=self.group, device=grads[0].device):
+                    for g in grads[i:i + 256]:
+                        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
+        for p, _ in pairs:
+            self._early_done.add(p.data_ptr())
+        self.buckets_launched += 1
+
+    def join(self):
+        torch.cuda.current_stream().wait_stream(self.side)
 
     def _hook(self, p):
+        if p.data_ptr() in self._early_done:      # reduced in place by early(); p.grad holds (or is a copy of) the sum
+            self._early_done.discard(p.data_ptr())
+            return
         self.pending.append(p.grad)
         self.pending_bytes += p.grad.numel() * p.grad.element_size()
         if self.pending_bytes >= self.bucket_bytes:

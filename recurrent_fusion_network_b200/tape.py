@@ -56,6 +56,23 @@ class _Streams:
 _KEEP = []
 
 
+#: data-parallel hook (dist.OverlappedGradSync.install sets it): an object with early(pairs, streams) and join().  Stage 1 owns
+#: 95 % of the parameters (distinct weights per fusion step) and its backward is the LAST thing a step computes: handing each
+#: fusion step's finished weight gradients to the all-reduce right away is what lets the collective overlap the remaining steps.
+GRAD_SINK = None
+
+#: phase markers for profiles/experiments/r2_phase_timeline.py: when a list, mark(name) records a timing event on the current
+#: stream (external events are legal inside a CUDA-graph capture and are re-recorded by every replay)
+MARKS = None
+
+
+def mark(name):
+    if MARKS is not None:
+        ev = torch.cuda.Event(enable_timing=True, external=True)
+        ev.record()
+        MARKS.append((name, ev))
+
+
 def _after(dst, src):
     """dst waits for everything issued to src so far."""
     ev = torch.cuda.Event()
@@ -272,6 +289,7 @@ class Stage1Fn(Function):
         g = [bufs[i] for i in ig]
         G = [bufs[i] for i in iG]
         torch.cat(h0, 1, out=Hs[0])
+        mark("s1_fwd_begin")
         mode = lib().rfn_get_gemm_mode()
         bf16 = 1 if mode == 5 else 0
         asplit = [None] * J
@@ -299,6 +317,7 @@ class Stage1Fn(Function):
         cbar = E(rows, R, dtype=_f32, device=dev)
         sm = _sid(main)
         _KEEP.clear()
+        mark("s1_fwd_end")
         check(lib().rfn_mean_tensors_f32(ptr(Hs[S0]), R, J, ptr(hbar), R, rows, R, J * R, sm), "rfn_mean_tensors_f32")
         check(lib().rfn_mean_tensors_f32(ptr(Cs[0][S0 - 1]), S0 * rows * R, J, ptr(cbar), R, rows, R, R, sm), "rfn_mean_tensors_f32")
         ctx.J, ctx.S0 = J, S0
@@ -360,6 +379,7 @@ class Stage1Fn(Function):
             if use_tc and rows * N[j] >= 1024 and A >= 256 and D[j] >= 256 and D[j] % 4 == 0:
                 _after(pool.wg[j], main)
                 At[j] = _transpose(att[j].view(rows * N[j], D[j]), _sid(pool.wg[j]))
+        mark("s1_bwd_begin")
         grads = [[None] * J for _ in range(S0)]
         big_dw = use_tc and rows >= 32 and 4 * R * J * R >= (1 << 21) and R % 4 == 0
         for s in range(S0 - 1, -1, -1):
@@ -403,14 +423,20 @@ class Stage1Fn(Function):
                                dz2h_b)
             for j in range(J):
                 _after(main, pool.enc[j])
+            if GRAD_SINK is not None:      # this step's 10 J weight gradients are final once the wgrad streams get there
+                GRAD_SINK.early([(P[s][j][k], grads[s][j][k]) for j in range(J) for k in range(10)], pool.wg + pool.enc)
         # h0_j is both the initial hidden and the initial cell state (misc/RecurrentFusionModel.py:333-343)
         dh0 = []
         for j in range(J):
             out = E(rows, R, dtype=_f32, device=dev)
             _sum([dhq[j][0], dC[j][0]] + [dHp[k][0][:, j * R:(j + 1) * R] for k in range(J)], 1.0, out, rows, R, sm)
             dh0.append(out)
+        mark("s1_bwd_chain_end")
         for j in range(J):
             _after(main, pool.wg[j])
+        if GRAD_SINK is not None:
+            GRAD_SINK.join()                # the early all-reduces wrote the gradients in place: order them before their consumers
+        mark("s1_bwd_wgrad_end")
         _KEEP.clear()
         flat = []
         for s in range(S0):
@@ -451,6 +477,7 @@ class Stage2Fn(Function):
         bufs = ar.build()
         g = [bufs[i] for i in ig]
         G = bufs[iG]
+        mark("s2_fwd_begin")
         for s in range(S1):
             p = prm[s * per:(s + 1) * per]
             hin = hbar if s == 0 else TVc[:, s - 1, :]
@@ -469,6 +496,7 @@ class Stage2Fn(Function):
             last = s == S1 - 1
             c_prev = cbar if s == 0 else Cs[s - 1]
             _cell(G[s], c_prev, None, 1.0, hfin if last else None, cfin if last else Cs[s], TVc[:, s, :], None, rows, R, sm)
+        mark("s2_fwd_end")
         ctx.J, ctx.S1 = J, S1
         ctx.save_for_backward(*TV, hbar, cbar, *prm, TVc, Cs, *Pb, *al, *z, *g, G)
         return TVc, hfin, cfin
@@ -513,6 +541,7 @@ class Stage2Fn(Function):
         dhq = [bufs[i] for i in idhq]
         dwv = [bufs[i] for i in idw]
         dUb = [bufs[i] for i in idUb]
+        mark("s2_bwd_begin")
         grads = [None] * S1
         for s in range(S1 - 1, -1, -1):
             p = prm[s * per:(s + 1) * per]
@@ -559,8 +588,10 @@ class Stage2Fn(Function):
         dhbar = E(rows, R, dtype=_f32, device=dev)
         _sum([dhx[0]] + [dhq[j][0] for j in range(J)], 1.0, dhbar, rows, R, sm)
         dcbar = dC[0]
+        mark("s2_bwd_chain_end")
         for j in range(J):
             _after(main, pool.wg[j])
+        mark("s2_bwd_wgrad_end")
         _KEEP.clear()
         flat = []
         for s in range(S1):
@@ -596,6 +627,7 @@ class DecoderFn(Function):
         G = E(T, rows, 4 * R, dtype=_f32, device=dev)
         g = torch.zeros(T, rows, A, dtype=_f32, device=dev)
         Hx[0].copy_(h0)
+        mark("dec_fwd_begin")
         # hoisted: the x_t . i2h^T + b term of every step (one (T*rows)-row GEMM, side stream), att_2_att_h(TV_comb)
         _after(side, main)
         _lin([X], [Wi], [bi], G.view(T * rows, 4 * R), T * rows, 4 * R, False, _sid(side))
@@ -607,10 +639,12 @@ class DecoderFn(Function):
             _lin([Hx[t], Z[t]], [Whh, Wz], [bh, bz], G[t], rows, 4 * R, True, sm)
             _cell(G[t], c0 if t == 0 else Cx[t - 1], mask[t] if mask is not None else None, scale, Hx[t + 1], Cx[t], None, None,
                   rows, R, sm)
+        mark("dec_fwd_loop_end")
         logits = E(T * rows, V, dtype=_f32, device=dev)
         _lin([Hx[1:].view(T * rows, R)], [Wl], [bl], logits, T * rows, V, False, sm)
         lp = E(T, rows, V, dtype=_f32, device=dev)
         check(lib().rfn_log_softmax_f32(ptr(logits), V, ptr(lp), V, T * rows, V, sm), "rfn_log_softmax_f32")
+        mark("dec_fwd_end")
         ctx.T, ctx.scale, ctx.has_mask = T, scale, mask is not None
         ctx.save_for_backward(X, TVc, c0, *prm, Pdec, Hx, Cx, Z, al, G, g, lp, *([mask] if mask is not None else []))
         return lp
@@ -636,6 +670,7 @@ class DecoderFn(Function):
         sw = _sid(w)
         E = torch.empty
         dlp = _cont(dlp)
+        mark("dec_bwd_begin")
         dlogits = E(T * rows, V, dtype=_f32, device=dev)
         check(lib().rfn_log_softmax_bwd_f32(ptr(lp), V, ptr(dlp), V, ptr(dlogits), V, T * rows, V, sm), "rfn_log_softmax_bwd_f32")
         ar = _Arena(dev)
@@ -654,6 +689,7 @@ class DecoderFn(Function):
         dC = E(2, rows, R, dtype=_f32, device=dev)
         dP = E(T, rows * S1, A, dtype=_f32, device=dev)
         dg = E(T, rows, A, dtype=_f32, device=dev)
+        mark("dec_bwd_loop_begin")
         for t in range(T - 1, -1, -1):
             srcs = [dHall[t]]
             if t < T - 1:
@@ -666,6 +702,7 @@ class DecoderFn(Function):
         dh0 = E(rows, R, dtype=_f32, device=dev)
         _sum([dhz[0][:, :R], dhq[0]], 1.0, dh0, rows, R, sm)
         dc0 = dC[0]
+        mark("dec_bwd_loop_end")
         # everything below is off the dependent chain: T-batched weight gradients, the embedding-side dX, the hoisted projection
         _after(w, main)
         dG2 = dG.view(T * rows, 4 * R)
@@ -685,6 +722,7 @@ class DecoderFn(Function):
         dWh_w = _dw(dg2, Hprev, sw)
         dWh_b = _colsum(dg2, sw)
         _after(main, w)
+        mark("dec_bwd_end")
         _KEEP.clear()
         return (None, None, dX, dTVc, dh0, dc0, None, dWi, dbi, dWhh, dbh, dWz, dbz, dU_w, dU_b, dWh_w, dWh_b,
                 dwv[:A].view(1, A), dwv[A:], dWl, dbl)

@@ -209,7 +209,9 @@ def rl_forward_loss(model, crit, fc_feats, att_feats, uniforms, reward_fn, top_t
     if getattr(model, "unique_feature_rows", False) and int(getattr(model, "dedup_rows", 1) or 1) > 1:
         rows *= int(model.dedup_rows)
     L = model.seq_length
+    tape.mark("rl_begin")
     TVc, reason_pred, state = _stages(model, fc, att)
+    tape.mark("rl_stages_end")
     with torch.no_grad():
         TVd = TVc.detach().contiguous()
         hd, cd = state[0].detach().squeeze(0).contiguous(), state[1].detach().squeeze(0).contiguous()
@@ -221,7 +223,9 @@ def rl_forward_loss(model, crit, fc_feats, att_feats, uniforms, reward_fn, top_t
             greedy, _ = _decode_tokens(model, TVd, hd, cd, None, 1.0)
         finally:
             lib().rfn_set_splitk(prev)
+        tape.mark("rl_decodes_end")
         reward = reward_fn(seq, greedy)
+        tape.mark("rl_reward_end")
         tokens = torch.cat([torch.zeros(rows, 1, dtype=torch.int64, device=seq.device), seq[:, :L - 1]], 1)
     if tape.usable(model):
         lp_all = tape.decode_teacher_forced(model, tokens, TVc, state)            # (rows, L, V) view of a time-major table
@@ -237,6 +241,7 @@ def rl_forward_loss(model, crit, fc_feats, att_feats, uniforms, reward_fn, top_t
         lp_all = torch.stack(lps, 1).contiguous()
         slp = torch.stack(slps, 1)
     loss = rl_criterion(crit, slp, seq, reward, lp_all, entropy_reg, [r.squeeze() for r in reason_pred], top_true, reason_weight)
+    tape.mark("rl_loss_end")
     return loss, seq, greedy, reward
 
 
@@ -278,6 +283,8 @@ class GraphedRLStep:
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             self.g_fb = torch.cuda.CUDAGraph()
+            if tape.MARKS is not None:
+                tape.MARKS.clear()          # keep the markers of the captured pass only
             with torch.cuda.graph(self.g_fb):
                 if grad_sync is not None:
                     grad_sync.install()
@@ -289,6 +296,7 @@ class GraphedRLStep:
             self.g_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.g_opt, pool=self.g_fb.pool()):
                 optimizer.step()
+                tape.mark("opt_end")
         finally:
             model._wsobj = saved_ws
 
@@ -298,9 +306,11 @@ class GraphedRLStep:
 
     def _fwd_bwd(self):
         self.opt.zero_grad(set_to_none=True)
+        tape.mark("step_begin")
         loss, seq, greedy, reward = rl_forward_loss(self.model, self.crit, self.fc, self.att, self.uniforms, self._reward, self.top,
                                                     self.reason_weight, self.entropy_reg, self.temperature)
         loss.backward()
+        tape.mark("bwd_end")
         return loss.detach(), seq, greedy, reward
 
     def __call__(self, fc=None, att=None, uniforms=None, top_true=None, gts=None):
@@ -358,6 +368,8 @@ class GraphedXEStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.g_fb = torch.cuda.CUDAGraph()
+        if tape.MARKS is not None:
+            tape.MARKS.clear()              # keep the markers of the captured pass only
         # grad_sync (dist.OverlappedGradSync): the data-parallel all-reduce is captured INSIDE the forward+backward graph,
         # bucket by bucket on a side stream while the backward of the earlier layers still runs (then `between` is unused)
         with torch.cuda.graph(self.g_fb):
@@ -371,12 +383,16 @@ class GraphedXEStep:
         self.g_opt = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.g_opt, pool=self.g_fb.pool()):
             optimizer.step()
+            tape.mark("opt_end")
 
     def _fwd_bwd(self):
         self.opt.zero_grad(set_to_none=True)
+        tape.mark("step_begin")
         lp, rp = forward_xe(self.model, self.fc, self.att, self.labels, col_any=self.col_any)
         loss = self.crit(lp, self.labels[:, 1:], self.masks[:, 1:], rp, self.top, self.reason_weight)
+        tape.mark("loss_end")
         loss.backward()
+        tape.mark("bwd_end")
         return loss.detach()
 
     def __call__(self, fc=None, att=None, labels=None, masks=None, top_true=None):

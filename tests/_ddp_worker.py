@@ -33,6 +33,29 @@ D.average_gradients(m.parameters())   # a generator on purpose (it us
 loss_sum = loss.detach().clone()
 dist.all_reduce(loss_sum)
 torch.cuda.synchronize()
+# the same step with the all-reduce overlapped inside the backward pass (dist.OverlappedGradSync: post-accumulate hooks plus
+# the early hand-over of each fusion step's weight gradients from tape.Stage1Fn): SUM of the rank gradients = world x the mean
+avg = {k: p.grad.clone() for k, p in m.named_parameters()}
+m.zero_grad(set_to_none=True)
+params = list(m.parameters())
+gs = D.OverlappedGradSync(params, bucket_bytes=8 << 20)
+gs.install()
+lp, rp = m([f[sl].cuda() for f in fc], [a[sl].cuda() for a in att], labels[sl].cuda())
+loss2 = crit(lp, labels[sl, 1:].cuda(), masks[sl, 1:].cuda(), rp, top[sl].cuda(), 10.0)
+loss2.backward()
+gs.finish()
+gs.remove()
+torch.cuda.synchronize()
+worst = 0.0
+for k, p in m.named_parameters():
+    scale = float(avg[k].abs().max()) + 1e-6
+    err = float((p.grad / world - avg[k]).abs().max())
+    worst = max(worst, err / scale)
+    assert err / scale <= 2e-5 or err <= 1e-6, f"overlapped sync, {k}: rel err {err / scale:.3g}"
+assert gs.buckets_launched >= 8, gs.buckets_launched
+print(f"OVERLAPPED_SYNC_OK rank {rank} buckets {gs.buckets_launched} worst rel err {worst:.2e}")
+for k, p in m.named_parameters():
+    p.grad = avg[k]
 if rank == 0:
     torch.save({"loss_mean": float(loss_sum) / world, "grads": {k: p.grad.cpu() for k, p in m.named_parameters()}}, sys.argv[1])
 dist.barrier()
