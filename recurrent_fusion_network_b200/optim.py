@@ -24,6 +24,9 @@ class FusedAdam(torch.optim.Optimizer):
                         grad_scale=grad_scale)
         super().__init__(params, defaults)
         self._hyper_t = {}     # group index -> (device {step, lr}, device {1, 0}); kept out of param_groups / state_dict
+        self._begun = False    # begin_step() already advanced the update count of the step in progress
+        self._done = set()     # id(p) of the parameters apply_to() has already updated in the step in progress
+        self._group_of = None
 
     def _hyper(self, gi, group):
         if gi not in self._hyper_t:
@@ -68,39 +71,90 @@ class FusedAdam(torch.optim.Optimizer):
                 self._hyper(gi, group)[0][1] = float(group["lr"])
 
     @torch.no_grad()
+    def begin_step(self):
+        """Advances the update count (bias correction) of the step that starts now.  step() does this itself; a caller that
+        applies part of the update early -- apply_to(), from inside the backward pass -- calls it first."""
+        if self._begun:
+            return
+        for gi, group in enumerate(self.param_groups):
+            for p in group["params"]:
+                st = self.state[p]
+                if p.requires_grad and not st:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            if group.get("capturable"):
+                hyper, one = self._hyper(gi, group)   # created from the update count BEFORE this step
+                hyper.add_(one)                        # step += 1 on the device (captured with the graph)
+            for p in group["params"]:
+                if self.state.get(p):
+                    self.state[p]["step"] += 1         # host mirror; not advanced by graph replays
+        self._begun = True
+
+    def _launch(self, gi, group, ps, grads):
+        for p, g in zip(ps, grads):
+            if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and g.is_contiguous() and g.dtype == torch.float32):
+                raise RuntimeError("FusedAdam needs contiguous fp32 CUDA parameters and gradients")
+        hyper = self._hyper(gi, group)[0] if group.get("capturable") else None
+        step = self.state[ps[0]]["step"]
+        n = len(ps)
+        numel = (C.c_int64 * n)(*[p.numel() for p in ps])
+        b1, b2 = group["betas"]
+        check(lib().rfn_adam_step_f32(n, ptr_array(ps), ptr_array(grads),
+                                      ptr_array([self.state[p]["exp_avg"] for p in ps]),
+                                      ptr_array([self.state[p]["exp_avg_sq"] for p in ps]), numel, float(group["lr"]),
+                                      float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
+                                      float(group.get("grad_clip", 0.0)), float(group.get("grad_scale", 1.0)), int(step),
+                                      ptr(hyper), stream()),
+              "rfn_adam_step_f32")
+
+    @torch.no_grad()
+    def apply_to(self, pairs):
+        """The update of some parameters from explicitly given, final gradients, on the CURRENT stream, before step(): the
+        hand-scheduled stage-1 backward (tape.Stage1Fn) finishes the weight gradients of a fusion step long before the
+        backward pass ends, and those 95 % of the parameters are touched by nothing after it, so their optimizer pass
+        overlaps the rest of the backward pass.  begin_step() must have been called; step() then skips them."""
+        if not self._begun:
+            raise RuntimeError("FusedAdam.apply_to: call begin_step() first")
+        if self._group_of is None:
+            self._group_of = {id(p): gi for gi, group in enumerate(self.param_groups) for p in group["params"]}
+        by_group = {}
+        for p, g in pairs:
+            gi = self._group_of.get(id(p))
+            if gi is None:
+                # the tape hands over the tensors autograd saved: the same storage as the registered Parameter
+                gi = self._by_ptr().get(p.data_ptr())
+                if gi is None:
+                    continue
+                p = self._ptr_param[p.data_ptr()]
+            by_group.setdefault(gi, []).append((p, g))
+        for gi, items in by_group.items():
+            self._launch(gi, self.param_groups[gi], [p for p, _ in items], [g for _, g in items])
+            for p, _ in items:
+                self._done.add(id(p))
+
+    def _by_ptr(self):
+        if getattr(self, "_ptr_group", None) is None:
+            self._ptr_group, self._ptr_param = {}, {}
+            for gi, group in enumerate(self.param_groups):
+                for p in group["params"]:
+                    self._ptr_group[p.data_ptr()] = gi
+                    self._ptr_param[p.data_ptr()] = p
+        return self._ptr_group
+
+    @torch.no_grad()
     def step(self, closure=None):
         loss = None
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        self.begin_step()
         for gi, group in enumerate(self.param_groups):
-            ps = [p for p in group["params"] if p.grad is not None]
+            ps = [p for p in group["params"] if p.grad is not None and id(p) not in self._done]
             if not ps:
                 continue
-            for p in ps:
-                st = self.state[p]
-                if not st:
-                    st["step"] = 0
-                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.grad.is_contiguous()):
-                    raise RuntimeError("FusedAdam needs contiguous fp32 CUDA parameters and gradients")
-            hyper = None
-            if group.get("capturable"):
-                hyper, one = self._hyper(gi, group)   # created from the update count BEFORE this step
-                hyper.add_(one)                        # step += 1 on the device (captured with the graph)
-            for p in ps:
-                self.state[p]["step"] += 1             # host mirror; not advanced by graph replays
-            step = self.state[ps[0]]["step"]
-            n = len(ps)
-            numel = (C.c_int64 * n)(*[p.numel() for p in ps])
-            b1, b2 = group["betas"]
-            check(lib().rfn_adam_step_f32(n, ptr_array(ps), ptr_array([p.grad for p in ps]),
-                                          ptr_array([self.state[p]["exp_avg"] for p in ps]),
-                                          ptr_array([self.state[p]["exp_avg_sq"] for p in ps]), numel, float(group["lr"]),
-                                          float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
-                                          float(group.get("grad_clip", 0.0)), float(group.get("grad_scale", 1.0)), int(step),
-                                          ptr(hyper), stream()),
-                  "rfn_adam_step_f32")
+            self._launch(gi, group, ps, [p.grad for p in ps])
+        self._begun = False
+        self._done = set()
         _capi.WEIGHTS_EPOCH[0] += 1   # the kernel wrote the parameters through raw pointers: invalidate derived weight caches
         return loss

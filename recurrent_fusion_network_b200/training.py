@@ -245,6 +245,48 @@ def rl_forward_loss(model, crit, fc_feats, att_feats, uniforms, reward_fn, top_t
     return loss, seq, greedy, reward
 
 
+class EarlyStep:
+    """tape.GRAD_SINK for the graphed training steps: as soon as tape.Stage1Fn's backward has issued the weight gradients of a
+    fusion step it (1) all-reduces them in place (data parallel: grad_sync = dist.OverlappedGradSync, on its NCCL side stream)
+    and (2) applies the clamp + Adam update to those parameters on the same side stream (FusedAdam.apply_to), while the
+    backward pass of the earlier fusion steps is still running.  Stage 1 holds 95 % of the parameters (distinct weights per
+    step) and is the last thing a backward pass computes; nothing reads a step's weights after its backward, so the update
+    cannot race with the rest of the pass.  What is left for optimizer.step() after the backward pass is the 5 % of the
+    parameters the decoder, stage 2 and the heads own."""
+
+    def __init__(self, optimizer, grad_sync=None):
+        self.opt, self.sync = optimizer, grad_sync
+        self.side = grad_sync.side if grad_sync is not None else torch.cuda.Stream()
+
+    def install(self):
+        if self.sync is not None:
+            self.sync.install()
+        tape.GRAD_SINK = self
+
+    def remove(self):
+        if self.sync is not None:
+            self.sync.remove()
+        if tape.GRAD_SINK is self:
+            tape.GRAD_SINK = None
+
+    def early(self, pairs, streams):
+        if self.sync is not None:
+            self.sync.early(pairs, streams)          # all-reduce (SUM) in place on self.side, ordered after `streams`
+        else:
+            for st in streams:
+                self.side.wait_stream(st)
+        with torch.cuda.stream(self.side):
+            self.opt.apply_to(pairs)
+
+    def join(self):
+        torch.cuda.current_stream().wait_stream(self.side)
+
+    def finish(self):
+        if self.sync is not None:
+            self.sync.finish()
+        self.join()
+
+
 class GraphedRLStep:
     """One self-critical RL iteration (train_rl.py:150-191: sample with grad, greedy baseline, CIDEr-D reward, criterion,
     backward, clip_gradient, Adam) replayed from CUDA graphs: rl_forward_loss + backward in one graph (with the bucketed
@@ -253,7 +295,7 @@ class GraphedRLStep:
     shape on the host -- are copied into static buffers; nothing is read back."""
 
     def __init__(self, model, crit, optimizer, fc, att, uniforms, top_true, gts, table, reward_opt, seq_per_img, reason_weight,
-                 entropy_reg=0.0, temperature=1.0, max_refs=5, max_ref_len=None, warmup=2, grad_sync=None):
+                 entropy_reg=0.0, temperature=1.0, max_refs=5, max_ref_len=None, warmup=2, grad_sync=None, early_optimizer=False):
         from . import reward as RW
         if not all(g.get("capturable") for g in optimizer.param_groups):
             raise RuntimeError("GraphedRLStep needs FusedAdam(capturable=True)")
@@ -285,14 +327,17 @@ class GraphedRLStep:
             self.g_fb = torch.cuda.CUDAGraph()
             if tape.MARKS is not None:
                 tape.MARKS.clear()          # keep the markers of the captured pass only
+            sink = EarlyStep(optimizer, grad_sync) if (early_optimizer and tape.usable(model)) else grad_sync
             with torch.cuda.graph(self.g_fb):
-                if grad_sync is not None:
-                    grad_sync.install()
+                if isinstance(sink, EarlyStep):
+                    optimizer.begin_step()          # the update count of this step, before its first early optimizer pass
+                if sink is not None:
+                    sink.install()
                 self.loss, self.seq, self.greedy, self.reward = self._fwd_bwd()
-                if grad_sync is not None:
-                    grad_sync.finish()
-            if grad_sync is not None:
-                grad_sync.remove()
+                if sink is not None:
+                    sink.finish()
+            if sink is not None:
+                sink.remove()
             self.g_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.g_opt, pool=self.g_fb.pool()):
                 optimizer.step()
@@ -347,7 +392,7 @@ class GraphedXEStep:
     reads a mask back to the host) and a FusedAdam(capturable=True)."""
 
     def __init__(self, model, crit, optimizer, fc, att, labels, masks, top_true, reason_weight, warmup=3, between=None,
-                 grad_sync=None):
+                 grad_sync=None, early_optimizer=False):
         if model.ss_prob > 0.0:
             raise RuntimeError("GraphedXEStep: scheduled sampling is not capturable (ss_prob must be 0)")
         if not all(g.get("capturable") for g in optimizer.param_groups):
@@ -372,14 +417,22 @@ class GraphedXEStep:
             tape.MARKS.clear()              # keep the markers of the captured pass only
         # grad_sync (dist.OverlappedGradSync): the data-parallel all-reduce is captured INSIDE the forward+backward graph,
         # bucket by bucket on a side stream while the backward of the earlier layers still runs (then `between` is unused)
+        # early_optimizer: the stage-1 parameters (95 % of the model) are updated from inside the backward pass (EarlyStep); not
+        # with `between` (an all-reduce between the two graphs must see every gradient before any update).  Measured on one
+        # B200 (profiles/r2_phase_timeline_xe.log): the optimizer graph shrinks from 2.75 to 0.57 ms but stage-1 backward grows
+        # by as much -- that pass is bound by GPU throughput, not by its dependent chain -- so it is off by default.
+        early = early_optimizer and between is None and tape.usable(model)
+        sink = EarlyStep(optimizer, grad_sync) if early else grad_sync
         with torch.cuda.graph(self.g_fb):
-            if grad_sync is not None:
-                grad_sync.install()
+            if early:
+                optimizer.begin_step()              # the update count of this step, before its first early optimizer pass
+            if sink is not None:
+                sink.install()
             self.loss = self._fwd_bwd()
-            if grad_sync is not None:
-                grad_sync.finish()
-        if grad_sync is not None:
-            grad_sync.remove()
+            if sink is not None:
+                sink.finish()
+        if sink is not None:
+            sink.remove()
         self.g_opt = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.g_opt, pool=self.g_fb.pool()):
             optimizer.step()

@@ -198,7 +198,8 @@ def test_fused_adam_matches_clip_gradient_plus_torch_adam():
     assert float(of._hyper_t[0][0][0]) == 4.0
 
 
-def test_graphed_xe_step_matches_eager_steps():
+@pytest.mark.parametrize("early", [False, True], ids=["optimizer_graph", "early_optimizer"])
+def test_graphed_xe_step_matches_eager_steps(early):
     """training.GraphedXEStep (CUDA graphs of forward+backward and of clip+Adam) == the eager step, three steps with
     fresh data each, dropout off (a captured dropout draws from the graph-safe Philox stream, not the eager one)."""
     from types import SimpleNamespace
@@ -232,7 +233,8 @@ def test_graphed_xe_step_matches_eager_steps():
         oa.step()
         losses_a.append(float(loss))
     mb, ob = make()
-    step = T.GraphedXEStep(mb, crit, ob, *batch(1), 10.0, warmup=1)
+    # early: the stage-1 parameters are updated from inside the backward pass (training.EarlyStep / FusedAdam.apply_to)
+    step = T.GraphedXEStep(mb, crit, ob, *batch(1), 10.0, warmup=1, early_optimizer=early)
     # capture does not execute: replay the six batches
     losses_b = [float(step(*batch(s))) for s in (1, 2, 3, 4, 5, 6)]
     assert max(abs(a - b) for a, b in zip(losses_a, losses_b)) <= 1e-4 * max(1.0, abs(losses_a[0]))
