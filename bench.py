@@ -437,18 +437,21 @@ def xe_train_bench(model, device, world, rank, steps, timed):
         p.grad = None
     ga, gd = graphed["as_written"], graphed["deduplicated"]
     return dict(metric="xe_train_tokens_per_sec", value=ga["value"], unit="target tokens/s", ms_per_step=ga["ms_per_step"],
-                api="training.GraphedXEStep: forward + backward (with the bucketed NCCL gradient all-reduce overlapped inside, "
-                    "dist.OverlappedGradSync) | mean + clamp + Adam, replayed from CUDA graphs",
+                api="training.GraphedXEStep: forward + backward through the hand-scheduled tape (tape.py: one autograd.Function per "
+                    "stage, encoder side streams, weight gradients off the dependent chain, T-batched decoder weight gradients), the "
+                    "NCCL gradient all-reduce overlapped inside (each fusion step's gradients leave as stage-1 backward finishes "
+                    "them) | mean + clamp + Adam; replayed from CUDA graphs",
                 eager=dict(value=round(tokens / (ms / 1e3), 1), ms_per_step=round(ms, 2),
-                           note="the same step issued op by op from Python (~2,100 kernels): bound by the host"),
+                           note="the same step issued from Python (model(...); loss.backward(); optimizer.step()): bound by the host"),
                 deduplicated=dict(value=gd["value"], ms_per_step=gd["ms_per_step"],
                                   eager=dict(value=round(tokens / (ms_dd / 1e3), 1), ms_per_step=round(ms_dd, 2))),
                 graph_loss=ga["loss"],
                 kernel_ms_and_launches=train_shares, rows_per_gpu=rows, tokens_per_step=int(tokens), loss=round(float(loss_box[0]), 4),
                 note="value: the step as written (80 replicated rows per GPU); deduplicated: stages 1-2 once per image (SURVEY D9).  "
-                     "Small-row GEMMs and dX on the split-K tcgen05 kernel (B operand "
-                     "MN-major for dX), dU = dP^T.A on the split-K 2-CTA kernel, dW with an 80-row contraction on the fp32 SIMT kernel; "
-                     "clip_gradient + Adam (train.py:56,160-163) fused in rfn_adam_step_f32", gpu_launches_per_step=launches // max(1, steps))
+                     "Stage-1 att_2_att_h on the split-fp16 engine; small-row GEMMs and dX on the split-K tcgen05 kernel (B operand "
+                     "MN-major for dX), dU = dP^T.A on the split-K 2-CTA kernel, large weight gradients through K-major copies on the "
+                     "tensor engine; clip_gradient + Adam (train.py:56,160-163) fused in rfn_adam_step_f32; phase timeline: "
+                     "profiles/r2_phase_timeline_xe.log", gpu_launches_per_step=launches // max(1, steps))
 
 
 def rl_train_bench(model, device, world, rank, steps, timed):
@@ -536,8 +539,9 @@ def rl_train_bench(model, device, world, rank, steps, timed):
         p.grad = None
     ga = graphed["as_written"]
     return dict(metric="rl_train_samples_per_sec", value=ga["value"], unit="sampled captions/s", ms_per_step=ga["ms_per_step"],
-                api="training.GraphedRLStep: sample + greedy baseline + CIDEr-D reward + criterion + backward (gradient all-reduce "
-                    "overlapped inside) | mean + clamp + Adam, replayed from CUDA graphs",
+                api="training.GraphedRLStep: stages 1-2 (taped, once) + multinomial and greedy no-tape decodes + CIDEr-D reward on the "
+                    "device + teacher-forced taped decoder over the sampled tokens + criterion + backward through the hand-scheduled "
+                    "tape (gradient all-reduce overlapped inside) | mean + clamp + Adam, replayed from CUDA graphs",
                 deduplicated=graphed["deduplicated"], graph_loss=ga["loss"], mean_reward=ga["mean_reward"],
                 eager=dict(value=round(rows * world / (ms / 1e3), 1), ms_per_step=round(ms, 2), sampled_length=box[1],
                            loss=round(float(box[0]), 4), gpu_launches_per_step=launches // max(1, steps),

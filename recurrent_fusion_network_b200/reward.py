@@ -23,7 +23,9 @@ def _tokens(s: str, vocab: Dict[str, int]) -> List[int]:
     out = []
     for w in s.split():
         if w not in vocab:
-            vocab[w] = len(vocab) + 1 if not w.lstrip("-").isdigit() else int(w)
+            # integer tokens keep their value; other words get ids above every int32 token id a caption can carry, so the two
+            # namespaces cannot collide in mixed input
+            vocab[w] = (1 << 30) + len(vocab) if not w.lstrip("-").isdigit() else int(w)
         out.append(vocab[w])
     return out
 
@@ -213,12 +215,19 @@ def _first_zero(seq):
     return out
 
 
-def get_self_critical_reward_feat_array(idx_to_word, model, fc_feat_array, att_feat_array, data, gen_result, opt, table=None):
+def get_self_critical_reward_feat_array(idx_to_word, model, fc_feat_array, att_feat_array, data, gen_result, opt, table=None,
+                                        baseline_in_train_mode=False):
     """get_rewards.py:115-129: greedy baseline decode (no grad) + CIDEr-D(sample) - CIDEr-D(greedy), broadcast over T.
-    Returns a numpy array like the reference (use compute_reward() to keep the rewards on the device)."""
+    Returns a numpy array like the reference (use compute_reward() to keep the rewards on the device).
+
+    The reference decodes the baseline in whatever mode train_rl.py left the model in -- train mode, so with
+    drop_prob_lm > 0 its greedy baseline is drawn through dropout.  The shipped RL scripts leave every dropout at 0
+    (opts.py defaults), where the two modes are the same computation; here the baseline is decoded in eval mode (the
+    fused no-tape device loop) unless baseline_in_train_mode=True asks for the reference's behaviour with dropout."""
     with torch.no_grad():
         was_training = model.training
-        model.eval()
+        if not baseline_in_train_mode:
+            model.eval()
         greedy_res = model.sample([f.detach() for f in fc_feat_array], [a.detach() for a in att_feat_array], {})[0]
         model.train(was_training)
     T = gen_result.shape[1]
