@@ -62,6 +62,9 @@ typedef struct rfn_dims {
   int32_t num_review_steps_0;             /* S0: stage-1 fusion steps */
   int32_t num_review_steps;               /* S1: stage-2 review steps */
   int32_t seq_length;                     /* L */
+  int32_t review_maxout;                  /* opt.review_maxout: stage-2 cells are 5R wide, in_transform = max of the last two R-blocks
+                                           * instead of tanh (misc/LSTMSoftMultiAttentionFeatArrayNoInputCore.py:25,60) */
+  int32_t decoder_maxout;                 /* opt.maxout: the same for the decoder cell (misc/LSTMSoftAttentionCore.py:25,89) */
 } rfn_dims;
 
 /* ---- library -------------------------------------------------------------------------- */
@@ -202,6 +205,15 @@ int rfn_lstm_cell_f32(const float* G, const float* c_prev, float* h_out, float* 
 int rfn_lstm_cell_drop_f32(const float* G, const float* c_prev, const float* mask, float scale, float* h_out,
                            float* c_out, float* h_out2, int ldh2, float* h_out3, int ldh3, int rows, int R,
                            rfn_stream_t stream);
+/* The maxout variant of the cell (opt.maxout / opt.review_maxout = 1): G is (rows, 5R) = [i|f|o|g1|g2] and the input
+ * transform is max(g1, g2) with no tanh (misc/LSTMSoftAttentionCore.py:89-91); maxout = 0 is rfn_lstm_cell_drop_f32.  Backward:
+ * the gradient of the transform goes to the larger of g1 / g2 (to both halves when they are equal, as torch.max does). */
+int rfn_lstm_cell_ex_f32(const float* G, const float* c_prev, const float* mask, float scale, int maxout, float* h_out,
+                         float* c_out, float* h_out2, int ldh2, float* h_out3, int ldh3, int rows, int R,
+                         rfn_stream_t stream);
+int rfn_lstm_cell_bwd_ex_f32(const float* G, const float* c_prev, int n_dh, const float* const* dh, const int* ld_dh,
+                             const float* mask, float scale, int maxout, const float* dc_next, float* dG, float* dc_prev,
+                             int rows, int R, rfn_stream_t stream);
 /* out[r,:] = alpha * sum_i x_i[r,:] over n <= 8 strided (rows, R) sources, and
  * out[r,:] = (((0 + in_0[r,:]) + in_1[r,:]) + ...) / n with in_j = in + j*stride (the stage-1 -> stage-2 bridge,
  * misc/RecurrentFusionModel.py:307-309, in Python's summation order). */

@@ -21,6 +21,7 @@ source TEXT at import time (nothing is copied into this repo).
 from __future__ import annotations
 
 import argparse
+import dataclasses
 import importlib.util
 import os
 import sys
@@ -62,7 +63,7 @@ def import_reference():
     return mod, opts, ref_utils
 
 
-def build_reference_model(mod, opts, cfg: O.RFNConfig):
+def build_reference_model(mod, opts, cfg: O.RFNConfig, fusion_maxout: int = 0):
     argv = sys.argv
     sys.argv = ["x", "--caption_model", "recurrent_fusion_model", "--feature_type", "feat_array",
                 "--use_cuda", "0"]
@@ -78,6 +79,9 @@ def build_reference_model(mod, opts, cfg: O.RFNConfig):
     opt.num_review_steps_0 = cfg.num_review_steps_0
     opt.num_review_steps = cfg.num_review_steps
     opt.top_words_count = cfg.top_words_count
+    opt.review_maxout = cfg.review_maxout      # opts.py:182
+    opt.maxout = cfg.decoder_maxout            # opts.py:180
+    opt.fusion_maxout = fusion_maxout          # opts.py:184: read by the model, never forwarded to the cells (:93-97)
     opt.feat_array_info = [dict(fc_feat_size=e.fc_feat_size, att_feat_size=e.att_feat_size,
                                 att_num=e.att_num) for e in cfg.encoders]
     model = mod.RecurrentFusionModel(opt)
@@ -256,6 +260,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden"))
     ap.add_argument("--skip-full", action="store_true")
+    ap.add_argument("--only", default=None, help="write this case only (and append its line to PIN_LOG.txt)")
     args = ap.parse_args()
     os.makedirs(args.out, exist_ok=True)
     torch.set_num_threads(8)
@@ -275,6 +280,9 @@ def main():
         ("tiny_j3_eos_a", O.tiny_config(3), 5, 1243, 8, TINY, 1),
         ("tiny_j3_eos_b", O.tiny_config(3), 5, 1246, 8, TINY, 1),
         ("tiny_j1", O.tiny_config(1), 2, 1237, 10, dict(init_range=0.5, logit_scale=3.0), 1),
+        # the maxout variants of the stage-2 and decoder cells (opts.py:180-183; default 0 in every shipped script)
+        ("tiny_j2_maxout", dataclasses.replace(O.tiny_config(2), review_maxout=1, decoder_maxout=1), 4, 1248, 8, TINY, 1),
+        ("tiny_j3_maxout_dec", dataclasses.replace(O.tiny_config(3), decoder_maxout=1), 5, 1243, 8, TINY, 1),
     ]
     if not args.skip_full:
         cases += [
@@ -283,9 +291,21 @@ def main():
             ("full_j5", O.RFNConfig(), 4, 1234, 7, {}, 97),
             ("full_j5_sharp", O.RFNConfig(), 4, 1234, 9, SHARP, 97),
         ]
+    if args.only:
+        cases = [c for c in cases if c[0] == args.only]
+        assert cases, args.only
+        # fusion_maxout = 1 changes nothing: FeatArrayFusionNoInputCore does not pass it on to its cells
+        m1, _ = build_reference_model(mod, opts, cases[0][1], fusion_maxout=1)
+        m0, _ = build_reference_model(mod, opts, cases[0][1], fusion_maxout=0)
+        assert {k: tuple(v.shape) for k, v in m1.state_dict().items()} == {k: tuple(v.shape) for k, v in m0.state_dict().items()}
+        log(f"[{args.only}] fusion_maxout=1 leaves every state_dict shape unchanged (never forwarded, misc/RecurrentFusionModel.py:93-97)")
     for name, cfg, rows, wseed, iseed, wkw, stride in cases:
         out = run_case(mod, opts, ref_utils, name, cfg, rows, wseed, iseed, wkw, stride, log=log)
         np.savez_compressed(os.path.join(args.out, name + ".npz"), **out)
+    if args.only:
+        with open(os.path.join(args.out, "PIN_LOG.txt"), "a") as f:
+            f.write("\n".join(lines) + "\n")
+        return
     np.savez_compressed(os.path.join(args.out, "ciderd.npz"), **ciderd_case(log))
     with open(os.path.join(args.out, "PIN_LOG.txt"), "w") as f:
         f.write("oracle/gen_golden.py -- oracle restatement vs the imported reference modules "

@@ -61,6 +61,8 @@ class RFNConfig:
     num_review_steps_0: int = 8      # opts.py:207-210
     num_review_steps: int = 8
     top_words_count: int = 1000      # opts.py:23
+    review_maxout: int = 0           # opts.py:182 (stage-2 cells 5R wide, misc/LSTMSoftMultiAttentionFeatArrayNoInputCore.py:25)
+    decoder_maxout: int = 0          # opts.py:180 `--maxout` (misc/LSTMSoftAttentionCore.py:25)
 
     @property
     def J(self) -> int:
@@ -114,17 +116,19 @@ def state_dict_shapes(cfg: RFNConfig) -> Dict[str, Tuple[int, ...]]:
             lin(p + ".z2h", 4 * R, e.att_feat_size)
     for j in range(J):
         lin(f"reason_linear_individual.{j}", K, R)
+    g2 = (5 if cfg.review_maxout else 4) * R
+    gd = (5 if cfg.decoder_maxout else 4) * R
     for s in range(cfg.num_review_steps):
         p = f"review_steps.{s}"
-        lin(p + ".h2h", 4 * R, R)
+        lin(p + ".h2h", g2, R)
         for j in range(J):
-            lin(p + f".z_2_h.{j}", 4 * R, R)
+            lin(p + f".z_2_h.{j}", g2, R)
         for j in range(J):
             att(p + f".att_model.{j}", R)
     lin("reason_linear", K, R)
-    lin("decoder.i2h", 4 * R, E)
-    lin("decoder.h2h", 4 * R, R)
-    lin("decoder.z2h", 4 * R, R)
+    lin("decoder.i2h", gd, E)
+    lin("decoder.h2h", gd, R)
+    lin("decoder.z2h", gd, R)
     lin("decoder.att_2_att_h", A, R)
     lin("decoder.h_2_att_h", A, R)
     lin("decoder.att_h_2_out", 1, A)
@@ -219,7 +223,10 @@ def lstm_cell(G: Tensor, c: Tensor) -> Tuple[Tensor, Tensor]:
     R = c.shape[1]
     sig = torch.sigmoid(G[:, :3 * R])
     i, f, o = sig[:, :R], sig[:, R:2 * R], sig[:, 2 * R:3 * R]
-    g = torch.tanh(G[:, 3 * R:4 * R])
+    if G.shape[1] == 5 * R:      # maxout variant: no tanh (misc/LSTMSoftAttentionCore.py:88-91, ...FeatArrayNoInputCore.py:59-62)
+        g = torch.max(G[:, 3 * R:4 * R], G[:, 4 * R:5 * R])
+    else:
+        g = torch.tanh(G[:, 3 * R:4 * R])
     c2 = f * c + i * g
     h2 = o * torch.tanh(c2)
     return h2, c2  # dropout is identity in eval mode / p = 0

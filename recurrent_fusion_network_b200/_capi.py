@@ -32,6 +32,8 @@ class RfnDims(C.Structure):
         ("num_review_steps_0", C.c_int32),
         ("num_review_steps", C.c_int32),
         ("seq_length", C.c_int32),
+        ("review_maxout", C.c_int32),
+        ("decoder_maxout", C.c_int32),
     ]
 
 
@@ -120,6 +122,8 @@ _SIGNATURES = {
     "rfn_adam_step_f32": (_i, [_i, _pp, _pp, _pp, _pp, C.POINTER(C.c_int64), _f, _f, _f, _f, _f, _f, _f, _i, _vp, _vp]),
     "rfn_rl_loss_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
     "rfn_lstm_cell_drop_f32": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp]),
+    "rfn_lstm_cell_ex_f32": (_i, [_vp, _vp, _vp, _f, _i, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp]),
+    "rfn_lstm_cell_bwd_ex_f32": (_i, [_vp, _vp, _i, _pp, C.POINTER(_i), _vp, _f, _i, _vp, _vp, _vp, _i, _i, _vp]),
     "rfn_sum_strided_f32": (_i, [_i, _pp, C.POINTER(_i), _f, _vp, _i, _i, _i, _vp]),
     "rfn_mean_tensors_f32": (_i, [_vp, _sz, _i, _vp, _i, _i, _i, _i, _vp]),
     "rfn_xe_loss_strided_f32": (_i, [_vp, _sz, _sz, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
@@ -195,7 +199,7 @@ def stream() -> int:
 
 
 def make_dims(encoders, rnn_size, att_hid_size, input_encoding_size, vocab_plus1, top_words_count,
-              num_review_steps_0, num_review_steps, seq_length) -> RfnDims:
+              num_review_steps_0, num_review_steps, seq_length, review_maxout=0, decoder_maxout=0) -> RfnDims:
     """encoders: sequence of (att_num, att_feat_size, fc_feat_size)."""
     if len(encoders) > MAX_ENCODERS:
         raise RfnError(f"at most {MAX_ENCODERS} encoders are supported")
@@ -206,6 +210,7 @@ def make_dims(encoders, rnn_size, att_hid_size, input_encoding_size, vocab_plus1
     d.rnn_size, d.att_hid_size, d.input_encoding_size = rnn_size, att_hid_size, input_encoding_size
     d.vocab_plus1, d.top_words_count = vocab_plus1, top_words_count
     d.num_review_steps_0, d.num_review_steps, d.seq_length = num_review_steps_0, num_review_steps, seq_length
+    d.review_maxout, d.decoder_maxout = (1 if review_maxout else 0), (1 if decoder_maxout else 0)
     return d
 
 

@@ -197,13 +197,15 @@ class CellFn(Function):
     """LSTM update, gate order [i|f|o|g] (misc/RecurrentFusionModel.py:55-73)."""
 
     @staticmethod
-    def forward(ctx, G, c_prev):
+    def forward(ctx, G, c_prev, maxout=0):
         G, c_prev = _c(G), _c(c_prev)
         rows, R = c_prev.shape
         h = torch.empty_like(c_prev)
         c = torch.empty_like(c_prev)
-        check(lib().rfn_lstm_cell_f32(ptr(G), ptr(c_prev), ptr(h), ptr(c), None, 0, rows, R, stream()), "rfn_lstm_cell_f32")
+        check(lib().rfn_lstm_cell_ex_f32(ptr(G), ptr(c_prev), None, 1.0, int(maxout), ptr(h), ptr(c), None, 0, None, 0, rows, R,
+                                         stream()), "rfn_lstm_cell_ex_f32")
         ctx.save_for_backward(G, c_prev)
+        ctx.maxout = int(maxout)
         return h, c
 
     @staticmethod
@@ -213,10 +215,12 @@ class CellFn(Function):
         rows, R = c_prev.shape
         dG = torch.empty_like(G)
         dcp = torch.empty_like(c_prev)
-        check(lib().rfn_lstm_cell_bwd_f32(ptr(G), ptr(c_prev), ptr(_c(dh)) if dh is not None else None,
-                                          ptr(_c(dc)) if dc is not None else None, ptr(dG), ptr(dcp), rows, R, stream()),
-              "rfn_lstm_cell_bwd_f32")
-        return dG, dcp
+        srcs = [_c(dh)] if dh is not None else []
+        ld = (C.c_int * 1)(R)
+        check(lib().rfn_lstm_cell_bwd_ex_f32(ptr(G), ptr(c_prev), len(srcs), ptr_array(srcs) if srcs else None, ld, None, 1.0,
+                                             ctx.maxout, ptr(_c(dc)) if dc is not None else None, ptr(dG), ptr(dcp), rows, R,
+                                             stream()), "rfn_lstm_cell_bwd_ex_f32")
+        return dG, dcp, None
 
 
 class LogSoftmaxFn(Function):

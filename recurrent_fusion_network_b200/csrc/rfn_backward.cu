@@ -375,12 +375,14 @@ struct CellBwdSrcs {
 };
 __global__ void lstm_cell_bwd_multi_kernel(const float* __restrict__ G, const float* __restrict__ c_prev, CellBwdSrcs src,
                                            const float* __restrict__ mask, float scale, const float* __restrict__ dc_next,
-                                           float* __restrict__ dG, float* __restrict__ dc_prev, int rows, int R) {
+                                           float* __restrict__ dG, float* __restrict__ dc_prev, int rows, int R, int maxout) {
   const size_t total = (size_t)rows * R;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / R), k = (int)(i % R);
-    const float* Gr = G + (size_t)r * 4 * R;
-    const float ig = sigm(Gr[k]), fg = sigm(Gr[R + k]), og = sigm(Gr[2 * R + k]), gg = tanhf(Gr[3 * R + k]);
+    const float* Gr = G + (size_t)r * (4 + maxout) * R;
+    const float ig = sigm(Gr[k]), fg = sigm(Gr[R + k]), og = sigm(Gr[2 * R + k]);
+    const float g1 = Gr[3 * R + k], g2 = maxout ? Gr[4 * R + k] : 0.f;
+    const float gg = maxout ? fmaxf(g1, g2) : tanhf(g1);
     const float cp = c_prev[i];
     const float c2 = fg * cp + ig * gg;
     const float tc = tanhf(c2);
@@ -388,22 +390,28 @@ __global__ void lstm_cell_bwd_multi_kernel(const float* __restrict__ G, const fl
     for (int s = 0; s < src.n; ++s) dhv += src.p[s][(size_t)r * src.ld[s] + k];
     if (mask) dhv *= mask[i] * scale;
     const float dc = (dc_next ? dc_next[i] : 0.f) + dhv * og * (1.f - tc * tc);
-    float* dGr = dG + (size_t)r * 4 * R;
+    float* dGr = dG + (size_t)r * (4 + maxout) * R;
     dGr[k] = dc * gg * ig * (1.f - ig);
     dGr[R + k] = dc * cp * fg * (1.f - fg);
     dGr[2 * R + k] = dhv * tc * og * (1.f - og);
-    dGr[3 * R + k] = dc * ig * (1.f - gg * gg);
+    if (maxout) {   // d max(g1, g2): to the larger one; split evenly on a tie (torch.max(a, b)'s backward)
+      const float dt = dc * ig;
+      dGr[3 * R + k] = g1 > g2 ? dt : (g1 == g2 ? 0.5f * dt : 0.f);
+      dGr[4 * R + k] = g2 > g1 ? dt : (g1 == g2 ? 0.5f * dt : 0.f);
+    } else {
+      dGr[3 * R + k] = dc * ig * (1.f - gg * gg);
+    }
     dc_prev[i] = dc * fg;
   }
 }
 int lstm_cell_bwd_multi(const float* G, const float* c_prev, const CellBwdSrcs& src, const float* mask, float scale,
-                        const float* dc_next, float* dG, float* dc_prev, int rows, int R, cudaStream_t st) {
+                        const float* dc_next, float* dG, float* dc_prev, int rows, int R, cudaStream_t st, int maxout = 0) {
   ProfScope prof__(TAG_CELL, st);
   RFN_CHECK_ARG(G && c_prev && dG && dc_prev, "lstm_cell_bwd_multi: null pointer");
   if (rows == 0) return RFN_OK;
   const size_t total = (size_t)rows * R;
   lstm_cell_bwd_multi_kernel<<<(int)min((size_t)148 * 8, (total + 255) / 256), 256, 0, st>>>(G, c_prev, src, mask, scale, dc_next,
-                                                                                          dG, dc_prev, rows, R);
+                                                                                          dG, dc_prev, rows, R, maxout ? 1 : 0);
   RFN_LAUNCH_CHECK();
   return RFN_OK;
 }
@@ -805,6 +813,11 @@ int rfn_rl_loss_bwd_strided_f32(const int64_t* seq, const float* reward, const f
 int rfn_lstm_cell_bwd_multi_f32(const float* G, const float* c_prev, int n_dh, const float* const* dh, const int* ld_dh,
                                 const float* mask, float scale, const float* dc_next, float* dG, float* dc_prev, int rows, int R,
                                 rfn_stream_t stream) {
+  return rfn_lstm_cell_bwd_ex_f32(G, c_prev, n_dh, dh, ld_dh, mask, scale, 0, dc_next, dG, dc_prev, rows, R, stream);
+}
+int rfn_lstm_cell_bwd_ex_f32(const float* G, const float* c_prev, int n_dh, const float* const* dh, const int* ld_dh,
+                             const float* mask, float scale, int maxout, const float* dc_next, float* dG, float* dc_prev, int rows,
+                             int R, rfn_stream_t stream) {
   RFN_CHECK_ARG(n_dh >= 0 && n_dh <= 8 && (n_dh == 0 || (dh && ld_dh)), "rfn_lstm_cell_bwd_multi_f32: 0..8 dh sources");
   CellBwdSrcs src{};
   src.n = n_dh;
@@ -813,7 +826,7 @@ int rfn_lstm_cell_bwd_multi_f32(const float* G, const float* c_prev, int n_dh, c
     src.p[s] = dh[s];
     src.ld[s] = ld_dh[s];
   }
-  return lstm_cell_bwd_multi(G, c_prev, src, mask, scale, dc_next, dG, dc_prev, rows, R, (cudaStream_t)stream);
+  return lstm_cell_bwd_multi(G, c_prev, src, mask, scale, dc_next, dG, dc_prev, rows, R, (cudaStream_t)stream, maxout);
 }
 /* dX[M,K] (+)= sum_i dY_i[M,N_i] . W_i[N_i,K]: the input gradient of y = sum_i x_i W_i^T, and with several dY_i the sum over
  * the consumers of one input (dH of a fusion step = sum over the J encoders' gate GEMMs) in ONE launch. */

@@ -497,6 +497,7 @@ void pd_bind_parts(const rfn_dims& d, PDArgs& a, float* base) {
 
 bool pd_supported(const rfn_dims& d, int rows) {
   if (!g_pd_enabled.load() || rows < 1 || rows > PD_MAX_ROWS) return false;
+  if (d.decoder_maxout) return false;   // the resident gate rows are laid out for the 4R cell: maxout keeps the per-step kernels
   if (d.rnn_size % 4 || d.att_hid_size % 4 || d.input_encoding_size % 4) return false;
   int dev = 0, n_sm = 0, coop = 0, max_smem = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return false;

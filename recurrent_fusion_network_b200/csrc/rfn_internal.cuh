@@ -172,7 +172,7 @@ int attention_from_scores(const float* A, const float* scores, int nslices, cons
                           int lda_bf16 = 0);
 int lstm_cell(const float* G, const float* c_prev, float* h_out, float* c_out, float* h_out2,
               int ldh2, float* h_out3, int ldh3, int rows, int R, cudaStream_t st, const float* mask = nullptr,
-              float scale = 1.f);
+              float scale = 1.f, int maxout = 0);
 int embed_gather_i64(const int64_t* tok, int ld_tok, const float* embed, float* x, int rows, int E,
                      int V1, cudaStream_t st);
 int embed_gather_i32(const int32_t* tok, const float* embed, float* x, int rows, int E, int V1,

@@ -48,8 +48,14 @@ struct Bump {
   }
 };
 
+// gate-row widths: 4R, or 5R with the maxout input transform (misc/LSTMSoftAttentionCore.py:25, ...FeatArrayNoInputCore.py:25)
+static inline int g2w(const rfn_dims& d) { return (4 + (d.review_maxout ? 1 : 0)) * d.rnn_size; }
+static inline int gdw(const rfn_dims& d) { return (4 + (d.decoder_maxout ? 1 : 0)) * d.rnn_size; }
+
 static int check_dims(const rfn_dims* d) {
   RFN_CHECK_ARG(d != nullptr, "dims is null");
+  RFN_CHECK_ARG((d->review_maxout == 0 || d->review_maxout == 1) && (d->decoder_maxout == 0 || d->decoder_maxout == 1),
+                "review_maxout / decoder_maxout must be 0 or 1");
   RFN_CHECK_ARG(d->J >= 1 && d->J <= RFN_MAX_ENCODERS, "J=%d not in 1..%d", d->J, RFN_MAX_ENCODERS);
   RFN_CHECK_ARG(d->rnn_size % 4 == 0 && d->att_hid_size % 4 == 0 && d->input_encoding_size % 4 == 0,
                 "rnn_size/att_hid_size/input_encoding_size must be multiples of 4");
@@ -229,7 +235,7 @@ struct WCache {
       int jn = 0;
       for (int grp = 0; grp < G2; ++grp) {   // the grouping of thought_vectors()'s stage-2 gate GEMMs
         WGroupDesc w{};
-        w.n_rows = 4 * R;
+        w.n_rows = g2w(d);
         int n = 0;
         if (grp == 0) { w.K[n] = R; w.pidx[n++] = ix.s2_h2h(s, 0); }
         while (n < 3 && jn < J) { w.K[n] = R; w.pidx[n++] = ix.s2_z2h(s, jn, 0); ++jn; }
@@ -242,7 +248,7 @@ struct WCache {
     add(K, {R}, {ix.reason(0)});
     add(A, {R}, {ix.dec(6)});
     add(A, {R}, {ix.dec(8)});
-    add(4 * R, {E, R, R}, {ix.dec(0), ix.dec(2), ix.dec(4)});
+    add(gdw(d), {E, R, R}, {ix.dec(0), ix.dec(2), ix.dec(4)});
     add(V, {R}, {ix.logit(0)});
   }
   // the cached operands of group i, or nullptr when there is no cache
@@ -282,7 +288,7 @@ static size_t carve_tv(const rfn_dims& d, int rows, bool need_tv, bool need_reas
     w.p_cap[j] = p_floats(d, rows, std::max(d.att_num[j], S0));
     w.P[j] = b.take<float>(w.p_cap[j]);
     w.z[j] = b.take<float>((size_t)rows * std::max(d.att_feat_size[j], R));
-    w.G[j] = b.take<float>((size_t)rows * 4 * R);
+    w.G[j] = b.take<float>((size_t)rows * std::max(4 * R, g2w(d)));
     w.h3[j] = H3Ws{};
     w.fsplit[j] = nullptr;
     w.fsplit_cap[j] = 0;
@@ -292,7 +298,7 @@ static size_t carve_tv(const rfn_dims& d, int rows, bool need_tv, bool need_reas
       w.fsplit[j] = b.take<char>(w.fsplit_cap[j]);
       w.h3[j].xcap = std::max({split2(rows, J * R, D), split1(rows, R), split1(rows, F), split3(rows, R, R, R), split1(rows * S1, R)});
       w.h3[j].x = b.take<char>(w.h3[j].xcap);
-      w.h3[j].wcap = std::max({split2(4 * R, J * R, D), split1(A, D), split1(A, R), split1(R, F), split3(4 * R, R, R, R), split1(K, R)});
+      w.h3[j].wcap = std::max({split2(4 * R, J * R, D), split1(A, D), split1(A, R), split1(R, F), split3(g2w(d), R, R, R), split1(K, R)});
       w.h3[j].w = b.take<char>(w.h3[j].wcap);
     }
   }
@@ -475,7 +481,7 @@ static int thought_vectors(const rfn_dims& d, const float* const* prm, const flo
         ga.src[n++] = GemmSrc{w.z[jn], prm[ix.s2_z2h(s, jn, 0)], prm[ix.s2_z2h(s, jn, 1)], R, R, R};
         ++jn;
       }
-      ga.nsrc = n; ga.y = w.G[0]; ga.ldy = 4 * R; ga.M = rows; ga.N = 4 * R; ga.accumulate = first ? 0 : 1;
+      ga.nsrc = n; ga.y = w.G[0]; ga.ldy = g2w(d); ga.M = rows; ga.N = g2w(d); ga.accumulate = first ? 0 : 1;
       {
         TagScope ts(TAG_GEMM_GATES);
         H3Operand wo[3];
@@ -484,7 +490,7 @@ static int thought_vectors(const rfn_dims& d, const float* const* prm, const flo
       first = false;
       ++grp;
     }
-    RFN_TRY(lstm_cell(w.G[0], c_out, hout, c_out, TVc + (size_t)s * R, S1 * R, nullptr, 0, rows, R, st));
+    RFN_TRY(lstm_cell(w.G[0], c_out, hout, c_out, TVc + (size_t)s * R, S1 * R, nullptr, 0, rows, R, st, nullptr, 1.f, d.review_maxout));
   }
   if (reason_pred) {
     H3Operand wo[3];
@@ -520,7 +526,7 @@ static size_t carve_dec(const rfn_dims& d, int rowsA, int rows, int beam, int n_
   w.x = b.take<float>((size_t)rows * E);
   w.g = b.take<float>((size_t)rows * A);
   w.z = b.take<float>((size_t)rows * R);
-  w.G = b.take<float>((size_t)rows * 4 * R);
+  w.G = b.take<float>((size_t)rows * gdw(d));
   w.logits = b.take<float>((size_t)rows * V * n_logit_bufs);
   w.rowmax = b.take<float>(rows);
   w.logsum = b.take<float>(rows);
@@ -546,7 +552,7 @@ static size_t carve_dec(const rfn_dims& d, int rowsA, int rows, int beam, int n_
     w.h3.wcap = split1(A, R);
     w.h3.w = b.take<char>(w.h3.wcap);
     w.wsplit_cap[0] = split1(A, R);
-    w.wsplit_cap[1] = split3(4 * R, E, R, R);
+    w.wsplit_cap[1] = split3(gdw(d), E, R, R);
     w.wsplit_cap[2] = split1(V, R);
     for (int i = 0; i < 3; ++i) w.wsplit[i] = b.take<char>(w.wsplit_cap[i]);
   }
@@ -593,7 +599,7 @@ static int decoder_prepare(const rfn_dims& d, const float* const* prm, const flo
     {
       const float* ws[3] = {prm[ix.dec(0)], prm[ix.dec(2)], prm[ix.dec(4)]};
       const int ld[3] = {E, R, R}, K[3] = {E, R, R};
-      RFN_TRY(h3_split(ws, ld, K, 3, 4 * R, bf, w->wsplit[1], w->w_gates, st));
+      RFN_TRY(h3_split(ws, ld, K, 3, gdw(d), bf, w->wsplit[1], w->w_gates, st));
     }
     {
       const float* ws[1] = {prm[ix.logit(0)]};
@@ -620,12 +626,12 @@ static int decoder_step(const rfn_dims& d, const float* const* prm, const float*
   ga.src[0] = GemmSrc{x, prm[ix.dec(0)], prm[ix.dec(1)], E, E, E};
   ga.src[1] = GemmSrc{hin, prm[ix.dec(2)], prm[ix.dec(3)], R, R, R};
   ga.src[2] = GemmSrc{w.z, prm[ix.dec(4)], prm[ix.dec(5)], R, R, R};
-  ga.nsrc = 3; ga.y = w.G; ga.ldy = 4 * R; ga.M = rows; ga.N = 4 * R;
+  ga.nsrc = 3; ga.y = w.G; ga.ldy = gdw(d); ga.M = rows; ga.N = gdw(d);
   {
     TagScope ts(TAG_GEMM_GATES);
     RFN_TRY(path_gemm(ga, sc, nullptr, w.w_gates, st));
   }
-  RFN_TRY(lstm_cell(w.G, cin, hout, cout, nullptr, 0, nullptr, 0, rows, R, st));
+  RFN_TRY(lstm_cell(w.G, cin, hout, cout, nullptr, 0, nullptr, 0, rows, R, st, nullptr, 1.f, d.decoder_maxout));
   if (fused) *fused = 0;
   if (logits) {
     GemmArgs la = gemm1(hout, R, prm[ix.logit(0)], prm[ix.logit(1)], R, logits, V, rows, V);

@@ -11,17 +11,18 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 __global__ void lstm_cell_kernel(const float* __restrict__ G, const float* c_prev,
                                  float* __restrict__ h_out, float* c_out,
                                  float* __restrict__ h_out2, int ldh2, float* __restrict__ h_out3,
-                                 int ldh3, int rows, int R, const float* __restrict__ mask, float scale) {
+                                 int ldh3, int rows, int R, const float* __restrict__ mask, float scale, int maxout) {
   pdl_trigger();
   pdl_wait();
   const size_t total = (size_t)rows * R;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / R), k = (int)(i % R);
-    const float* Gr = G + (size_t)r * 4 * R;
+    const float* Gr = G + (size_t)r * (4 + maxout) * R;
     const float ig = sigmoidf_(Gr[k]);
     const float fg = sigmoidf_(Gr[R + k]);
     const float og = sigmoidf_(Gr[2 * R + k]);
-    const float gg = tanhf(Gr[3 * R + k]);
+    // maxout: in_transform = max of the last two R-blocks of a 5R-wide gate row, no tanh (misc/LSTMSoftAttentionCore.py:89-91)
+    const float gg = maxout ? fmaxf(Gr[3 * R + k], Gr[4 * R + k]) : tanhf(Gr[3 * R + k]);
     const float c2 = fg * c_prev[i] + ig * gg;
     float h2 = og * tanhf(c2);
     if (mask) h2 = scale * h2 * mask[i];   // nn.Dropout with an explicit keep-mask (training): the state carries the dropped h
@@ -33,13 +34,13 @@ __global__ void lstm_cell_kernel(const float* __restrict__ G, const float* c_pre
 }
 
 int lstm_cell(const float* G, const float* c_prev, float* h_out, float* c_out, float* h_out2, int ldh2,
-              float* h_out3, int ldh3, int rows, int R, cudaStream_t st, const float* mask, float scale) {
+              float* h_out3, int ldh3, int rows, int R, cudaStream_t st, const float* mask, float scale, int maxout) {
   ProfScope prof__(TAG_CELL, st);
   RFN_CHECK_ARG(G && c_prev && c_out, "lstm_cell: null pointer");
   if (rows == 0) return RFN_OK;
   const size_t total = (size_t)rows * R;
   const int blocks = (int)min((size_t)148 * 8, (total + 255) / 256);
-  RFN_CUDA(launch_pdl(lstm_cell_kernel, dim3(blocks), dim3(256), 0, st, G, c_prev, h_out, c_out, h_out2, ldh2, h_out3, ldh3, rows, R, mask, scale));
+  RFN_CUDA(launch_pdl(lstm_cell_kernel, dim3(blocks), dim3(256), 0, st, G, c_prev, h_out, c_out, h_out2, ldh2, h_out3, ldh3, rows, R, mask, scale, maxout ? 1 : 0));
   RFN_LAUNCH_CHECK();
   return RFN_OK;
 }
@@ -161,6 +162,12 @@ int mean_logits8(const PtrList8& ptrs, int n, float* out, size_t count, cudaStre
 extern "C" int rfn_lstm_cell_f32(const float* G, const float* c_prev, float* h_out, float* c_out, float* h_out2,
                                  int ldh2, int rows, int R, rfn_stream_t stream) {
   return rfn::lstm_cell(G, c_prev, h_out, c_out, h_out2, ldh2, nullptr, 0, rows, R, (cudaStream_t)stream);
+}
+
+extern "C" int rfn_lstm_cell_ex_f32(const float* G, const float* c_prev, const float* mask, float scale, int maxout, float* h_out,
+                                    float* c_out, float* h_out2, int ldh2, float* h_out3, int ldh3, int rows, int R,
+                                    rfn_stream_t stream) {
+  return rfn::lstm_cell(G, c_prev, h_out, c_out, h_out2, ldh2, h_out3, ldh3, rows, R, (cudaStream_t)stream, mask, scale, maxout);
 }
 
 extern "C" int rfn_lstm_cell_drop_f32(const float* G, const float* c_prev, const float* mask, float scale, float* h_out,

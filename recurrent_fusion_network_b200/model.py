@@ -99,14 +99,16 @@ def linear(srcs, rows: int, out_features: int, out: Optional[torch.Tensor] = Non
     return y
 
 
-def lstm_cell(G: torch.Tensor, c_prev: torch.Tensor):
+def lstm_cell(G: torch.Tensor, c_prev: torch.Tensor, maxout: int = 0):
+    """maxout: G is (rows, 5R) and the input transform is the max of its last two R-blocks (no tanh)."""
     if _taping(G, c_prev):
         from . import autograd as AG
-        return AG.CellFn.apply(G, c_prev)
+        return AG.CellFn.apply(G, c_prev, int(bool(maxout)))
     rows, R = c_prev.shape
     h = torch.empty_like(c_prev)
     c = torch.empty_like(c_prev)
-    check(lib().rfn_lstm_cell_f32(ptr(G), ptr(c_prev), ptr(h), ptr(c), None, 0, rows, R, stream()), "rfn_lstm_cell_f32")
+    check(lib().rfn_lstm_cell_ex_f32(ptr(G), ptr(c_prev), None, 1.0, int(bool(maxout)), ptr(h), ptr(c), None, 0, None, 0, rows, R,
+                                     stream()), "rfn_lstm_cell_ex_f32")
     return h, c
 
 
@@ -162,13 +164,14 @@ class LSTMFusionNoInputCore(nn.Module):
 
     def __init__(self, H_size, rnn_size, att_feat_size, att_num, att_hid_size, drop_prob_fusion, maxout=0):
         super().__init__()
-        if maxout:
-            raise _capi.RfnError("fusion maxout is unreachable in the reference (SURVEY D-minor) and not built")
+        # maxout = 1 is unreachable through RecurrentFusionModel (FeatArrayFusionNoInputCore never forwards fusion_maxout,
+        # misc/RecurrentFusionModel.py:93-97); the cell itself supports it as the reference class does (:33-38, :61-65)
         self.drop_prob_fusion, self.att_hid_size, self.maxout = drop_prob_fusion, att_hid_size, maxout
         self.H_size, self.rnn_size, self.att_feat_size, self.att_num = H_size, rnn_size, att_feat_size, att_num
         self.att_model = AttentionModelCore(rnn_size, att_feat_size, att_num, att_hid_size)
-        self.H2h = nn.Linear(H_size, 4 * rnn_size)
-        self.z2h = nn.Linear(att_feat_size, 4 * rnn_size)
+        gw = (5 if maxout else 4) * rnn_size
+        self.H2h = nn.Linear(H_size, gw)
+        self.z2h = nn.Linear(att_feat_size, gw)
         self.dropout = nn.Dropout(drop_prob_fusion)
         self.H2h.weight.data.uniform_(-_INIT, _INIT)   # biases keep nn.Linear's default (:43-45)
         self.z2h.weight.data.uniform_(-_INIT, _INIT)
@@ -176,8 +179,8 @@ class LSTMFusionNoInputCore(nn.Module):
     def forward(self, H, att_feat, state):
         pre_h, pre_c = _last_layer(state[0]), _last_layer(state[1])
         z = self.att_model(pre_h, att_feat)
-        G = linear([(H, self.H2h), (z, self.z2h)], pre_h.shape[0], 4 * self.rnn_size)
-        next_h, next_c = lstm_cell(G, _f32c(pre_c))
+        G = linear([(H, self.H2h), (z, self.z2h)], pre_h.shape[0], self.H2h.out_features)
+        next_h, next_c = lstm_cell(G, _f32c(pre_c), self.maxout)
         next_h = _dropout(next_h, self.drop_prob_fusion, self.training)
         return next_h, (next_h.unsqueeze(0), next_c.unsqueeze(0))
 
@@ -211,14 +214,13 @@ class LSTMSoftMultiAttentionFeatArrayNoInputCore(nn.Module):
 
     def __init__(self, rnn_size, att_feat_size, att_num, att_hid_size, drop_prob_lm, maxout=0):
         super().__init__()
-        if maxout:
-            raise _capi.RfnError("review_maxout=1 is not built (default 0 in every shipped script)")
         assert len(att_feat_size) == len(att_num)
         self.rnn_size, self.att_feat_size, self.att_num = rnn_size, att_feat_size, att_num
         self.num_feat_array = len(att_feat_size)
         self.drop_prob_lm, self.att_hid_size, self.maxout = drop_prob_lm, att_hid_size, maxout
-        self.h2h = nn.Linear(rnn_size, 4 * rnn_size)
-        self.z_2_h = nn.ModuleList([nn.Linear(att_feat_size[i], 4 * rnn_size) for i in range(self.num_feat_array)])
+        gw = (5 if maxout else 4) * rnn_size                   # :25-30
+        self.h2h = nn.Linear(rnn_size, gw)
+        self.z_2_h = nn.ModuleList([nn.Linear(att_feat_size[i], gw) for i in range(self.num_feat_array)])
         self.att_model = nn.ModuleList([AttentionModelCore(rnn_size, att_feat_size[i], att_num[i], att_hid_size)
                                         for i in range(self.num_feat_array)])
         self.dropout = nn.Dropout(drop_prob_lm)
@@ -228,8 +230,8 @@ class LSTMSoftMultiAttentionFeatArrayNoInputCore(nn.Module):
         pre_h, pre_c = _last_layer(state[0]), _last_layer(state[1])
         zs = [self.att_model[i](pre_h, att_seq[i]) for i in range(self.num_feat_array)]
         srcs = [(pre_h, self.h2h)] + [(zs[i], self.z_2_h[i]) for i in range(self.num_feat_array)]
-        G = linear(srcs, pre_h.shape[0], 4 * self.rnn_size)
-        next_h, next_c = lstm_cell(G, _f32c(pre_c))
+        G = linear(srcs, pre_h.shape[0], self.h2h.out_features)
+        next_h, next_c = lstm_cell(G, _f32c(pre_c), self.maxout)
         next_h = _dropout(next_h, self.drop_prob_lm, self.training)
         return next_h, (next_h.unsqueeze(0), next_c.unsqueeze(0))
 
@@ -239,13 +241,12 @@ class LSTMSoftAttentionCore(nn.Module):
 
     def __init__(self, input_encoding_size, rnn_size, att_feat_size, att_num, att_hid_size, drop_prob_lm, maxout=0):
         super().__init__()
-        if maxout:
-            raise _capi.RfnError("decoder maxout=1 is not built (default 0 in every shipped script)")
         self.input_encoding_size, self.rnn_size, self.drop_prob_lm = input_encoding_size, rnn_size, drop_prob_lm
         self.att_feat_size, self.att_num, self.att_hid_size, self.maxout = att_feat_size, att_num, att_hid_size, maxout
-        self.i2h = nn.Linear(input_encoding_size, 4 * rnn_size)
-        self.h2h = nn.Linear(rnn_size, 4 * rnn_size)
-        self.z2h = nn.Linear(att_feat_size, 4 * rnn_size)
+        gw = (5 if maxout else 4) * rnn_size                   # :25-32
+        self.i2h = nn.Linear(input_encoding_size, gw)
+        self.h2h = nn.Linear(rnn_size, gw)
+        self.z2h = nn.Linear(att_feat_size, gw)
         self.att_2_att_h = nn.Linear(att_feat_size, att_hid_size)
         self.h_2_att_h = nn.Linear(rnn_size, att_hid_size)
         self.att_h_2_out = nn.Linear(att_hid_size, 1)
@@ -256,8 +257,8 @@ class LSTMSoftAttentionCore(nn.Module):
     def forward(self, xt, att_seq, state):
         pre_h, pre_c = _last_layer(state[0]), _last_layer(state[1])
         z = _attention(self, pre_h, att_seq)
-        G = linear([(xt, self.i2h), (pre_h, self.h2h), (z, self.z2h)], pre_h.shape[0], 4 * self.rnn_size)
-        next_h, next_c = lstm_cell(G, _f32c(pre_c))
+        G = linear([(xt, self.i2h), (pre_h, self.h2h), (z, self.z2h)], pre_h.shape[0], self.i2h.out_features)
+        next_h, next_c = lstm_cell(G, _f32c(pre_c), self.maxout)
         next_h = _dropout(next_h, self.drop_prob_lm, self.training)
         return next_h, (next_h.unsqueeze(0), next_c.unsqueeze(0))
 
@@ -269,12 +270,11 @@ class LSTMSoftAttentionNoInputCore(nn.Module):
 
     def __init__(self, rnn_size, att_feat_size, att_num, att_hid_size, drop_prob_lm, maxout=0):
         super().__init__()
-        if maxout:
-            raise _capi.RfnError("maxout=1 is not built")
         self.rnn_size, self.drop_prob_lm = rnn_size, drop_prob_lm
         self.att_feat_size, self.att_num, self.att_hid_size, self.maxout = att_feat_size, att_num, att_hid_size, maxout
-        self.h2h = nn.Linear(rnn_size, 4 * rnn_size)
-        self.z2h = nn.Linear(att_feat_size, 4 * rnn_size)
+        gw = (5 if maxout else 4) * rnn_size                   # :23-28
+        self.h2h = nn.Linear(rnn_size, gw)
+        self.z2h = nn.Linear(att_feat_size, gw)
         self.att_2_att_h = nn.Linear(att_feat_size, att_hid_size)
         self.h_2_att_h = nn.Linear(rnn_size, att_hid_size)
         self.att_h_2_out = nn.Linear(att_hid_size, 1)
@@ -287,8 +287,8 @@ class LSTMSoftAttentionNoInputCore(nn.Module):
     def forward(self, att_seq, mil_feats, matching_feats, state):
         pre_h, pre_c = _last_layer(state[0]), _last_layer(state[1])
         z = _attention(self, pre_h, att_seq)
-        G = linear([(pre_h, self.h2h), (z, self.z2h)], pre_h.shape[0], 4 * self.rnn_size)
-        next_h, next_c = lstm_cell(G, _f32c(pre_c))
+        G = linear([(pre_h, self.h2h), (z, self.z2h)], pre_h.shape[0], self.h2h.out_features)
+        next_h, next_c = lstm_cell(G, _f32c(pre_c), self.maxout)
         next_h = _dropout(next_h, self.drop_prob_lm, self.training)
         return next_h, (next_h.unsqueeze(0), next_c.unsqueeze(0))
 
@@ -412,7 +412,7 @@ class RecurrentFusionModel(nn.Module):
         self._dims = _capi.make_dims(list(zip(self.att_num, self.att_feat_size, self.fc_feat_size)), R,
                                      self.att_hid_size, self.input_encoding_size, self.vocab_size + 1,
                                      self.top_words_count, self.num_review_steps_0, self.num_review_steps,
-                                     self.seq_length)
+                                     self.seq_length, review_maxout=self.review_maxout, decoder_maxout=self.decoder_maxout)
         self._pcache = None
         self._wsobj = _Workspace()   # this model's scratch for the C ABI (grow-only; swapped by graphs.GraphedBeamSearch)
 

@@ -220,10 +220,10 @@ def _att_bwd(A, P, g, v_w, alpha, dz, dP, dg, dw, dwb, dA, rows, N, D, Ah, st):
                                            ptr(dw), ptr(dwb), ptr(dA), rows, N, D, Ah, 1, st), "rfn_attention_step_bwd_f32")
 
 
-def _cell(G, c_prev, mask, scale, h, c, h2, h3, rows, R, st):
-    check(lib().rfn_lstm_cell_drop_f32(ptr(G), ptr(c_prev), ptr(mask), float(scale), ptr(h), ptr(c), ptr(h2),
-                                       h2.stride(0) if h2 is not None else 0, ptr(h3), h3.stride(0) if h3 is not None else 0,
-                                       rows, R, st), "rfn_lstm_cell_drop_f32")
+def _cell(G, c_prev, mask, scale, h, c, h2, h3, rows, R, st, maxout=0):
+    check(lib().rfn_lstm_cell_ex_f32(ptr(G), ptr(c_prev), ptr(mask), float(scale), int(maxout), ptr(h), ptr(c), ptr(h2),
+                                     h2.stride(0) if h2 is not None else 0, ptr(h3), h3.stride(0) if h3 is not None else 0,
+                                     rows, R, st), "rfn_lstm_cell_ex_f32")
 
 
 def _sum(srcs, alpha, out, rows, R, st):
@@ -242,15 +242,15 @@ def _sum(srcs, alpha, out, rows, R, st):
     return out
 
 
-def _cell_bwd(G, c_prev, srcs, mask, scale, dc_next, dG, dc_prev, rows, R, st, scratch=None):
+def _cell_bwd(G, c_prev, srcs, mask, scale, dc_next, dG, dc_prev, rows, R, st, scratch=None, maxout=0):
     srcs = [s for s in srcs if s is not None]
     if len(srcs) > 8:      # more encoders than the kernel has source slots: pre-sum the tail
         _sum(srcs[7:], 1.0, scratch, rows, R, st)
         srcs = srcs[:7] + [scratch]
     ld = (C.c_int * max(1, len(srcs)))(*[t.stride(0) for t in srcs])
-    check(lib().rfn_lstm_cell_bwd_multi_f32(ptr(G), ptr(c_prev), len(srcs), ptr_array(srcs) if srcs else None, ld, ptr(mask),
-                                            float(scale), ptr(dc_next), ptr(dG), ptr(dc_prev), rows, R, st),
-          "rfn_lstm_cell_bwd_multi_f32")
+    check(lib().rfn_lstm_cell_bwd_ex_f32(ptr(G), ptr(c_prev), len(srcs), ptr_array(srcs) if srcs else None, ld, ptr(mask),
+                                         float(scale), int(maxout), ptr(dc_next), ptr(dG), ptr(dc_prev), rows, R, st),
+          "rfn_lstm_cell_bwd_ex_f32")
 
 
 def _cont(t):
@@ -473,7 +473,9 @@ class Stage2Fn(Function):
         z = [E(S1, rows, R, dtype=_f32, device=dev) for _ in range(J)]
         ar = _Arena(dev)
         ig = [ar.take(S1, rows, A) for _ in range(J)]
-        iG = ar.take(S1, rows, 4 * R)
+        GW = prm[0].shape[0]                       # 4R, or 5R with review_maxout
+        mo = 1 if GW == 5 * R else 0
+        iG = ar.take(S1, rows, GW)
         bufs = ar.build()
         g = [bufs[i] for i in ig]
         G = bufs[iG]
@@ -492,10 +494,10 @@ class Stage2Fn(Function):
             for j in range(J):
                 _after(main, pool.enc[j])
             _lin([hin] + [z[j][s] for j in range(J)], [p[0]] + [p[2 + 2 * j] for j in range(J)],
-                 [p[1]] + [p[3 + 2 * j] for j in range(J)], G[s], rows, 4 * R, True, sm)
+                 [p[1]] + [p[3 + 2 * j] for j in range(J)], G[s], rows, GW, True, sm)
             last = s == S1 - 1
             c_prev = cbar if s == 0 else Cs[s - 1]
-            _cell(G[s], c_prev, None, 1.0, hfin if last else None, cfin if last else Cs[s], TVc[:, s, :], None, rows, R, sm)
+            _cell(G[s], c_prev, None, 1.0, hfin if last else None, cfin if last else Cs[s], TVc[:, s, :], None, rows, R, sm, mo)
         mark("s2_fwd_end")
         ctx.J, ctx.S1 = J, S1
         ctx.save_for_backward(*TV, hbar, cbar, *prm, TVc, Cs, *Pb, *al, *z, *g, G)
@@ -522,7 +524,9 @@ class Stage2Fn(Function):
         sm = _sid(main)
         E = torch.empty
         dTVc = _cont(dTVc) if dTVc is not None else None
-        dG = E(S1, rows, 4 * R, dtype=_f32, device=dev)
+        GW = prm[0].shape[0]
+        mo = 1 if GW == 5 * R else 0
+        dG = E(S1, rows, GW, dtype=_f32, device=dev)
         dC = E(2, rows, R, dtype=_f32, device=dev)
         dP = [E(S1, rows * S0, A, dtype=_f32, device=dev) for _ in range(J)]
         dg = [E(S1, rows, A, dtype=_f32, device=dev) for _ in range(J)]
@@ -554,7 +558,7 @@ class Stage2Fn(Function):
                 srcs += [dhq[j][s + 1] for j in range(J)]
             c_prev = cbar if s == 0 else Cs[s - 1]
             dc_next = (_cont(dcfin) if dcfin is not None else None) if s == S1 - 1 else dC[(s + 1) & 1]
-            _cell_bwd(G[s], c_prev, srcs, None, 1.0, dc_next, dG[s], dC[s & 1], rows, R, sm, scratch)
+            _cell_bwd(G[s], c_prev, srcs, None, 1.0, dc_next, dG[s], dC[s & 1], rows, R, sm, scratch, mo)
             gs = [None] * per
             for j in range(J):
                 e, w = pool.enc[j], pool.wg[j]
@@ -624,21 +628,23 @@ class DecoderFn(Function):
         Cx = E(T, rows, R, dtype=_f32, device=dev)
         Z = E(T, rows, R, dtype=_f32, device=dev)
         al = E(T, rows, S1, dtype=_f32, device=dev)
-        G = E(T, rows, 4 * R, dtype=_f32, device=dev)
+        GW = Wi.shape[0]                           # 4R, or 5R with opt.maxout
+        mo = 1 if GW == 5 * R else 0
+        G = E(T, rows, GW, dtype=_f32, device=dev)
         g = torch.zeros(T, rows, A, dtype=_f32, device=dev)
         Hx[0].copy_(h0)
         mark("dec_fwd_begin")
         # hoisted: the x_t . i2h^T + b term of every step (one (T*rows)-row GEMM, side stream), att_2_att_h(TV_comb)
         _after(side, main)
-        _lin([X], [Wi], [bi], G.view(T * rows, 4 * R), T * rows, 4 * R, False, _sid(side))
+        _lin([X], [Wi], [bi], G.view(T * rows, GW), T * rows, GW, False, _sid(side))
         _lin([TVc.view(rows * S1, R)], [U_w], [U_b], Pdec, rows * S1, A, False, sm)
         _after(main, side)
         for t in range(T):
             _lin([Hx[t]], [Wh_w], [Wh_b], g[t], rows, A, True, sm)
             _att_fwd(TVc, Pdec, g[t], v_w, v_b, Z[t], al[t], rows, S1, R, A, sm)
-            _lin([Hx[t], Z[t]], [Whh, Wz], [bh, bz], G[t], rows, 4 * R, True, sm)
+            _lin([Hx[t], Z[t]], [Whh, Wz], [bh, bz], G[t], rows, GW, True, sm)
             _cell(G[t], c0 if t == 0 else Cx[t - 1], mask[t] if mask is not None else None, scale, Hx[t + 1], Cx[t], None, None,
-                  rows, R, sm)
+                  rows, R, sm, mo)
         mark("dec_fwd_loop_end")
         logits = E(T * rows, V, dtype=_f32, device=dev)
         _lin([Hx[1:].view(T * rows, R)], [Wl], [bl], logits, T * rows, V, False, sm)
@@ -685,7 +691,9 @@ class DecoderFn(Function):
         dWl = _dw(dlogits, Hx[1:].view(T * rows, R), sw)
         dbl = _colsum(dlogits, sw)
         Wcat = torch.cat([Whh, Wz], 1)                 # (4R, 2R): dG . [h2h | z2h] in one launch per step
-        dG = E(T, rows, 4 * R, dtype=_f32, device=dev)
+        GW = Wi.shape[0]
+        mo = 1 if GW == 5 * R else 0
+        dG = E(T, rows, GW, dtype=_f32, device=dev)
         dC = E(2, rows, R, dtype=_f32, device=dev)
         dP = E(T, rows * S1, A, dtype=_f32, device=dev)
         dg = E(T, rows, A, dtype=_f32, device=dev)
@@ -695,7 +703,7 @@ class DecoderFn(Function):
             if t < T - 1:
                 srcs += [dhz[t + 1][:, :R], dhq[t + 1]]
             _cell_bwd(G[t], c0 if t == 0 else Cx[t - 1], srcs, mask[t] if mask is not None else None, scale,
-                      None if t == T - 1 else dC[(t + 1) & 1], dG[t], dC[t & 1], rows, R, sm)
+                      None if t == T - 1 else dC[(t + 1) & 1], dG[t], dC[t & 1], rows, R, sm, None, mo)
             _bwd_x([dG[t]], [Wcat], dhz[t], rows, 2 * R, True, sm)
             _att_bwd(TVc, Pdec, g[t], v_w, al[t], dhz[t][:, R:], dP[t], dg[t], dwv[:A], dwv[A:], dTVc, rows, S1, R, A, sm)
             _bwd_x([dg[t]], [Wh_w], dhq[t], rows, R, True, sm)
@@ -705,7 +713,7 @@ class DecoderFn(Function):
         mark("dec_bwd_loop_end")
         # everything below is off the dependent chain: T-batched weight gradients, the embedding-side dX, the hoisted projection
         _after(w, main)
-        dG2 = dG.view(T * rows, 4 * R)
+        dG2 = dG.view(T * rows, GW)
         dX = E(T * rows, E_, dtype=_f32, device=dev)
         _bwd_x([dG2], [Wi], dX, T * rows, E_, False, sw)
         dPs = E(rows * S1, A, dtype=_f32, device=dev)      # sum over the steps of dP_t (P is loop invariant)

@@ -2,6 +2,7 @@
 reference, written by oracle/gen_golden.py), regenerate its weights/inputs from their seeds and
 verify them against the checksums stored beside the outputs."""
 import ast
+import dataclasses
 import os
 
 import numpy as np
@@ -18,6 +19,8 @@ CONFIGS = {
     "tiny_j2_eos_b": lambda: O.tiny_config(2),
     "tiny_j3_eos_a": lambda: O.tiny_config(3),
     "tiny_j3_eos_b": lambda: O.tiny_config(3),
+    "tiny_j2_maxout": lambda: dataclasses.replace(O.tiny_config(2), review_maxout=1, decoder_maxout=1),
+    "tiny_j3_maxout_dec": lambda: dataclasses.replace(O.tiny_config(3), decoder_maxout=1),
     "config1_n49": lambda: O.config1(49),
     "config1_n196_sharp": lambda: O.config1(196),
     "full_j5": lambda: O.RFNConfig(),

@@ -14,7 +14,7 @@ def opt_from_cfg(cfg: O.RFNConfig, **kw):
         vocab_size=cfg.vocab_size, input_encoding_size=cfg.input_encoding_size, rnn_size=cfg.rnn_size,
         seq_length=cfg.seq_length, num_review_steps=cfg.num_review_steps,
         num_review_steps_0=cfg.num_review_steps_0, top_words_count=cfg.top_words_count,
-        att_hid_size=cfg.att_hid_size, **kw)
+        att_hid_size=cfg.att_hid_size, review_maxout=cfg.review_maxout, maxout=cfg.decoder_maxout, **kw)
 
 
 def build_model(cfg, sd, **kw):

@@ -75,3 +75,35 @@ def test_fused_tape_rl_forward_loss_equals_per_op():
     assert torch.equal(out[True][1], out[False][1])
     assert abs(out[True][0] - out[False][0]) <= 1e-5 * max(1.0, abs(out[False][0]))
     _close(out[True][2], out[False][2], 1e-4)
+
+
+@pytest.mark.parametrize("review_maxout,decoder_maxout", [(1, 1), (0, 1), (1, 0)])
+@pytest.mark.parametrize("fused", [True, False], ids=["fused_tape", "per_op_tape"])
+def test_maxout_gradients_match_oracle(review_maxout, decoder_maxout, fused):
+    """opt.review_maxout / opt.maxout = 1 (5R-wide cells, in_transform = max of the last two R-blocks,
+    misc/LSTMSoftAttentionCore.py:25,89; misc/LSTMSoftMultiAttentionFeatArrayNoInputCore.py:25,60): loss and all gradients
+    against autograd through the oracle, whose maxout cells are pinned to the reference by the tiny_j2_maxout fixtures."""
+    import dataclasses
+    from recurrent_fusion_network_b200.criteria import ReviewNetEnsembleCriterion
+    cfg = dataclasses.replace(O.tiny_config(2), review_maxout=review_maxout, decoder_maxout=decoder_maxout)
+    sd = O.make_state_dict(cfg, seed=91, init_range=0.5, logit_scale=3.0)
+    rows = 5
+    fc, att = O.make_inputs(cfg, rows, seed=4)
+    labels, masks, top = O.make_labels(cfg, rows, seed=6)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    lp_o, rp_o = O.forward_xe(leaves, cfg, fc, att, labels)
+    want_loss = O.xe_loss(lp_o, labels[:, 1:], masks[:, 1:], rp_o, top, 10.0, 0.1)
+    want_loss.backward()
+    crit = ReviewNetEnsembleCriterion(SimpleNamespace(use_label_smoothing=1, label_smoothing_epsilon=0.1, use_cuda=1))
+    m = build_model(cfg, sd).train()
+    m.fused_tape = fused
+    lp, rp = m(cuda_list(fc), cuda_list(att), labels.cuda())
+    loss = crit(lp, labels[:, 1:].cuda(), masks[:, 1:].cuda(), rp, top.cuda(), 10.0)
+    loss.backward()
+    assert maxdiff(lp, lp_o) <= 2e-5
+    assert abs(float(loss.detach()) - float(want_loss.detach())) <= 1e-4 * max(1.0, abs(float(want_loss.detach())))
+    for k, p in m.named_parameters():
+        w = leaves[k].grad if leaves[k].grad is not None else torch.zeros_like(leaves[k])
+        g = p.grad if p.grad is not None else torch.zeros_like(p)
+        scale = float(w.abs().max()) + 1e-6
+        assert maxdiff(g, w) <= 2e-4 * scale + 1e-6, f"{k}: {maxdiff(g, w):.3g} vs scale {scale:.3g}"
