@@ -59,8 +59,8 @@ __device__ __forceinline__ void tc_epilogue_store(float (&acc)[COLS], float* sta
       const int n = nb + c;
       if (n + 3 < a.N) {
         float4 o = *reinterpret_cast<const float4*>(stage + r * LD + c);
-        if (atomic) {   // split-K partial tile
-          atomicAdd(yr + n, o.x); atomicAdd(yr + n + 1, o.y); atomicAdd(yr + n + 2, o.z); atomicAdd(yr + n + 3, o.w);
+        if (atomic) {   // split-K partial tile: one 16-byte vector reduction per lane instead of four scalar atomics
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(yr + n), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
           continue;
         }
         if (a.accumulate) {

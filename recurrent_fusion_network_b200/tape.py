@@ -380,6 +380,11 @@ class Stage1Fn(Function):
                 _after(pool.wg[j], main)
                 At[j] = _transpose(att[j].view(rows * N[j], D[j]), _sid(pool.wg[j]))
         mark("s1_bwd_begin")
+        # dU_{s,j} = dP_{s,j}^T . A_j shares A_j over the S0 steps: the steps' dP^T are stacked into one (S0*A, rows*N) operand and
+        # all S0 gradients of an encoder come from ONE GEMM with S0*A rows after the loop -- enough output tiles to fill the GPU
+        # without split-K, so it runs on the split-fp16 engine in modes 4 / 5 (the per-step form needs the 3xTF32 split-K kernel)
+        batch_dU = [At[j] is not None and (rows * N[j]) % 4 == 0 and S0 * A >= 256 for j in range(J)]
+        dPt = [E(S0 * A, At[j].shape[1], dtype=_f32, device=dev) if batch_dU[j] else None for j in range(J)]
         grads = [[None] * J for _ in range(S0)]
         big_dw = use_tc and rows >= 32 and 4 * R * J * R >= (1 << 21) and R % 4 == 0
         for s in range(S0 - 1, -1, -1):
@@ -412,19 +417,24 @@ class Stage1Fn(Function):
                 _bwd_x([dg[j][s]], [Wh_w], dhq[j][s], rows, R, True, st)
                 _bwd_x([dG[j][s]], [H2h_w], dHp[j][s], rows, J * R, True, st)
                 _after(w, e)
-                if At[j] is not None:
+                if batch_dU[j]:
+                    dU_w = None
+                    check(lib().rfn_transpose_f32(ptr(dP[j][s]), A, rows * N[j], A, ptr(dPt[j][s * A:(s + 1) * A]), dPt[j].shape[1], sw),
+                          "rfn_transpose_f32")
+                elif At[j] is not None:
                     dU_w = _dw_pre(dP[j][s], At[j], D[j], sw)
                 else:
                     dU_w = _dw(dP[j][s], att[j].view(rows * N[j], D[j]), sw)
                 check(lib().rfn_colsum_f32(ptr(dP[j][s]), A, rows * N[j], A, ptr(dUb[j][s]), 1, sw), "rfn_colsum_f32")
                 dWh_w = _dw(dg[j][s], h_in, sw)
                 dWh_b = _colsum(dg[j][s], sw)
-                grads[s][j] = (dU_w, dUb[j][s], dWh_w, dWh_b, dwv[j][s][:A].view(1, A), dwv[j][s][A:], dH2h_w, dH2h_b, dz2h_w,
-                               dz2h_b)
+                grads[s][j] = [dU_w, dUb[j][s], dWh_w, dWh_b, dwv[j][s][:A].view(1, A), dwv[j][s][A:], dH2h_w, dH2h_b, dz2h_w,
+                               dz2h_b]
             for j in range(J):
                 _after(main, pool.enc[j])
             if GRAD_SINK is not None:      # this step's 10 J weight gradients are final once the wgrad streams get there
-                GRAD_SINK.early([(P[s][j][k], grads[s][j][k]) for j in range(J) for k in range(10)], pool.wg + pool.enc)
+                GRAD_SINK.early([(P[s][j][k], grads[s][j][k]) for j in range(J) for k in range(10) if grads[s][j][k] is not None],
+                                pool.wg + pool.enc)
         # h0_j is both the initial hidden and the initial cell state (misc/RecurrentFusionModel.py:333-343)
         dh0 = []
         for j in range(J):
@@ -432,6 +442,29 @@ class Stage1Fn(Function):
             _sum([dhq[j][0], dC[j][0]] + [dHp[k][0][:, j * R:(j + 1) * R] for k in range(J)], 1.0, out, rows, R, sm)
             dh0.append(out)
         mark("s1_bwd_chain_end")
+        mode = lib().rfn_get_gemm_mode()
+        for j in range(J):
+            if not batch_dU[j]:
+                continue
+            sw = _sid(pool.wg[j])
+            Kc = rows * N[j]
+            dU_all = E(S0 * A, D[j], dtype=_f32, device=dev)
+            if mode >= 4 and D[j] >= 256:
+                bf16 = 1 if mode == 5 else 0
+                xs = _split(dPt[j][:, :Kc], sw, bf16)
+                ws = _split(At[j][:, :Kc], sw, bf16)
+                ks = (C.c_int * 1)(Kc)
+                check(lib().rfn_linear_split(bf16, 1, ptr(xs), ptr(ws), ks, ptr_array([None]), ptr(dU_all), D[j], S0 * A, D[j], 0, sw),
+                      "rfn_linear_split")
+            else:
+                ld = (C.c_int * 1)(dPt[j].shape[1])
+                ks = (C.c_int * 1)(dPt[j].shape[1])
+                check(lib().rfn_linear_f32(1, ptr_array([dPt[j]]), ld, ptr_array([At[j]]), ks, ptr_array([None]), ptr(dU_all), D[j],
+                                           S0 * A, D[j], 0, sw), "rfn_linear_f32")
+            for s in range(S0):
+                grads[s][j][0] = dU_all[s * A:(s + 1) * A]
+        if GRAD_SINK is not None and any(batch_dU):
+            GRAD_SINK.early([(P[s][j][0], grads[s][j][0]) for s in range(S0) for j in range(J) if batch_dU[j]], pool.wg)
         for j in range(J):
             _after(main, pool.wg[j])
         if GRAD_SINK is not None:
