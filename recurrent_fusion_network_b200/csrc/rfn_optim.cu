@@ -37,20 +37,55 @@ adam_kernel(AdamChunk c, float lr, float beta1, float beta2, float eps, float wd
   float* __restrict__ m = c.m[t];
   float* __restrict__ v = c.v[t];
   const float step_size = lr / bc1;
+  const float ob1 = 1.f - beta1, ob2 = 1.f - beta2;
+  auto upd = [&](float gk, float pk, float& mk, float& vk) -> float {
+    gk *= gscale;                                              // 1 / world: the mean of data-parallel gradient sums
+    if (clip > 0.f) gk = fminf(fmaxf(gk, -clip), clip);      // clip_gradient: element-wise clamp
+    gk = fmaf(wd, pk, gk);                                     // L2 weight decay added to the gradient
+    mk = beta1 * mk + ob1 * gk;
+    vk = beta2 * vk + ob2 * gk * gk;
+    const float denom = sqrtf(vk) / bc2_sqrt + eps;
+    return pk - step_size * (mk / denom);
+  };
+  // 16-byte accesses when the four streams allow it (every torch allocation and every arena view of the tape does): the
+  // scalar version moved 13.7 GB at 4.9 TB/s, 75 % of the measured HBM rate
+  const bool vec = ((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)m) | ((uintptr_t)v)) & 15) == 0;
+  if (vec) {
+#pragma unroll
+    for (int i = 0; i < AD_BLOCK_ELEMS / (256 * 4); ++i) {
+      const long long k = base + ((long long)i * 256 + threadIdx.x) * 4;
+      if (k + 3 < n) {
+        const float4 g4 = *reinterpret_cast<const float4*>(g + k);
+        const float4 p4 = *reinterpret_cast<const float4*>(p + k);
+        float4 m4 = *reinterpret_cast<const float4*>(m + k);
+        float4 v4 = *reinterpret_cast<const float4*>(v + k);
+        float4 o;
+        o.x = upd(g4.x, p4.x, m4.x, v4.x);
+        o.y = upd(g4.y, p4.y, m4.y, v4.y);
+        o.z = upd(g4.z, p4.z, m4.z, v4.z);
+        o.w = upd(g4.w, p4.w, m4.w, v4.w);
+        *reinterpret_cast<float4*>(m + k) = m4;
+        *reinterpret_cast<float4*>(v + k) = v4;
+        *reinterpret_cast<float4*>(p + k) = o;
+      } else {
+        for (long long e = k; e < n && e < k + 4; ++e) {
+          float mk = m[e], vk = v[e];
+          p[e] = upd(g[e], p[e], mk, vk);
+          m[e] = mk;
+          v[e] = vk;
+        }
+      }
+    }
+    return;
+  }
 #pragma unroll 4
   for (int i = threadIdx.x; i < AD_BLOCK_ELEMS; i += 256) {
     const long long k = base + i;
     if (k >= n) break;
-    float gk = g[k] * gscale;                                  // 1 / world: the mean of data-parallel gradient sums
-    if (clip > 0.f) gk = fminf(fmaxf(gk, -clip), clip);      // clip_gradient: element-wise clamp
-    const float pk = p[k];
-    gk = fmaf(wd, pk, gk);                                     // L2 weight decay added to the gradient
-    const float mk = beta1 * m[k] + (1.f - beta1) * gk;
-    const float vk = beta2 * v[k] + (1.f - beta2) * gk * gk;
+    float mk = m[k], vk = v[k];
+    p[k] = upd(g[k], p[k], mk, vk);
     m[k] = mk;
     v[k] = vk;
-    const float denom = sqrtf(vk) / bc2_sqrt + eps;
-    p[k] = pk - step_size * (mk / denom);
   }
 }
 
