@@ -169,16 +169,24 @@ def rl_criterion(crit, input, seq, reward, logprobs_all, entropy_reg, top_pred, 
 
 
 
-def _decode_tokens(model, TVc, h, c, uniforms, temperature):
+def _decode_tokens(model, TVc, h, c, uniforms, temperature, second_workspace=False):
     """Tokens of a greedy (uniforms None) or multinomial decode from given stage-2 outputs, all on the device and without
-    gradients (rfn_decode_sample): seq (rows, L) int64 with finished rows zeroed (:647), T on the device."""
+    gradients (rfn_decode_sample): seq (rows, L) int64 with finished rows zeroed (:647), T on the device.
+    second_workspace: scratch of its own, for a decode that runs side by side with another one of the same model."""
     import ctypes as C
     from ._capi import check, lib, ptr, stream
     rows, dev, L = h.shape[0], h.device, model.seq_length
     seq = torch.empty(rows, L, dtype=torch.int64, device=dev)
     slp = torch.empty(rows, L, dtype=torch.float32, device=dev)
     dT = torch.zeros(1, dtype=torch.int32, device=dev)
-    ws = model._ws(rows, rows, dev)
+    if second_workspace:
+        from .model import _Workspace
+        wsb = model.__dict__.get("_wsobj_b")
+        if wsb is None:
+            wsb = model.__dict__["_wsobj_b"] = _Workspace()
+        ws = wsb.get(lib().rfn_workspace_bytes(C.byref(model._dims), rows, rows), dev)
+    else:
+        ws = model._ws(rows, rows, dev)
     check(lib().rfn_decode_sample(C.byref(model._dims), model._params(), ptr(TVc), ptr(h), ptr(c), rows, ptr(uniforms),
                                   float(temperature), ptr(seq), ptr(slp), None, ptr(dT), ptr(ws), ws.numel(), stream()),
           "rfn_decode_sample")
@@ -218,11 +226,22 @@ def rl_forward_loss(model, crit, fc_feats, att_feats, uniforms, reward_fn, top_t
         from ._capi import lib
         prev = lib().rfn_get_splitk()
         lib().rfn_set_splitk(1)      # a few hundred rows: split-K GEMMs fill the GPU (the tokens are samples and a baseline)
+        # no split-weight cache for these decodes: the weights change with every optimizer step, and a cache built while a
+        # CUDA graph of the iteration is captured would be replayed stale
+        saved_wc, model.weight_cache = model.weight_cache, False
         try:
-            seq, _ = _decode_tokens(model, TVd, hd, cd, uniforms.to(TVd.device).float().contiguous(), temperature)
-            greedy, _ = _decode_tokens(model, TVd, hd, cd, None, 1.0)
+            # the two decodes are independent chains of small kernels (a few hundred rows): side by side on two streams
+            main = torch.cuda.current_stream()
+            side = tape._Streams.get(TVd.device, 1).enc[0]
+            u = uniforms.to(TVd.device).float().contiguous()
+            tape._after(side, main)
+            seq, _ = _decode_tokens(model, TVd, hd, cd, u, temperature)
+            with torch.cuda.stream(side):
+                greedy, _ = _decode_tokens(model, TVd, hd, cd, None, 1.0, second_workspace=True)
+            tape._after(main, side)
         finally:
             lib().rfn_set_splitk(prev)
+            model.weight_cache = saved_wc
         tape.mark("rl_decodes_end")
         reward = reward_fn(seq, greedy)
         tape.mark("rl_reward_end")
@@ -314,7 +333,10 @@ class GraphedRLStep:
         self.loss = self.seq = self.greedy = self.reward = None
         from .model import _Workspace
         self._ws = _Workspace()            # the no-tape decodes' scratch: private, the graph holds raw pointers into it
+        self._ws_b = _Workspace()
         saved_ws, model._wsobj = model._wsobj, self._ws
+        saved_ws_b = model.__dict__.get("_wsobj_b")
+        model.__dict__["_wsobj_b"] = self._ws_b
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -344,6 +366,7 @@ class GraphedRLStep:
                 tape.mark("opt_end")
         finally:
             model._wsobj = saved_ws
+            model.__dict__["_wsobj_b"] = saved_ws_b
 
     def _reward(self, seq, greedy):
         from . import reward as RW
