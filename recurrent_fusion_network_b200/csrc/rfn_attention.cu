@@ -123,32 +123,6 @@ attention_step_kernel(const float* __restrict__ A, const float* __restrict__ P,
   const int per = (nvec + gridDim.y - 1) / gridDim.y;
   const int v0 = blockIdx.y * per;
   const int v1 = min(nvec, v0 + per);
-  if (A16 && (D & 7) == 0 && (lda16 & 7) == 0 && gridDim.y == 1) {
-    // 8 bf16 (one 16-byte load) per thread per location, four locations in flight: the same 64 bytes per thread as the fp32
-    // path keeps in flight (with 8-byte loads the bf16 stream reached 89 % of the HBM peak against 99 % for fp32)
-    const uint4* Ar16 = reinterpret_cast<const uint4*>(A16 + (size_t)ra * N * lda16);
-    const int pitch = lda16 >> 3;
-    for (int v = tid; v < (D >> 3); v += ATT_THREADS) {
-      float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), hi = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-      for (int n = 0; n < N; ++n) {
-        const uint4 q = __ldg(Ar16 + (size_t)n * pitch + v);
-        const float a0 = s_e[n];
-        lo.x = fmaf(a0, __uint_as_float(q.x << 16), lo.x);
-        lo.y = fmaf(a0, __uint_as_float(q.x & 0xffff0000u), lo.y);
-        lo.z = fmaf(a0, __uint_as_float(q.y << 16), lo.z);
-        lo.w = fmaf(a0, __uint_as_float(q.y & 0xffff0000u), lo.w);
-        hi.x = fmaf(a0, __uint_as_float(q.z << 16), hi.x);
-        hi.y = fmaf(a0, __uint_as_float(q.z & 0xffff0000u), hi.y);
-        hi.z = fmaf(a0, __uint_as_float(q.w << 16), hi.z);
-        hi.w = fmaf(a0, __uint_as_float(q.w & 0xffff0000u), hi.w);
-      }
-      float* zo = z + (size_t)r * ldz + v * 8;
-      *reinterpret_cast<float4*>(zo) = lo;
-      *reinterpret_cast<float4*>(zo + 4) = hi;
-    }
-    return;
-  }
   if (A16) {
     const uint2* Ar16 = reinterpret_cast<const uint2*>(A16 + (size_t)ra * N * lda16);
     const int pitch = lda16 >> 2;   // uint2 (4 bf16) per feature row
