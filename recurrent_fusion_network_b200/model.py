@@ -364,6 +364,9 @@ class RecurrentFusionModel(nn.Module):
     #: training only, with dedup_rows = g > 1: the feature tensors passed in hold ONE row per image (what
     #: ingest.FeatureIngest ships over PCIe) while labels hold g consecutive rows per image
     unique_feature_rows = False
+    #: training only: gradient-enabled calls go through the hand-scheduled multi-stream tape (tape.py) whenever stage-1 /
+    #: stage-2 dropout is off and (for forward()) scheduled sampling is off; False selects the op-by-op tape (autograd.py)
+    fused_tape = True
 
     def __init__(self, opt):
         super().__init__()
