@@ -111,6 +111,11 @@ int rfn_get_splitk(void);
  * 2 = persistent 2-CTA clusters looping over tiles with the epilogue overlapped (3xTF32 mode). */
 int rfn_set_tc_cluster(int on);
 int rfn_get_tc_cluster(void);
+/* Split-fp16 / bf16 engine (modes 4 / 5): CTAs per cluster.  2 (default) = one tcgen05 cta_group::2 pair per 256 x 256 tile;
+ * 4 = two pairs on vertically adjacent tiles that share the W tile through TMA multicast (each CTA fetches half of its W rows):
+ * 25 % less L2 -> shared-memory traffic per MMA, for GEMMs with more than 256 rows. */
+int rfn_set_h3_cluster(int ctas);
+int rfn_get_h3_cluster(void);
 /* Debugging aid: device buffer receiving 8 clock64() stamps per CTA of the 2-CTA GEMM kernel
  * (start, init done, first MMA, last MMA, last drain, epilogue done, exit); NULL switches it off. */
 int rfn_debug_set_timeline(long long* d_buf, int epilogue_kind /* -1 all, 0 store, 1 score, 2 vocab */);

@@ -62,6 +62,8 @@ _SIGNATURES = {
     "rfn_get_splitk": (_i, []),
     "rfn_set_tc_cluster": (_i, [_i]),
     "rfn_get_tc_cluster": (_i, []),
+    "rfn_set_h3_cluster": (_i, [_i]),
+    "rfn_get_h3_cluster": (_i, []),
     "rfn_debug_set_timeline": (_i, [_vp, _i]),
     "rfn_set_concurrency": (_i, [_i]),
     "rfn_set_pdl": (_i, [_i]),
@@ -167,6 +169,9 @@ def lib() -> C.CDLL:
         pdl = os.environ.get("RFN_PDL")
         if pdl is not None:
             check(_lib.rfn_set_pdl(int(pdl)), "rfn_set_pdl")
+        h3c = os.environ.get("RFN_H3_CLUSTER")
+        if h3c is not None:
+            check(_lib.rfn_set_h3_cluster(int(h3c)), "rfn_set_h3_cluster")
         cl = os.environ.get("RFN_TC_CLUSTER")
         if cl is not None:
             check(_lib.rfn_set_tc_cluster(int(cl)), "rfn_set_tc_cluster")

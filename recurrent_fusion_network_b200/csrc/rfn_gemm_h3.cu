@@ -14,6 +14,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <atomic>
 
 #include "rfn_h3.cuh"
 #include "rfn_tc_ptx.cuh"
@@ -32,6 +33,7 @@ constexpr int H3_EPI_BYTES = 8 * H3_GSLOTS * 128 * 4;   // 20 KB: g rows (score)
 struct H3Args {
   CUtensorMap tm_x[3][2];
   CUtensorMap tm_w[3][2];
+  CUtensorMap tm_w64[3][2];   // the same W pieces with a 64-row box (4-CTA clusters: each pair loads half a W tile and multicasts it)
   int K[3];
   const float* bias[3];
   int nsrc;
@@ -75,6 +77,17 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
       "}" ::"r"(bar), "r"(parity)
       : "memory");
 }
+// TMA load delivered to the same shared-memory offset (and mbarrier offset) of every CTA in `mask`
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mask(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
 // instruction descriptor, kind::f16: D fp32, A/B fp16 (format 0) or bf16 (format 1), both K-major
 __host__ __device__ constexpr uint32_t make_idesc_16(int bm, int bn, int bf16) {
   return (1u << 4) | ((uint32_t)bf16 << 7) | ((uint32_t)bf16 << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(bm >> 4) << 24);
@@ -89,7 +102,11 @@ struct H3Cfg {
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + H3_EPI_BYTES + 4096 + 1024;
 };
 
-template <int EPI, int NPROD>
+// CL = 2: one CTA pair per cluster.  CL = 4: two pairs that work on vertically adjacent 256-row tiles of the SAME 256 output
+// columns and share the W tile: each CTA loads half of its 128 W rows and multicasts it to its counterpart in the other pair
+// (L2 -> SM traffic per CTA and k-block: x 128 rows + W 64 rows instead of 128 + 128).  The stage is released only when both
+// pairs' MMAs have retired (the empty barriers count two commits, multicast to all four CTAs).
+template <int EPI, int NPROD, int CL>
 __global__ void __launch_bounds__(H3_THREADS, 1) gemm_h3_kernel(const __grid_constant__ H3Args a, int n_tiles, int total_tiles,
                                                                 int bf16) {
   using Cfg = H3Cfg<NPROD>;
@@ -110,10 +127,15 @@ __global__ void __launch_bounds__(H3_THREADS, 1) gemm_h3_kernel(const __grid_con
   float* s_cs = s_wv + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t crank = cluster_ctarank();
+  const uint32_t rank = crank & 1u;                 // rank inside the CTA pair
+  const uint32_t pr = (CL == 4) ? (crank >> 1) : 0u;  // which pair of the cluster
+  const uint32_t lead = pr * 2u;                    // cluster rank of this pair's leader CTA
   const bool leader = (rank == 0);
-  const int cluster = blockIdx.x >> 1;
-  const int n_clusters = gridDim.x >> 1;
+  const int cluster = blockIdx.x / CL;
+  const int n_clusters = gridDim.x / CL;
+  constexpr int MP = CL / 2;                        // 256-row tiles per cluster step
+  const uint16_t pair_mask = (uint16_t)(3u << (2u * pr));
   pdl_trigger();
 
   int total_kb = 0;
@@ -126,7 +148,7 @@ __global__ void __launch_bounds__(H3_THREADS, 1) gemm_h3_kernel(const __grid_con
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(&full[s]), 1);
       mbar_init(smem_u32(&pfull[s]), 1);
-      mbar_init(smem_u32(&empty[s]), 1);
+      mbar_init(smem_u32(&empty[s]), MP);   // one commit per pair of the cluster
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&cfull[b]), 1);
@@ -150,7 +172,7 @@ __global__ void __launch_bounds__(H3_THREADS, 1) gemm_h3_kernel(const __grid_con
       int it = 0;
       for (int tile = cluster; tile < total_tiles; tile += n_clusters) {
         const int n0 = (tile % n_tiles) * H3_BN + (int)rank * H3_BH;
-        const int m0 = (tile / n_tiles) * (2 * TC_BM) + (int)rank * TC_BM;
+        const int m0 = ((tile / n_tiles) * MP + (int)pr) * (2 * TC_BM) + (int)rank * TC_BM;
         for (int s = 0; s < a.nsrc; ++s) {
           const int nkb = (a.K[s] + H3_BK - 1) / H3_BK;
           for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -163,7 +185,11 @@ __global__ void __launch_bounds__(H3_THREADS, 1) gemm_h3_kernel(const __grid_con
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
               tma_load_2d(&a.tm_x[s][p], fb, stage + p * H3_TILE, kb * H3_BK, m0);
-              tma_load_2d(&a.tm_w[s][p], fb, stage + (NP + p) * H3_TILE, kb * H3_BK, n0);
+              if (CL == 4)   // my half (64 rows) of this CTA's 128 W rows, to me and to the same-rank CTA of the other pair
+                tma_load_2d_mc(&a.tm_w64[s][p], fb, stage + (NP + p) * H3_TILE + pr * (H3_TILE / 2), kb * H3_BK, n0 + (int)pr * (H3_BH / 2),
+                               (uint16_t)((1u << rank) | (1u << (rank + 2u))));
+              else
+                tma_load_2d(&a.tm_w[s][p], fb, stage + (NP + p) * H3_TILE, kb * H3_BK, n0);
             }
           }
         }
@@ -203,8 +229,8 @@ __global__ void __launch_bounds__(H3_THREADS, 1) gemm_h3_kernel(const __grid_con
                 umma2_bf16(td, dx0 + (uint64_t)(k * 2), dw1 + (uint64_t)(k * 2), idesc, 1u);
               }
             }
-            umma2_commit(smem_u32(&empty[st]));
-            if (chunk_end) umma2_commit(smem_u32(&cfull[b]));
+            umma2_commit_mask(smem_u32(&empty[st]), CL == 4 ? (uint16_t)0xF : (uint16_t)0x3);
+            if (chunk_end) umma2_commit_mask(smem_u32(&cfull[b]), pair_mask);
           }
           __syncwarp();
           if (chunk_end) ++gc;
@@ -218,7 +244,7 @@ __global__ void __launch_bounds__(H3_THREADS, 1) gemm_h3_kernel(const __grid_con
           const int st = it % STAGES;
           const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
           mbar_wait(smem_u32(&full[st]), ph);
-          if (lane == 0) mbar_arrive_remote_release(smem_u32(&pfull[st]), 0);
+          if (lane == 0) mbar_arrive_remote_release(smem_u32(&pfull[st]), lead);
           __syncwarp();
         }
       }
@@ -236,7 +262,7 @@ __global__ void __launch_bounds__(H3_THREADS, 1) gemm_h3_kernel(const __grid_con
     int gc = 0;
     for (int tile = cluster; tile < total_tiles; tile += n_clusters) {
       const int n0 = (tile % n_tiles) * H3_BN;
-      const int m0 = (tile / n_tiles) * (2 * TC_BM) + (int)rank * TC_BM;
+      const int m0 = ((tile / n_tiles) * MP + (int)pr) * (2 * TC_BM) + (int)rank * TC_BM;
       const int m = m0 + wq * 32 + lane;
       const float rs = (a.row_inv && m < a.M) ? __ldg(a.row_inv + m) : 1.f;
 #pragma unroll
@@ -255,7 +281,7 @@ __global__ void __launch_bounds__(H3_THREADS, 1) gemm_h3_kernel(const __grid_con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (leader) mbar_arrive(smem_u32(&drained[b])); else mbar_arrive_remote(smem_u32(&drained[b]), 0);
+          if (leader) mbar_arrive(smem_u32(&drained[b])); else mbar_arrive_remote(smem_u32(&drained[b]), lead);
         }
       }
       // ----- epilogue of this tile (the MMA warp is already working on the next one) -----
@@ -522,7 +548,7 @@ static EncodeTiledFn16 get_encode16() {
 }
 
 // 2-D 16-bit tensor map over a row-major (rows, K) matrix with pitch ld elements: box = 64 elements (128 bytes) x 128 rows
-static int make_map16(CUtensorMap* tm, const void* base, int rows, int K, int ld, bool bf16) {
+static int make_map16(CUtensorMap* tm, const void* base, int rows, int K, int ld, bool bf16, int box_rows = TC_BM) {
   EncodeTiledFn16 enc = get_encode16();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -530,7 +556,7 @@ static int make_map16(CUtensorMap* tm, const void* base, int rows, int K, int ld
   }
   cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)H3_BK, (cuuint32_t)TC_BM};
+  cuuint32_t box[2] = {(cuuint32_t)H3_BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -562,44 +588,62 @@ void h3_view(const void* buf, int rows, const int* K, int nsrc, bool bf16, H3Ope
   }
 }
 
-template <int EPI, int NPROD>
+// rfn_set_h3_cluster(4): 4-CTA clusters (two pairs sharing the W tile by TMA multicast) for GEMMs with at least two 256-row tiles
+static std::atomic<int> g_h3_cluster{2};
+
+template <int EPI, int NPROD, int CL>
 static int launch_h3(const H3Args& t, int bf16, cudaStream_t st) {
   using Cfg = H3Cfg<NPROD>;
   static bool configured = false;
   static int n_sm = 0;
+  static int max_clusters = 0;
   if (!configured) {
-    RFN_CUDA(cudaFuncSetAttribute(gemm_h3_kernel<EPI, NPROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    RFN_CUDA(cudaFuncSetAttribute(gemm_h3_kernel<EPI, NPROD, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     int dev = 0;
     RFN_CUDA(cudaGetDevice(&dev));
     RFN_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    max_clusters = n_sm / CL;
+    if (CL > 2) {   // how many 4-CTA clusters of this kernel the GPCs can hold at once
+      cudaLaunchConfig_t q{};
+      q.gridDim = dim3((unsigned)(CL * (n_sm / CL)), 1, 1);
+      q.blockDim = dim3(H3_THREADS, 1, 1);
+      q.dynamicSmemBytes = Cfg::SMEM;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = CL; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      q.attrs = qa; q.numAttrs = 1;
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, gemm_h3_kernel<EPI, NPROD, CL>, &q) == cudaSuccess && nc > 0) max_clusters = nc;
+      else cudaGetLastError();
+    }
     configured = true;
   }
   const int n_tiles = (t.N + H3_BN - 1) / H3_BN;
-  const int n_pairs = (t.M + 2 * TC_BM - 1) / (2 * TC_BM);
+  const int n_pairs = ((t.M + 2 * TC_BM - 1) / (2 * TC_BM) + CL / 2 - 1) / (CL / 2);   // cluster steps along M
   const int total = n_tiles * n_pairs;
   // as few clusters as finish in the same number of waves: a launch of 314 tiles takes 5 waves on 74 cluster slots and on 63,
   // and the 22 SMs it then leaves alone run the other encoder streams' kernels meanwhile (matters for small shards)
-  int slots = n_sm / 2;
+  int slots = max_clusters;
   // short launches issued side by side with other encoder streams (concurrency_hint() > 1) take half of the cluster slots:
   // 314 tiles are 5 waves on 74 slots but 9 on 37, i.e. 4.5 waves' worth of the machine, with a sibling launch in the other half
   if (concurrency_hint() > 1 && total <= 6 * slots) slots = (slots + 1) / 2;
   const int waves = (total + slots - 1) / slots;
   const int clusters = (total + waves - 1) / waves;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(2 * clusters), 1, 1);
+  cfg.gridDim = dim3((unsigned)(CL * clusters), 1, 1);
   cfg.blockDim = dim3(H3_THREADS, 1, 1);
   cfg.dynamicSmemBytes = Cfg::SMEM;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.x = CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  RFN_CUDA(cudaLaunchKernelEx(&cfg, gemm_h3_kernel<EPI, NPROD>, t, n_tiles, total, bf16));
+  RFN_CUDA(cudaLaunchKernelEx(&cfg, gemm_h3_kernel<EPI, NPROD, CL>, t, n_tiles, total, bf16));
   RFN_LAUNCH_CHECK();
   count_engine(bf16 ? ENG_BF16 : ENG_H3);
   return RFN_OK;
@@ -612,12 +656,14 @@ int gemm_h3(const H3Gemm& a, cudaStream_t st) {
   H3Args t{};
   t.nsrc = a.nsrc;
   const int np = a.bf16 ? 1 : 2;
+  const bool cl4 = g_h3_cluster.load() == 4 && a.M > 2 * TC_BM;
   for (int s = 0; s < a.nsrc; ++s) {
     const H3Src& g = a.src[s];
     RFN_CHECK_ARG(g.x.p0 && g.w.p0 && (a.bf16 || (g.x.p1 && g.w.p1)) && g.x.ld % 8 == 0 && g.w.ld % 8 == 0, "gemm_h3: bad operand %d", s);
     for (int p = 0; p < np; ++p) {
       RFN_TRY(make_map16(&t.tm_x[s][p], p ? g.x.p1 : g.x.p0, a.M, g.K, g.x.ld, a.bf16));
       RFN_TRY(make_map16(&t.tm_w[s][p], p ? g.w.p1 : g.w.p0, a.N, g.K, g.w.ld, a.bf16));
+      if (cl4) RFN_TRY(make_map16(&t.tm_w64[s][p], p ? g.w.p1 : g.w.p0, a.N, g.K, g.w.ld, a.bf16, TC_BM / 2));
     }
     t.K[s] = g.K;
     t.bias[s] = g.bias;
@@ -627,14 +673,24 @@ int gemm_h3(const H3Gemm& a, cudaStream_t st) {
   t.y = a.y; t.ldy = a.ldy; t.M = a.M; t.N = a.N; t.accumulate = a.accumulate;
   t.g = a.g; t.ldg = a.ldg; t.wv = a.wv; t.score = a.score; t.natt = a.natt > 0 ? a.natt : 1;
   t.st_max = a.st_max; t.st_sum = a.st_sum; t.st_val = a.st_val; t.st_idx = a.st_idx; t.ktop = a.ktop;
-  if (a.bf16) {
-    if (a.epi == 0) return launch_h3<0, 1>(t, 1, st);
-    if (a.epi == 1) return launch_h3<1, 1>(t, 1, st);
-    return launch_h3<2, 1>(t, 1, st);
+  if (cl4) {
+    if (a.bf16) {
+      if (a.epi == 0) return launch_h3<0, 1, 4>(t, 1, st);
+      if (a.epi == 1) return launch_h3<1, 1, 4>(t, 1, st);
+      return launch_h3<2, 1, 4>(t, 1, st);
+    }
+    if (a.epi == 0) return launch_h3<0, 3, 4>(t, 0, st);
+    if (a.epi == 1) return launch_h3<1, 3, 4>(t, 0, st);
+    return launch_h3<2, 3, 4>(t, 0, st);
   }
-  if (a.epi == 0) return launch_h3<0, 3>(t, 0, st);
-  if (a.epi == 1) return launch_h3<1, 3>(t, 0, st);
-  return launch_h3<2, 3>(t, 0, st);
+  if (a.bf16) {
+    if (a.epi == 0) return launch_h3<0, 1, 2>(t, 1, st);
+    if (a.epi == 1) return launch_h3<1, 1, 2>(t, 1, st);
+    return launch_h3<2, 1, 2>(t, 1, st);
+  }
+  if (a.epi == 0) return launch_h3<0, 3, 2>(t, 0, st);
+  if (a.epi == 1) return launch_h3<1, 3, 2>(t, 0, st);
+  return launch_h3<2, 3, 2>(t, 0, st);
 }
 
 size_t h3_auto_bytes(const GemmArgs& a, bool bf16) {
@@ -661,6 +717,13 @@ int gemm_h3_auto(const GemmArgs& a, bool bf16, void* scratch, size_t scratch_byt
 }
 
 }  // namespace rfn
+
+extern "C" int rfn_set_h3_cluster(int ctas) {
+  RFN_CHECK_ARG(ctas == 2 || ctas == 4, "rfn_set_h3_cluster: 2 or 4 CTAs per cluster");
+  rfn::g_h3_cluster.store(ctas);
+  return RFN_OK;
+}
+extern "C" int rfn_get_h3_cluster(void) { return rfn::g_h3_cluster.load(); }
 
 extern "C" size_t rfn_split_bytes(int rows, int n_src, const int* K, int bf16) {
   if (rows < 0 || n_src < 1 || n_src > 3 || !K) return 0;

@@ -350,3 +350,25 @@ def test_split_operator_api_and_bf16():
             rowmax = x.abs().max(dim=1, keepdim=True)[0].double()
             assert float(((rec - x.double()).abs() / rowmax).max()) <= 2.0 ** -21
             assert float((p0.abs().max(dim=1)[0]).min()) >= 2.0 ** 14 - 16 and float(p0.abs().max()) <= 2.0 ** 15
+
+
+@pytest.mark.parametrize("engine", [4, 5])
+def test_h3_four_cta_clusters_are_bit_identical(engine):
+    """rfn_set_h3_cluster(4): two CTA pairs per cluster share the W tile by TMA multicast (each CTA loads half of its W rows for
+    both pairs).  Same MMA sequence per tile, so the output must equal the 2-CTA form bit for bit -- including a last cluster
+    step whose second pair lies entirely beyond M.  (Measured: no faster, profiles/r2_h3_cluster4_multicast.log; default 2.)"""
+    from recurrent_fusion_network_b200._capi import check, lib
+    g = torch.Generator().manual_seed(5)
+    try:
+        for M, N, Ks in [(1000, 2048, [2560, 1280]), (520, 512, [2048]), (777, 256, [72]), (1300, 768, [512, 512, 512])]:
+            xs = cuda_list([torch.randn(M, k, generator=g) for k in Ks])
+            ws = cuda_list([(torch.rand(N, k, generator=g) * 2 - 1) * 0.1 for k in Ks])
+            bs = cuda_list([torch.randn(N, generator=g) for _ in Ks])
+            check(lib().rfn_set_h3_cluster(2))
+            y2 = _linear_engine(engine, xs, ws, bs, M, N)
+            check(lib().rfn_set_h3_cluster(4))
+            y4 = _linear_engine(engine, xs, ws, bs, M, N)
+            torch.cuda.synchronize()
+            assert torch.equal(y2, y4), (engine, M, N, Ks, maxdiff(y2, y4))
+    finally:
+        check(lib().rfn_set_h3_cluster(2))
