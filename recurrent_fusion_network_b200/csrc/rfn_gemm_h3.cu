@@ -5,8 +5,9 @@
 //   warp 0      TMA producer: per 64-element k-block the two pieces of this CTA's 128 rows of x and of its 128 rows of W
 //               (4 x 16 KB, SWIZZLE_128B) into a 3-stage ring; runs ahead through the tiles
 //   warp 1      leader CTA: MMA issuer, 4 x {x0.w0} + 4 x {x1.w0, x0.w1} tcgen05.mma.cta_group::2.kind::f16 per k-block into
-//               one of two TMEM accumulators (alternating every CH k-blocks, across tiles); peer CTA: relay that tells the
-//               leader when the peer's half of a stage has landed
+//               one of two TMEM accumulators (alternating every CH k-blocks, across tiles).  Both CTAs' TMA loads count
+//               their bytes on the LEADER's full barrier (cp.async.bulk.tensor.cta_group::2), so the issuer waits on one
+//               barrier per stage; the peer's warp 1 is idle (4-CTA clusters keep the relay of the first design)
 //   warps 4..11 drain (tcgen05.ld of finished chunks into round-to-nearest fp32 registers) + epilogue of the tile
 //               (scaled store / fused attention score / fused vocabulary statistics) while the MMA warp works ahead
 #include <cuda.h>
@@ -84,6 +85,18 @@ __device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* tm, uint32_t b
       ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
       : "memory");
 }
+// TMA load issued by either CTA of a pair whose completion bytes are counted on the LEADER's mbarrier (`bar` = the barrier's
+// shared-memory address with the peer bit cleared): the leader's MMA warp then waits on ONE barrier per stage and no thread
+// has to relay "my half has landed" across the pair (that relay was an mbarrier.arrive.release.cluster per k-block, which
+// compiles to MEMBAR.ALL.GPU + ERRBAR, with a CCTL.IVALL on the acquiring side: ~1.2 k cycles per k-block, the bound of the
+// single-pass bf16 kernel, profiles/r2_h3_bf16_score_ncu.txt)
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
 __device__ __forceinline__ void umma2_commit_mask(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
                : "memory");
@@ -112,12 +125,13 @@ __global__ void __launch_bounds__(H3_THREADS, 1) gemm_h3_kernel(const __grid_con
   using Cfg = H3Cfg<NPROD>;
   constexpr int STAGES = Cfg::STAGES, NP = Cfg::NP, CH = Cfg::CH;
   constexpr int COLS = H3_BN / 2;
+  constexpr bool DIRECT = (CL == 2);   // both CTAs' TMA bytes land on the leader's full barrier (no relay warp)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES;
   uint64_t* bars = (uint64_t*)(epi_smem + H3_EPI_BYTES);
-  uint64_t* full = bars;                   // local: this CTA's TMA landed
-  uint64_t* pfull = bars + STAGES;         // leader: the peer's TMA landed (relayed)
+  uint64_t* full = bars;                   // DIRECT: leader only, both CTAs' TMA landed; else local: this CTA's TMA landed
+  uint64_t* pfull = bars + STAGES;         // !DIRECT: leader: the peer's TMA landed (relayed)
   uint64_t* empty = bars + 2 * STAGES;     // both: stage free (tcgen05.commit multicast)
   uint64_t* cfull = bars + 3 * STAGES;     // [2] both: accumulator chunk complete
   uint64_t* drained = cfull + 2;           // [2] leader: both halves drained
@@ -179,17 +193,25 @@ __global__ void __launch_bounds__(H3_THREADS, 1) gemm_h3_kernel(const __grid_con
             const int st = it % STAGES;
             const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
             mbar_wait(smem_u32(&empty[st]), ph ^ 1u);
-            const uint32_t fb = smem_u32(&full[st]);
-            mbar_arrive_expect_tx(fb, (uint32_t)Cfg::STAGE_BYTES);
             const uint32_t stage = smem_u32(smem + st * Cfg::STAGE_BYTES);
+            if (DIRECT) {
+              const uint32_t fb = smem_u32(&full[st]) & PEER_BIT_MASK;   // the leader's barrier, from either CTA
+              if (leader) mbar_arrive_expect_tx(fb, (uint32_t)(2 * Cfg::STAGE_BYTES));
 #pragma unroll
-            for (int p = 0; p < NP; ++p) {
-              tma_load_2d(&a.tm_x[s][p], fb, stage + p * H3_TILE, kb * H3_BK, m0);
-              if (CL == 4)   // my half (64 rows) of this CTA's 128 W rows, to me and to the same-rank CTA of the other pair
+              for (int p = 0; p < NP; ++p) {
+                tma_load_2d_pair(&a.tm_x[s][p], fb, stage + p * H3_TILE, kb * H3_BK, m0);
+                tma_load_2d_pair(&a.tm_w[s][p], fb, stage + (NP + p) * H3_TILE, kb * H3_BK, n0);
+              }
+            } else {
+              const uint32_t fb = smem_u32(&full[st]);
+              mbar_arrive_expect_tx(fb, (uint32_t)Cfg::STAGE_BYTES);
+#pragma unroll
+              for (int p = 0; p < NP; ++p) {
+                tma_load_2d(&a.tm_x[s][p], fb, stage + p * H3_TILE, kb * H3_BK, m0);
+                // my half (64 rows) of this CTA's 128 W rows, to me and to the same-rank CTA of the other pair
                 tma_load_2d_mc(&a.tm_w64[s][p], fb, stage + (NP + p) * H3_TILE + pr * (H3_TILE / 2), kb * H3_BK, n0 + (int)pr * (H3_BH / 2),
                                (uint16_t)((1u << rank) | (1u << (rank + 2u))));
-              else
-                tma_load_2d(&a.tm_w[s][p], fb, stage + (NP + p) * H3_TILE, kb * H3_BK, n0);
+              }
             }
           }
         }
@@ -209,7 +231,7 @@ __global__ void __launch_bounds__(H3_THREADS, 1) gemm_h3_kernel(const __grid_con
           const int b = gc & 1;
           if (chunk_start && gc >= 2) mbar_wait(smem_u32(&drained[b]), (uint32_t)((gc >> 1) - 1) & 1u);
           mbar_wait(smem_u32(&full[st]), ph);
-          mbar_wait_cluster(smem_u32(&pfull[st]), ph);
+          if (!DIRECT) mbar_wait_cluster(smem_u32(&pfull[st]), ph);
           tc_fence_after();
           if (lane == 0) {
             const uint32_t td = tmem_base + (uint32_t)(b * H3_BN);
@@ -236,8 +258,8 @@ __global__ void __launch_bounds__(H3_THREADS, 1) gemm_h3_kernel(const __grid_con
           if (chunk_end) ++gc;
         }
       }
-    } else {
-      // ===================== relay: the peer's half of the stage has landed =====================
+    } else if (!DIRECT) {
+      // ===================== relay (4-CTA clusters only): the peer's half of the stage has landed =====================
       int it = 0;
       for (int tile = cluster; tile < total_tiles; tile += n_clusters) {
         for (int kb = 0; kb < total_kb; ++kb, ++it) {
