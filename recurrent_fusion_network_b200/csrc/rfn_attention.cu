@@ -6,6 +6,8 @@
 // materialises three).
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "rfn_internal.cuh"
 
 namespace rfn {
@@ -25,13 +27,14 @@ constexpr int ATT_THREADS = 256;
 
 // A16 != nullptr (engine mode 5): the feature map is read as the bf16 copy the GEMM engine already made (row pitch lda16
 // elements), half the bytes of the fp32 map; everything else (scores, softmax, accumulation) stays fp32
+template <bool BF16, int WIDE = 0>
 __global__ void __launch_bounds__(ATT_THREADS)
 attention_step_kernel(const float* __restrict__ A, const float* __restrict__ P,
                       const float* __restrict__ g, const float* __restrict__ w,
                       const float* __restrict__ d_wb, float* __restrict__ z, int ldz,
                       float* __restrict__ alpha, int N, int D, int Ah, int div,
                       const float* __restrict__ scores, int nslices, size_t slice_stride,
-                      const __nv_bfloat16* __restrict__ A16 = nullptr, int lda16 = 0) {
+                      const __nv_bfloat16* __restrict__ A16, int lda16) {
   extern __shared__ __align__(16) float smem[];
   float* s_g = smem;            // Ah
   float* s_w = smem + Ah;       // Ah
@@ -123,13 +126,83 @@ attention_step_kernel(const float* __restrict__ A, const float* __restrict__ P,
   const int per = (nvec + gridDim.y - 1) / gridDim.y;
   const int v0 = blockIdx.y * per;
   const int v1 = min(nvec, v0 + per);
-  if (A16) {
+  if (BF16 && WIDE && ((D | lda16) & 7) == 0) {
+    // 16-byte loads (8 bf16 per thread and location), four in flight per thread (64 bytes, what the fp32 path keeps in flight), the
+    // row pointer advanced by adds, four softmax weights per LDS.128: 1.1 instructions per feature byte against 1.6 for the
+    // 8-byte form below -- at the power-capped clocks of a long decode (1.3 GHz) the 8-byte form was bound by instruction issue,
+    // not by HBM (ncu: 32 % issue-active at 56 % of the DRAM peak)
+    const int nvec8 = D >> 3;
+    const int per8 = (nvec8 + gridDim.y - 1) / gridDim.y;
+    const int w0 = blockIdx.y * per8;
+    const int w1 = min(nvec8, w0 + per8);
+    const size_t rowb = (size_t)lda16 * 2;
+    const char* base = reinterpret_cast<const char*>(A16 + (size_t)ra * N * lda16);
+    for (int v = w0 + tid; v < w1; v += ATT_THREADS) {
+      const char* p = base + (size_t)v * 16;
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      auto fma8 = [&](float a0, const uint4& q) {
+        acc[0] = fmaf(a0, __uint_as_float(q.x << 16), acc[0]);
+        acc[1] = fmaf(a0, __uint_as_float(q.x & 0xffff0000u), acc[1]);
+        acc[2] = fmaf(a0, __uint_as_float(q.y << 16), acc[2]);
+        acc[3] = fmaf(a0, __uint_as_float(q.y & 0xffff0000u), acc[3]);
+        acc[4] = fmaf(a0, __uint_as_float(q.z << 16), acc[4]);
+        acc[5] = fmaf(a0, __uint_as_float(q.z & 0xffff0000u), acc[5]);
+        acc[6] = fmaf(a0, __uint_as_float(q.w << 16), acc[6]);
+        acc[7] = fmaf(a0, __uint_as_float(q.w & 0xffff0000u), acc[7]);
+      };
+      int n = 0;
+      if (WIDE == 2) {   // eight 16-byte loads in flight: short feature maps (N = 49 / 64) are bound by the latency of their few batches
+        for (; n + 8 <= N; n += 8) {
+          uint4 q[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) q[i] = __ldg(reinterpret_cast<const uint4*>(p + i * rowb));
+          p += 8 * rowb;
+          const float4 a4 = *reinterpret_cast<const float4*>(s_e + n);
+          const float4 b4 = *reinterpret_cast<const float4*>(s_e + n + 4);
+          fma8(a4.x, q[0]); fma8(a4.y, q[1]); fma8(a4.z, q[2]); fma8(a4.w, q[3]);
+          fma8(b4.x, q[4]); fma8(b4.y, q[5]); fma8(b4.z, q[6]); fma8(b4.w, q[7]);
+        }
+      }
+      for (; n + 4 <= N; n += 4) {
+        const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(p));
+        const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(p + rowb));
+        const uint4 q2 = __ldg(reinterpret_cast<const uint4*>(p + 2 * rowb));
+        const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(p + 3 * rowb));
+        p += 4 * rowb;
+        const float4 a4 = *reinterpret_cast<const float4*>(s_e + n);
+        fma8(a4.x, q0); fma8(a4.y, q1); fma8(a4.z, q2); fma8(a4.w, q3);
+      }
+      for (; n < N; ++n, p += rowb) fma8(s_e[n], __ldg(reinterpret_cast<const uint4*>(p)));
+      float4* zo = reinterpret_cast<float4*>(z + (size_t)r * ldz + v * 8);
+      zo[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      zo[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+    return;
+  }
+  if (BF16) {
     const uint2* Ar16 = reinterpret_cast<const uint2*>(A16 + (size_t)ra * N * lda16);
     const int pitch = lda16 >> 2;   // uint2 (4 bf16) per feature row
     for (int v = v0 + tid; v < v1; v += ATT_THREADS) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-      for (int n = 0; n < N; ++n) {
+      // 8 loads of 8 bytes issued before their first use = the 64 bytes per thread the fp32 path keeps in flight (4 x 16);
+      // a plain `#pragma unroll 8` is scheduled by ptxas as two groups of 4 loads (checked in the SASS)
+      int n = 0;
+      for (; n + 8 <= N; n += 8) {
+        uint2 q[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) q[i] = __ldg(Ar16 + (size_t)(n + i) * pitch + v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float a0 = s_e[n + i];
+          acc.x = fmaf(a0, __uint_as_float(q[i].x << 16), acc.x);
+          acc.y = fmaf(a0, __uint_as_float(q[i].x & 0xffff0000u), acc.y);
+          acc.z = fmaf(a0, __uint_as_float(q[i].y << 16), acc.z);
+          acc.w = fmaf(a0, __uint_as_float(q[i].y & 0xffff0000u), acc.w);
+        }
+      }
+      for (; n < N; ++n) {
         const uint2 q = __ldg(Ar16 + (size_t)n * pitch + v);
         const float a0 = s_e[n];
         acc.x = fmaf(a0, __uint_as_float(q.x << 16), acc.x);
@@ -179,8 +252,8 @@ int attention_step(const float* A, const float* P, const float* g, const float* 
   const size_t smem = (size_t)(2 * Ah + N) * sizeof(float);
   RFN_CHECK_ARG(smem <= 200 * 1024, "attention_step: N=%d Ah=%d exceed shared memory", N, Ah);
   if (smem > 48 * 1024)
-    RFN_CUDA(cudaFuncSetAttribute(attention_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  RFN_CUDA(launch_pdl(attention_step_kernel, dim3(rows, dsplit), dim3(ATT_THREADS), smem, st, A, P, g, w, d_wb, z, ldz, alpha, N, D, Ah,
+    RFN_CUDA(cudaFuncSetAttribute(attention_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RFN_CUDA(launch_pdl(attention_step_kernel<false>, dim3(rows, dsplit), dim3(ATT_THREADS), smem, st, A, P, g, w, d_wb, z, ldz, alpha, N, D, Ah,
                       div, (const float*)nullptr, 0, (size_t)0, (const __nv_bfloat16*)nullptr, 0));
   RFN_LAUNCH_CHECK();
   return RFN_OK;
@@ -197,11 +270,24 @@ int attention_from_scores(const float* A, const float* scores, int nslices, cons
   while (rows * dsplit < 296 && dsplit < 8 && (D / 4) / (dsplit * 2) >= 64) dsplit *= 2;
   const size_t smem = (size_t)N * sizeof(float);
   RFN_CHECK_ARG(smem <= 200 * 1024, "attention_from_scores: N=%d exceeds shared memory", N);
-  if (smem > 48 * 1024)
-    RFN_CUDA(cudaFuncSetAttribute(attention_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  RFN_CUDA(launch_pdl(attention_step_kernel, dim3(rows, dsplit), dim3(ATT_THREADS), smem, st, A, (const float*)nullptr,
-                      (const float*)nullptr, (const float*)nullptr, d_wb, z, ldz, alpha, N, D, 0, div, scores, nslices,
-                      (size_t)rows * N, (const __nv_bfloat16*)A_bf16, lda_bf16));
+  if (A_bf16) {
+    // RFN_ATT_BF16_WIDE (experiment switch, read once): 0 = 8-byte loads, 1 = 16-byte loads, 2 (default) = 16-byte loads in batches
+    // of eight locations and no second pass over a handful of leftover columns (D = 2208 is 276 16-byte vectors: two CTAs of
+    // 138 instead of 256 + 20).  Measured inside the bench on one box (profiles/r2_attention_bf16_variants.txt): 4.2 / 5.2 / 6.2 TB/s
+    static const int wide = [] { const char* e = getenv("RFN_ATT_BF16_WIDE"); return e ? atoi(e) : 2; }();
+    auto kern = wide == 2 ? attention_step_kernel<true, 2> : wide == 1 ? attention_step_kernel<true, 1> : attention_step_kernel<true, 0>;
+    if (wide == 2 && D % 8 == 0 && (D / 8) / dsplit > ATT_THREADS && (D / 8) / dsplit < 2 * ATT_THREADS) dsplit *= 2;
+    if (smem > 48 * 1024) RFN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RFN_CUDA(launch_pdl(kern, dim3(rows, dsplit), dim3(ATT_THREADS), smem, st, A, (const float*)nullptr,
+                        (const float*)nullptr, (const float*)nullptr, d_wb, z, ldz, alpha, N, D, 0, div, scores, nslices,
+                        (size_t)rows * N, (const __nv_bfloat16*)A_bf16, lda_bf16));
+  } else {
+    if (smem > 48 * 1024)
+      RFN_CUDA(cudaFuncSetAttribute(attention_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RFN_CUDA(launch_pdl(attention_step_kernel<false>, dim3(rows, dsplit), dim3(ATT_THREADS), smem, st, A, (const float*)nullptr,
+                        (const float*)nullptr, (const float*)nullptr, d_wb, z, ldz, alpha, N, D, 0, div, scores, nslices,
+                        (size_t)rows * N, (const __nv_bfloat16*)nullptr, 0));
+  }
   RFN_LAUNCH_CHECK();
   return RFN_OK;
 }
