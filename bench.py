@@ -276,10 +276,12 @@ def run_ours(args):
                          launches=g_n, avg_launch_ms=round(g_ms / max(1, g_n), 4), share_of_step=shares.get("gemm_att2att_stage1"),
                          peak_source=peaks["source"] + ", dense bf16 sustained; this engine computes in " + args_dtype(mode))
         roof_attn = dict(kernel="attention_step_stage1", bound="hbm", achieved=round(gbs, 1), peak=peaks["hbm"], unit="GB/s",
-                         frac=round(gbs / peaks["hbm"], 4), traffic=(1.657e9 if mode != 5 else None),
+                         frac=round(gbs / peaks["hbm"], 4), traffic=(1.657e9 if mode != 5 else 0.840e9),
                          traffic_note=("ncu capture of one launch (resnet encoder, 1024 images): 1.648 GB read + 0.011 GB written "
                                        "vs 1.644 GB algorithmic (A read once); profiles/r2_attention_step_ncu.txt" if mode != 5 else
-                                       "no ncu capture of the bf16-feature variant"), launches=a_n,
+                                       "ncu capture of one launch (resnet encoder, 1024 images, bf16 features): 0.825 GB read + 0.015 GB "
+                                       "written vs 0.822 GB algorithmic (bf16 A read once); profiles/r2_final_attention_bf16_ncu.txt"),
+                         launches=a_n,
                          avg_launch_ms=round(a_ms / max(1, a_n), 4), share_of_step=shares.get("attention_step_stage1"),
                          peak_source=peaks["source"])
         return roof_gemm, roof_attn, shares, g_ms, a_ms
