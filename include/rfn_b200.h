@@ -13,8 +13,8 @@
  *     path: rfn_linear_f32_engine with engines 3 / 4 / 5 (an engine-test entry) takes its operand
  *     scratch from the stream-ordered pool (cudaMallocAsync / cudaFreeAsync on `stream`);
  *   - process-wide state the library DOES keep (all of it configuration or lazily created handles,
- *     none of it data): the engine selection (rfn_set_gemm_mode, rfn_set_tc_cluster,
- *     rfn_set_concurrency), per-device side streams + events for the encoder fork / join, the
+ *     none of it data): the engine selection (rfn_set_gemm_mode, rfn_set_tc_cluster, rfn_set_h3_cluster,
+ *     rfn_set_att_bf16_variant, rfn_set_pdl, rfn_set_splitk, rfn_set_concurrency), per-device side streams + events for the encoder fork / join, the
  *     kernels' one-time cudaFuncSetAttribute flags, the launch / engine counters and the optional
  *     profile records; the error string is thread-local.  Calls on different streams from different
  *     host threads are safe as long as they do not share a workspace; the engine selection is global;
@@ -116,6 +116,11 @@ int rfn_get_tc_cluster(void);
  * 25 % less L2 -> shared-memory traffic per MMA, for GEMMs with more than 256 rows. */
 int rfn_set_h3_cluster(int ctas);
 int rfn_get_h3_cluster(void);
+/* Engine mode 5: load scheme of the attention context sum over the bf16 feature copy (z = sum_n a_n A_n,
+ * misc/AttentionModelCore.py:45-47).  0 = 8-byte loads, 1 = 16-byte loads, 2 (default) = 16-byte loads in batches of eight
+ * locations with D split across CTAs instead of a pass over a few leftover columns.  Same results in all three. */
+int rfn_set_att_bf16_variant(int variant);
+int rfn_get_att_bf16_variant(void);
 /* Debugging aid: device buffer receiving 8 clock64() stamps per CTA of the 2-CTA GEMM kernel
  * (start, init done, first MMA, last MMA, last drain, epilogue done, exit); NULL switches it off. */
 int rfn_debug_set_timeline(long long* d_buf, int epilogue_kind /* -1 all, 0 store, 1 score, 2 vocab */);

@@ -64,6 +64,8 @@ _SIGNATURES = {
     "rfn_get_tc_cluster": (_i, []),
     "rfn_set_h3_cluster": (_i, [_i]),
     "rfn_get_h3_cluster": (_i, []),
+    "rfn_set_att_bf16_variant": (_i, [_i]),
+    "rfn_get_att_bf16_variant": (_i, []),
     "rfn_debug_set_timeline": (_i, [_vp, _i]),
     "rfn_set_concurrency": (_i, [_i]),
     "rfn_set_pdl": (_i, [_i]),
@@ -172,6 +174,9 @@ def lib() -> C.CDLL:
         h3c = os.environ.get("RFN_H3_CLUSTER")
         if h3c is not None:
             check(_lib.rfn_set_h3_cluster(int(h3c)), "rfn_set_h3_cluster")
+        aw = os.environ.get("RFN_ATT_BF16_WIDE")
+        if aw is not None:
+            check(_lib.rfn_set_att_bf16_variant(int(aw)), "rfn_set_att_bf16_variant")
         cl = os.environ.get("RFN_TC_CLUSTER")
         if cl is not None:
             check(_lib.rfn_set_tc_cluster(int(cl)), "rfn_set_tc_cluster")

@@ -6,7 +6,7 @@
 // materialises three).
 #include <cuda_bf16.h>
 
-#include <cstdlib>
+#include <atomic>
 
 #include "rfn_internal.cuh"
 
@@ -24,6 +24,7 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 constexpr int ATT_THREADS = 256;
+static std::atomic<int> g_att_bf16_variant{2};
 
 // A16 != nullptr (engine mode 5): the feature map is read as the bf16 copy the GEMM engine already made (row pitch lda16
 // elements), half the bytes of the fp32 map; everything else (scores, softmax, accumulation) stays fp32
@@ -271,10 +272,10 @@ int attention_from_scores(const float* A, const float* scores, int nslices, cons
   const size_t smem = (size_t)N * sizeof(float);
   RFN_CHECK_ARG(smem <= 200 * 1024, "attention_from_scores: N=%d exceeds shared memory", N);
   if (A_bf16) {
-    // RFN_ATT_BF16_WIDE (experiment switch, read once): 0 = 8-byte loads, 1 = 16-byte loads, 2 (default) = 16-byte loads in batches
-    // of eight locations and no second pass over a handful of leftover columns (D = 2208 is 276 16-byte vectors: two CTAs of
-    // 138 instead of 256 + 20).  Measured inside the bench on one box (profiles/r2_attention_bf16_variants.txt): 4.2 / 5.2 / 6.2 TB/s
-    static const int wide = [] { const char* e = getenv("RFN_ATT_BF16_WIDE"); return e ? atoi(e) : 2; }();
+    // rfn_set_att_bf16_variant: 0 = 8-byte loads, 1 = 16-byte loads, 2 (default) = 16-byte loads in batches of eight locations and
+    // no second pass over a handful of leftover columns (D = 2208 is 276 16-byte vectors: two CTAs of 138 instead of 256 + 20).
+    // Measured inside the bench on one box (profiles/r2_attention_bf16_variants.txt): 4.2 / 5.2 / 6.2 TB/s
+    const int wide = g_att_bf16_variant.load();
     auto kern = wide == 2 ? attention_step_kernel<true, 2> : wide == 1 ? attention_step_kernel<true, 1> : attention_step_kernel<true, 0>;
     if (wide == 2 && D % 8 == 0 && (D / 8) / dsplit > ATT_THREADS && (D / 8) / dsplit < 2 * ATT_THREADS) dsplit *= 2;
     if (smem > 48 * 1024) RFN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -293,6 +294,13 @@ int attention_from_scores(const float* A, const float* scores, int nslices, cons
 }
 
 }  // namespace rfn
+
+extern "C" int rfn_set_att_bf16_variant(int variant) {
+  RFN_CHECK_ARG(variant >= 0 && variant <= 2, "rfn_set_att_bf16_variant: 0, 1 or 2");
+  rfn::g_att_bf16_variant.store(variant);
+  return RFN_OK;
+}
+extern "C" int rfn_get_att_bf16_variant(void) { return rfn::g_att_bf16_variant.load(); }
 
 extern "C" int rfn_attention_step_f32(const float* A, const float* P, const float* g, const float* w,
                                       const float* d_wb, float* z, int ldz, float* alpha, int rows,
