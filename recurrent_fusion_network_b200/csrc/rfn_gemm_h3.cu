@@ -711,6 +711,8 @@ int gemm_h3(const H3Gemm& a, cudaStream_t st) {
   ProfScope prof__(a.epi == 2 ? TAG_GEMM_LOGIT : TAG_GEMM_OTHER, st);
   RFN_CHECK_ARG(a.nsrc >= 1 && a.nsrc <= 3 && h3_shape_ok(a.M, a.N), "gemm_h3: needs 1..3 sources and M, N >= 256 (M=%d N=%d)", a.M, a.N);
   RFN_CHECK_ARG(a.epi != 0 || (a.N % 4 == 0 && a.ldy % 4 == 0 && ((uintptr_t)a.y % 16) == 0), "gemm_h3: y must be 16-byte aligned, N %% 4 == 0");
+  RFN_CHECK_ARG(a.epi != 2 || (a.ktop >= 1 && a.st_max && a.st_sum && a.st_val && a.st_idx),
+                "gemm_h3: the vocabulary epilogue needs k >= 1 and its four statistics buffers");
   H3Args t{};
   t.nsrc = a.nsrc;
   const int np = a.bf16 ? 1 : 2;
