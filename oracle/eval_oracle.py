@@ -8,10 +8,12 @@ the model oracle (oracle/rfnet_oracle.py, itself pinned bit-for-bit against the 
   eval_ensemble         eval_utils.py:387-719  beam search over the logit-mean ensemble, 'log_prob' = masked sum of seqLogprobs
   eval_ensemble_greedy  eval_utils.py:729-975  greedy search over the logit-mean ensemble
 
-The reference's own functions cannot be executed: their ensemble code calls get_thought_vectors / one_time_step with stale
-signatures and reads loader keys that do not exist, and language_eval needs the Java scorers.  Parity of this
-restatement is therefore pinned through the MODEL oracle (every number it produces comes from functions that are) and by
-review of the cited lines; DESIGN.md lists it as 'restated, control flow unpinned'."""
+Pin: eval_split is checked against the REFERENCE's own eval_split, executed from its source text on the reference model
+(oracle/gen_golden_eval.py; fixture tests/golden/eval_split_cases.json: prediction lists equal, loss difference 0).  The two
+ensemble drivers cannot be executed: they call get_thought_vectors / one_time_step with stale signatures and read loader keys
+that do not exist, and language_eval needs the Java scorers; their restatement is pinned through the MODEL
+oracle only (every number it produces comes from functions that are) and by review of the cited lines -- DESIGN.md lists the
+ensemble drivers as 'restated, control flow unpinned'."""
 import numpy as np
 import torch
 

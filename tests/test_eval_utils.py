@@ -104,10 +104,11 @@ def test_eval_ensemble_matches_ensemble_beam():
 
 # ---- against the restated oracle of the reference's drivers (oracle/eval_oracle.py) ---------------------------------
 @pytest.mark.gpu
-@pytest.mark.parametrize("beam_size,val_images_use,n_images,batch", [(3, 7, 7, 3), (1, 4, 7, 3), (3, -1, 5, 2), (1, 100, 5, 2)])
+@pytest.mark.parametrize("beam_size,val_images_use,n_images,batch", [(3, 7, 7, 3), (1, 4, 7, 3), (3, -1, 5, 2), (1, 100, 5, 2), (3, 2, 6, 4)])
 def test_eval_split_matches_reference_driver_oracle(beam_size, val_images_use, n_images, batch):
     """Mean loss, the prediction list (ids, captions, what gets popped) and both break conditions of eval_utils.py:66-265,
-    incl. the quirk that val_images_use = -1 stops after the first batch (`n >= -1`)."""
+    incl. the quirk that val_images_use = -1 stops after the first batch (`n >= -1`).  The oracle's results for these very cases
+    are pinned against the reference's own eval_split (tests/golden/eval_split_cases.json, oracle/gen_golden_eval.py)."""
     from oracle import eval_oracle as EO
     from recurrent_fusion_network_b200 import eval_utils as EU
     from recurrent_fusion_network_b200.criteria import ReviewNetEnsembleCriterion
@@ -122,6 +123,11 @@ def test_eval_split_matches_reference_driver_oracle(beam_size, val_images_use, n
     want_loss, want_preds = EO.eval_split(sd, cfg, FakeLoader(cfg, n_images, batch, 2, seed=3), kw)
     assert preds == want_preds
     assert abs(loss - want_loss) <= 1e-4 * max(1.0, abs(want_loss))
+    import json, os
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "eval_split_cases.json")))
+    ref = [c for c in fx["cases"] if (c["beam_size"], c["val_images_use"], c["n_images"], c["batch"]) == (beam_size, val_images_use, n_images, batch)]
+    assert len(ref) == 1 and preds == ref[0]["predictions"]            # the REFERENCE driver's own output
+    assert abs(loss - ref[0]["loss"]) <= 1e-4 * max(1.0, abs(ref[0]["loss"]))
 
 
 @pytest.mark.gpu

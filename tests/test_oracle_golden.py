@@ -88,3 +88,21 @@ def test_beam_merge_edge_cases():
     # all beams ended -> None
     seq[1] = 0
     assert O.beam_merge(b, 3, L, ys, ix, seq, lp, sm, done) is None
+
+
+def test_eval_split_oracle_reproduces_reference_driver_fixture():
+    """oracle/eval_oracle.eval_split against the return values of the REFERENCE's own eval_split (eval_utils.py:66-265), run from
+    its source text by oracle/gen_golden_eval.py on the reference model: prediction lists (ids, captions, what gets popped, both
+    break conditions, the val_images_use = -1 quirk) equal, mean loss within 2e-6."""
+    import json
+    import os
+    from oracle import eval_oracle as EO
+    from tests.test_eval_utils import FakeLoader
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "eval_split_cases.json")))
+    cfg = O.tiny_config(2)
+    sd = O.make_state_dict(cfg, seed=fx["weights_seed"], init_range=0.5, logit_scale=3.0, eos_bias=0.8)
+    for c in fx["cases"]:
+        kw = {"eval_split": "val", "val_images_use": c["val_images_use"], "beam_size": c["beam_size"], "reason_weight": 10}
+        loss, preds = EO.eval_split(sd, cfg, FakeLoader(cfg, c["n_images"], c["batch"], fx["seq_per_img"], seed=fx["loader_seed"]), kw)
+        assert preds == c["predictions"], c
+        assert abs(loss - c["loss"]) <= 2e-6 * max(1.0, abs(c["loss"])), (loss, c["loss"])
