@@ -14,7 +14,8 @@ follows the dataloader.DataLoader protocol the driver uses (reset_iterator / get
 seq_per_img, bounds with it_pos_now / it_max / wrapped).  What is stored is the REFERENCE's return value (mean loss and the
 prediction list); the oracle restatement must reproduce it: prediction lists equal, loss within 2e-6.
 
-eval_ensemble / eval_ensemble_greedy cannot be pinned this way: they call the model with stale signatures."""
+eval_ensemble / eval_ensemble_greedy cannot be run this way: they call the model with stale signatures and read loader keys that do
+not exist.  What CAN be pinned is the ensemble STEP they share (ensemble_step_case below)."""
 from __future__ import annotations
 
 import contextlib
@@ -97,5 +98,66 @@ def main():
     print("wrote", path)
 
 
+def ensemble_step_case():
+    """The ensemble step hook model_ensemble_feat_array_one_step (eval_utils.py:268-290), executed from the reference's source
+    text on three reference models.  The hook calls model.one_time_step with a stale six-argument signature; a
+    signature shim forwards (xt, fc, thought_vectors, mil, matching, state) to the model's own four-argument method -- the
+    arithmetic (per-model step, running sum of the logits, division, log_softmax) is entirely the reference's.  Two consecutive
+    steps are compared with the oracle's ensemble step (one_time_step per model, log_softmax(sum(logits) / M))."""
+    mod, opts, _ = import_reference()
+    ref_eval = import_reference_eval_utils()
+    cfg = O.tiny_config(2)
+    seeds = (1250, 1251, 1252)
+    sds = [O.make_state_dict(cfg, seed=s, init_range=0.5, logit_scale=3.0, eos_bias=0.8) for s in seeds]
+    models = []
+    for sd in sds:
+        m, _ = build_reference_model(mod, opts, cfg)
+        m.load_state_dict(sd)
+        models.append(m)
+
+    class Shim:
+        def __init__(self, m):
+            self.m = m
+
+        def one_time_step(self, xt, fc, tv, mil, matching, state):
+            return self.m.one_time_step(xt, fc, tv, state)
+
+    rows = 5
+    fc, att = O.make_inputs(cfg, rows, seed=9)
+    worst = 0.0
+    ref_lps = []
+    with torch.no_grad():
+        r_tv, r_st, o_tv, o_st = [], [], [], []
+        for m, sd in zip(models, sds):
+            tv, _, st = m.get_thought_vectors(fc, att, m.get_init_state(fc))
+            r_tv.append(tv); r_st.append(st)
+            tvo, _, sto = O.get_thought_vectors(sd, cfg, att, O.get_init_state(sd, cfg, fc))
+            o_tv.append(tvo); o_st.append(sto)
+        tok = torch.zeros(rows, dtype=torch.int64)
+        for step in range(2):
+            xt_list = [m.embed(tok) for m in models]
+            _, r_st, r_lp = ref_eval.model_ensemble_feat_array_one_step([Shim(m) for m in models], xt_list, fc, att, None, None,
+                                                                        r_st, r_tv, "recurrent_fusion_model")
+            logits = []
+            for k, sd in enumerate(sds):
+                lg, o_st[k] = O.one_time_step(sd, sd["embed.weight"][tok], o_tv[k], o_st[k])
+                logits.append(lg)
+            o_lp = torch.log_softmax(sum(logits) / len(sds), dim=1)
+            d = float((r_lp - o_lp).abs().max())
+            ds = max(float((a[0].reshape(rows, -1) - b[0]).abs().max()) for a, b in zip(r_st, o_st))
+            worst = max(worst, d, ds)
+            assert torch.equal(r_lp.argmax(1), o_lp.argmax(1))
+            ref_lps.append(r_lp.numpy())
+            tok = r_lp.argmax(1)
+    print(f"[ensemble step hook, 3 models, 2 steps] oracle-vs-reference: max |log-prob / state diff| = {worst:.3g}")
+    assert worst <= 2e-6
+    import numpy as np
+    path = os.path.join(ROOT, "tests", "golden", "ensemble_step_case.npz")
+    np.savez_compressed(path, seeds=np.array(seeds), rows=rows, input_seed=9, logprobs=np.stack(ref_lps))
+    print("wrote", path)
+    return worst
+
+
 if __name__ == "__main__":
     main()
+    ensemble_step_case()

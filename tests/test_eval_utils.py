@@ -167,3 +167,32 @@ def test_ensemble_greedy_full_size_two_models():
         oseq, oslp = EO.ensemble_sample_greedy(sds, cfg, fc, att)
     assert seq.shape == oseq.shape and torch.equal(seq.cpu(), oseq)
     assert maxdiff(slp, oslp) <= LP_TOL
+
+
+@pytest.mark.gpu
+def test_ensemble_step_matches_reference_hook_fixture():
+    """ensemble.model_ensemble_feat_array_one_step (per-model one_time_step + rfn_mean_log_softmax_f32) against the log-probs the
+    REFERENCE's own hook (eval_utils.py:268-290) produced on three reference models, two consecutive greedy steps
+    (tests/golden/ensemble_step_case.npz, written by oracle/gen_golden_eval.py)."""
+    import os
+    from recurrent_fusion_network_b200.ensemble import model_ensemble_feat_array_one_step
+    from tests._gpu_util import LP_TOL, build_model, cuda_list, maxdiff
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "ensemble_step_case.npz"))
+    cfg = O.tiny_config(2)
+    sds = [O.make_state_dict(cfg, seed=int(s), init_range=0.5, logit_scale=3.0, eos_bias=0.8) for s in fx["seeds"]]
+    models = [build_model(cfg, sd) for sd in sds]
+    rows = int(fx["rows"])
+    fc, att = O.make_inputs(cfg, rows, seed=int(fx["input_seed"]))
+    with torch.no_grad():
+        tvs, sts = [], []
+        for m in models:
+            tv, _, st = m.get_thought_vectors(cuda_list(fc), cuda_list(att), m.get_init_state(cuda_list(fc)))
+            tvs.append(tv); sts.append(st)
+        tok = torch.zeros(rows, dtype=torch.int64, device="cuda")
+        for step in range(fx["logprobs"].shape[0]):
+            xts = [m.embed.weight[tok] for m in models]
+            _, sts, lp = model_ensemble_feat_array_one_step(models, xts, sts, tvs)
+            want = torch.from_numpy(fx["logprobs"][step])
+            assert maxdiff(lp, want) <= LP_TOL
+            assert torch.equal(lp.argmax(1).cpu(), want.argmax(1))
+            tok = lp.argmax(1)

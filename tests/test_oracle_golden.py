@@ -106,3 +106,30 @@ def test_eval_split_oracle_reproduces_reference_driver_fixture():
         loss, preds = EO.eval_split(sd, cfg, FakeLoader(cfg, c["n_images"], c["batch"], fx["seq_per_img"], seed=fx["loader_seed"]), kw)
         assert preds == c["predictions"], c
         assert abs(loss - c["loss"]) <= 2e-6 * max(1.0, abs(c["loss"])), (loss, c["loss"])
+
+
+def test_ensemble_step_oracle_reproduces_reference_hook_fixture():
+    """The ensemble step (per-model one_time_step, logit mean, log_softmax) against the output of the reference's own hook
+    model_ensemble_feat_array_one_step (eval_utils.py:268-290), run from its source text on three reference models by
+    oracle/gen_golden_eval.py: two consecutive greedy steps, log-probs within 2e-6 (measured difference: 0)."""
+    import os
+    import numpy as np
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "ensemble_step_case.npz"))
+    cfg = O.tiny_config(2)
+    sds = [O.make_state_dict(cfg, seed=int(s), init_range=0.5, logit_scale=3.0, eos_bias=0.8) for s in fx["seeds"]]
+    rows = int(fx["rows"])
+    fc, att = O.make_inputs(cfg, rows, seed=int(fx["input_seed"]))
+    with torch.no_grad():
+        tvs, sts = [], []
+        for sd in sds:
+            tv, _, st = O.get_thought_vectors(sd, cfg, att, O.get_init_state(sd, cfg, fc))
+            tvs.append(tv); sts.append(st)
+        tok = torch.zeros(rows, dtype=torch.int64)
+        for step in range(fx["logprobs"].shape[0]):
+            logits = []
+            for k, sd in enumerate(sds):
+                lg, sts[k] = O.one_time_step(sd, sd["embed.weight"][tok], tvs[k], sts[k])
+                logits.append(lg)
+            lp = torch.log_softmax(sum(logits) / len(sds), dim=1)
+            assert float((lp - torch.from_numpy(fx["logprobs"][step])).abs().max()) <= 2e-6
+            tok = lp.argmax(1)
