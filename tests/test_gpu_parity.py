@@ -110,6 +110,27 @@ def test_review_net_core_alias():
     assert maxdiff(og, ho) <= 2e-5 and maxdiff(cg[0], co) <= 2e-5
 
 
+def test_review_net_core_matches_reference_module_fixture():
+    """SURVEY 8(a) row a4 against the REFERENCE class itself: tests/golden/review_core_cases.npz holds the state_dict, inputs and
+    outputs of misc/LSTMSoftAttentionNoInputCore.py (oracle/gen_golden_cores.py: three chained steps, plain and maxout)."""
+    import os
+    import numpy as np
+    from recurrent_fusion_network_b200 import LSTMSoftAttentionNoInputCore
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "review_core_cases.npz"))
+    for name in fx["names"]:
+        R, D, N, A, maxout, rows = (int(v) for v in fx[f"{name}.dims"])
+        mod = LSTMSoftAttentionNoInputCore(R, D, N, A, 0.0, maxout)
+        mod.load_state_dict({k[len(name) + 4:]: torch.from_numpy(fx[k]) for k in fx.files if k.startswith(f"{name}.sd.")})
+        mod = mod.cuda().eval()
+        att = torch.from_numpy(fx[f"{name}.att"]).cuda()
+        state = (torch.from_numpy(fx[f"{name}.h0"]).cuda(), torch.from_numpy(fx[f"{name}.c0"]).cuda())
+        with torch.no_grad():
+            for step in range(fx[f"{name}.h"].shape[0]):
+                out, state = mod(att, None, None, state)
+                assert maxdiff(out, fx[f"{name}.h"][step]) <= 2e-5 and maxdiff(state[0][0], fx[f"{name}.h"][step]) <= 2e-5
+                assert maxdiff(state[1][0], fx[f"{name}.c"][step]) <= 2e-5
+
+
 # ---- path level vs the REAL reference's outputs (golden fixtures) -----------------------------------
 @pytest.fixture(params=[4, 1, 3, 0], ids=["tc_fp16x3", "tc3xtf32", "tc_tf32_bf16x", "simt"])
 def gemm_mode(request):

@@ -133,3 +133,23 @@ def test_ensemble_step_oracle_reproduces_reference_hook_fixture():
             lp = torch.log_softmax(sum(logits) / len(sds), dim=1)
             assert float((lp - torch.from_numpy(fx["logprobs"][step])).abs().max()) <= 2e-6
             tok = lp.argmax(1)
+
+
+def test_review_core_oracle_math_reproduces_reference_module_fixture():
+    """misc/LSTMSoftAttentionNoInputCore.py run by oracle/gen_golden_cores.py (the reference class itself, three
+    chained steps, plain and maxout).  The oracle's attention + cell composition with h2h(pre_h) must reproduce its outputs."""
+    import os
+    import numpy as np
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "review_core_cases.npz"))
+    for name in fx["names"]:
+        R, D, N, A, maxout, rows = (int(v) for v in fx[f"{name}.dims"])
+        sd = {"m." + k[len(name) + 4:]: torch.from_numpy(fx[k]) for k in fx.files if k.startswith(f"{name}.sd.")}
+        att = torch.from_numpy(fx[f"{name}.att"])
+        h, c = torch.from_numpy(fx[f"{name}.h0"])[0], torch.from_numpy(fx[f"{name}.c0"])[0]
+        for step in range(fx[f"{name}.h"].shape[0]):
+            z = O.attention(sd, "m", h, att)
+            G = torch.nn.functional.linear(h, sd["m.h2h.weight"], sd["m.h2h.bias"]) + \
+                torch.nn.functional.linear(z, sd["m.z2h.weight"], sd["m.z2h.bias"])
+            h, c = O.lstm_cell(G, c)          # (5R-wide G selects the maxout form)
+            assert float((h - torch.from_numpy(fx[f"{name}.h"][step])).abs().max()) <= 2e-6
+            assert float((c - torch.from_numpy(fx[f"{name}.c"][step])).abs().max()) <= 2e-6
