@@ -98,3 +98,28 @@ def test_self_critical_reward_end_to_end():
     greedy_p = torch.nn.functional.pad(greedy_o, (0, max(0, T - greedy_o.shape[1])))[:, :T]
     want, _ = CD.self_critical_reward(gen_o.numpy(), greedy_p.numpy(), gts, None, None, spi)
     assert got.shape == want.shape and np.abs(got - want).max() <= 1e-5
+
+
+def _reward_cases():
+    d = np.load(os.path.join(GOLDEN, "reward_cases.npz"))
+    for name in d["names"]:
+        n_img, spi, use_baseline = (int(v) for v in d[f"{name}.meta"])
+        gts = [[d[f"{name}.gts"][i, j] for j in range(int(d[f"{name}.n_refs"][i]))] for i in range(n_img)]
+        yield name, d[f"{name}.gen"], d[f"{name}.greedy"], gts, spi, bool(use_baseline), float(d[f"{name}.cider_weight"]), d[f"{name}.rewards"]
+
+
+def test_oracle_reward_assembly_matches_reference_compute_reward_fixture():
+    """get_rewards.py:39-112 compute_reward run from the reference's source text (oracle/gen_golden_reward.py): array_to_str, the
+    hypothesis / reference bookkeeping, sampled minus greedy (or sampled alone), the weight, the repeat along T."""
+    for name, gen, greedy, gts, spi, use_baseline, w, want in _reward_cases():
+        got, _ = CD.self_critical_reward(gen, greedy, gts, None, None, spi, cider_weight=w, use_baseline=use_baseline)
+        assert got.shape == want.shape and np.abs(got - want).max() <= 1e-12, name
+
+
+@pytest.mark.gpu
+def test_device_reward_matches_reference_compute_reward_fixture():
+    from recurrent_fusion_network_b200 import reward as RW
+    for name, gen, greedy, gts, spi, use_baseline, w, want in _reward_cases():
+        opt = SimpleNamespace(cider_weight=w, bleu4_weight=0, spice_weight=0, use_baseline=1 if use_baseline else 0)
+        rew, _ = RW.compute_reward(torch.from_numpy(gen).cuda(), torch.from_numpy(greedy).cuda(), gts, None, opt, seq_per_img=spi)
+        assert rew.shape == want.shape and np.abs(rew.cpu().numpy() - want).max() <= 1e-6, name
